@@ -1,0 +1,86 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (double precision, reference operation order) of StaticMapping's
+ * registrators/ hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product
+ * (staticmapping_b200/, libsm_b200.so) never does.
+ *
+ * PARITY UNPINNED: the reference ships no test, golden vector or fixture for
+ * registrators/ (README.md:203-206; builder/data/test/test_cloud_types.cc:158 is an
+ * empty stub) and cannot be compiled in this image (Eigen, PCL, libnabo, glog, Boost
+ * absent), so this restatement is checked only against analytic known-answer scenes,
+ * brute force and scipy's cKDTree (tests/test_oracle_*.py).
+ *
+ * All matrices crossing this API use Eigen's default layout: column-major.
+ * Clouds are 3xN column-major doubles (x0,y0,z0,x1,...), as Eigen::MatrixXd in
+ * data::EigenPointCloud (builder/data/cloud_types.h:143-146).
+ */
+#ifndef ORACLE_SM_ORACLE_H_
+#define ORACLE_SM_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* EigenPointCloud::CalculateNormals (builder/data/cloud_types.cc:347-368 with
+ * BuildNormals :105-144 and the leaf routine :73-103).  points_io: 3xN in, 3xM out
+ * (compacted in place like the reference); normals_out: 3xN capacity, 3xM written.
+ * tie_mode 0: total-order comparator (coord, index) and leaf representative =
+ * smallest original index (deterministic); tie_mode 1: literal std::nth_element with
+ * the reference's coordinate-only comparator and representative = indices[first].
+ * Returns M (number of surviving points). */
+int64_t sm_oracle_calculate_normals(double* points_io, double* normals_out, int64_t n,
+                                    int tie_mode);
+
+/* libnabo 1.0.7 KDTREE_LINEAR_HEAP restatement (external dependency pinned by
+ * setup/install_libnabo.sh:18; call sites registrators/icp_fast.cc:466-467, :177-178).
+ * k = 1, ALLOW_SELF_MATCH, maxRadius = inf.  dists2_out are SQUARED distances;
+ * ids_out = -1 / dists2 = +inf when nothing was found (NNS::InvalidIndex/Value).
+ * bucket_size: 8 for libnabo's default.  Returns 0 on success. */
+int sm_oracle_knn1(const double* target, int64_t n_target, const double* query,
+                   int64_t n_query, double epsilon, int bucket_size, int tie_mode,
+                   int32_t* ids_out, double* dists2_out);
+
+/* Exhaustive 1-NN (first minimum wins) — independent check for the two above. */
+int sm_oracle_knn1_brute(const double* target, int64_t n_target, const double* query,
+                         int64_t n_query, int32_t* ids_out, double* dists2_out);
+
+typedef struct sm_oracle_icp_options {
+  int32_t max_iteration;      /* icp_fast.h:58, default 100 */
+  float dist_outlier_ratio;   /* icp_fast.h:59, default 0.7f (a FLOAT on purpose) */
+  double knn_epsilon;         /* icp_fast.cc:174, 3.16 */
+  int32_t disable_convergence_check; /* throughput runs: fixed iteration count */
+  int32_t tie_mode;
+} sm_oracle_icp_options;
+
+typedef struct sm_oracle_icp_trace {   /* optional per-iteration record */
+  double T_iter[16];
+  double limit;
+  int64_t kept;
+  double A[36];
+  double b[6];
+} sm_oracle_icp_trace;
+
+/* IcpFast::Align (registrators/icp_fast.cc:455-529).  source: 3xNs, target 3xNt with
+ * unit normals 3xNt (the caller ran CalculateNormals, map_builder.cc:286,389).
+ * Returns 1 (Align always returns true) or a negative code where the reference would
+ * CHECK-fail: -1 empty input, -2 no finite match distance, -3 no point to minimise. */
+int sm_oracle_icp_fast_align(const double* source, int64_t n_source, const double* target,
+                             const double* target_normals, int64_t n_target,
+                             const double* guess, const sm_oracle_icp_options* opt,
+                             double* result, double* final_score, int32_t* iterations,
+                             sm_oracle_icp_trace* trace, int32_t trace_capacity);
+
+/* Pieces exposed for unit tests of the restatement itself. */
+int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
+int sm_oracle_quantile_index(int64_t n, float ratio);
+void sm_oracle_check_convergence_inputs(const double* Ts, int n, int* converged);
+
+int sm_oracle_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORACLE_SM_ORACLE_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of oracle/libsm_oracle.so — the CPU restatement used as the parity
+checker.  TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_DIR = os.path.join(_ROOT, "oracle")
+_SO = os.path.join(_DIR, "libsm_oracle.so")
+
+
+class IcpOptions(C.Structure):
+    _fields_ = [("max_iteration", C.c_int32), ("dist_outlier_ratio", C.c_float),
+                ("knn_epsilon", C.c_double), ("disable_convergence_check", C.c_int32),
+                ("tie_mode", C.c_int32)]
+
+
+class IcpTrace(C.Structure):
+    _fields_ = [("T_iter", C.c_double * 16), ("limit", C.c_double), ("kept", C.c_int64),
+                ("A", C.c_double * 36), ("b", C.c_double * 6)]
+
+
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(_DIR, f) for f in os.listdir(_DIR) if f.endswith((".cc", ".h"))]
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+        return
+    subprocess.check_call(["make", "-C", _DIR, "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        _lib.sm_oracle_calculate_normals.restype = C.c_int64
+        _lib.sm_oracle_calculate_normals.argtypes = [dp, dp, C.c_int64, C.c_int]
+        _lib.sm_oracle_knn1.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int,
+                                        C.c_int, ip, dp]
+        _lib.sm_oracle_knn1_brute.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, dp]
+        _lib.sm_oracle_icp_fast_align.argtypes = [
+            dp, C.c_int64, dp, dp, C.c_int64, dp, C.POINTER(IcpOptions), dp, dp, ip,
+            C.POINTER(IcpTrace), C.c_int32]
+        _lib.sm_oracle_solve6.argtypes = [dp, dp, dp, C.POINTER(C.c_int)]
+        _lib.sm_oracle_quantile_index.argtypes = [C.c_int64, C.c_float]
+        _lib.sm_oracle_check_convergence_inputs.argtypes = [dp, C.c_int, C.POINTER(C.c_int)]
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _cloud(a):
+    """(N,3) array-like -> C-contiguous (N,3) float64 == 3xN column-major."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    assert a.ndim == 2 and a.shape[1] == 3
+    return a
+
+
+def calculate_normals(points, tie_mode=0):
+    """EigenPointCloud::CalculateNormals -> (points_kept (M,3), normals (M,3))."""
+    p = _cloud(points).copy()
+    n = np.zeros_like(p)
+    m = lib().sm_oracle_calculate_normals(_d(p), _d(n), p.shape[0], tie_mode)
+    return p[:m].copy(), n[:m].copy()
+
+
+def knn1(target, query, epsilon=3.16, bucket_size=8, tie_mode=0):
+    t, q = _cloud(target), _cloud(query)
+    ids = np.empty(q.shape[0], dtype=np.int32)
+    d2 = np.empty(q.shape[0], dtype=np.float64)
+    rc = lib().sm_oracle_knn1(_d(t), t.shape[0], _d(q), q.shape[0], epsilon, bucket_size,
+                              tie_mode, _i(ids), _d(d2))
+    assert rc == 0
+    return ids, d2
+
+
+def knn1_brute(target, query):
+    t, q = _cloud(target), _cloud(query)
+    ids = np.empty(q.shape[0], dtype=np.int32)
+    d2 = np.empty(q.shape[0], dtype=np.float64)
+    lib().sm_oracle_knn1_brute(_d(t), t.shape[0], _d(q), q.shape[0], _i(ids), _d(d2))
+    return ids, d2
+
+
+def icp_fast_align(source, target, target_normals, guess=None, max_iteration=100,
+                   dist_outlier_ratio=0.7, knn_epsilon=3.16, disable_convergence_check=False,
+                   tie_mode=0, trace=False):
+    """IcpFast::Align.  Returns dict(result 4x4, score, iterations, rc[, trace])."""
+    s, t, n = _cloud(source), _cloud(target), _cloud(target_normals)
+    g = np.eye(4) if guess is None else np.asarray(guess, dtype=np.float64)
+    g_cm = np.ascontiguousarray(g.T).ravel()  # column-major
+    opt = IcpOptions(max_iteration, dist_outlier_ratio, knn_epsilon,
+                     int(disable_convergence_check), tie_mode)
+    res = np.zeros(16)
+    score = C.c_double(0.0)
+    iters = C.c_int32(0)
+    cap = max_iteration if trace else 0
+    tr = (IcpTrace * max(cap, 1))()
+    rc = lib().sm_oracle_icp_fast_align(_d(s), s.shape[0], _d(t), _d(n), t.shape[0], _d(g_cm),
+                                        C.byref(opt), _d(res), C.byref(score), C.byref(iters),
+                                        tr, cap)
+    out = {"rc": rc, "result": res.reshape(4, 4).T.copy(), "score": score.value,
+           "iterations": iters.value}
+    if trace:
+        out["trace"] = [
+            {"T_iter": np.array(tr[i].T_iter).reshape(4, 4).T.copy(), "limit": tr[i].limit,
+             "kept": tr[i].kept, "A": np.array(tr[i].A).reshape(6, 6),
+             "b": np.array(tr[i].b)} for i in range(iters.value)]
+    return out
+
+
+def solve6(A, b):
+    A = np.asarray(A, dtype=np.float64)
+    a_cm = np.ascontiguousarray(A.T).ravel()
+    bb = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+    x = np.zeros(6)
+    path = C.c_int(-1)
+    lib().sm_oracle_solve6(_d(a_cm), _d(bb), _d(x), C.byref(path))
+    return x, path.value
+
+
+def quantile_index(n, ratio=0.7):
+    return lib().sm_oracle_quantile_index(n, ratio)
+
+
+def num_threads():
+    return lib().sm_oracle_num_threads()
