@@ -1,0 +1,118 @@
+/* sm_b200.h — C ABI of libsm_b200.so, the B200-native scan-matching engine that stands in
+ * for StaticMapping's registrators/ hot path.
+ *
+ * Drop-in boundary: the reference has no FFI of its own (it is one C++ process); the
+ * interface a maintainer binds is registrator::Interface
+ * (/root/reference/registrators/interface.h:67-119).  Each entry point below names the
+ * reference member it replaces.  INTEGRATION.md shows the C++ adapter
+ * (adapter/registrators_b200.h) that maps these 1:1 onto that class.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; never throws across the ABI;
+ *   - 4x4 transforms are 16 doubles, COLUMN-major (Eigen::Matrix4d storage);
+ *   - clouds are 3xN column-major doubles (x0,y0,z0,x1,...) == Eigen::MatrixXd of
+ *     data::EigenPointCloud::points / ::normals (builder/data/cloud_types.h:143-146);
+ *   - return value: >= 0 success, < 0 error (sm_last_error gives the text).  Where the
+ *     reference would glog-CHECK-abort the C++ adapter turns the negative code into the
+ *     same CHECK failure (SURVEY.md section 5 "failure detection");
+ *   - one handle is used by one thread at a time; different handles may run concurrently
+ *     from different threads (map_builder.cc:655,706-708; loop_detector.cc:224-228).  Each
+ *     handle owns its CUDA stream and workspace.
+ */
+#ifndef SM_B200_H_
+#define SM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sm_handle sm_handle;
+
+/* registrator::Type (interface.h:41-50); values match the XML `type="N"` attribute. */
+enum sm_matcher_type {
+  SM_TYPE_ICP_PM = 1,
+  SM_TYPE_NDT_WITH_GICP = 3,
+  SM_TYPE_NDT = 5,
+  SM_TYPE_FAST_ICP = 6
+};
+
+enum sm_error {
+  SM_OK = 0,
+  SM_ERR_BAD_ARGUMENT = -1,
+  SM_ERR_NO_FINITE_MATCH = -2,   /* CHECK(!values.empty())            icp_fast.cc:81  */
+  SM_ERR_NOTHING_TO_MINIMIZE = -3, /* CHECK_GT(points_count, 0)        icp_fast.cc:114 */
+  SM_ERR_MISSING_INPUT = -4,     /* CHECK(cloud) / missing normals    icp_fast.cc:422-430 */
+  SM_ERR_UNKNOWN_OPTION = -10,   /* "Init an unknown option"          interface.cc:66-67 */
+  SM_ERR_UNSUPPORTED_TYPE = -11, /* CreateMatcher default branch      interface.cc:158-160 */
+  SM_ERR_NO_DEVICE = -20,        /* no CUDA device: the engine has no CPU fallback */
+  SM_ERR_CUDA = -100
+};
+
+/* CreateMatcher(options) (interface.cc:139-173) + the concrete constructors
+ * (IcpFast::IcpFast icp_fast.cc:407-419).  `device` is the CUDA ordinal. */
+int sm_create(int type, int device, sm_handle** out);
+int sm_destroy(sm_handle* h);
+
+/* Interface::InitWithXml (interface.cc:62-90): one <param name=...>text</param> entry.
+ * `text` is parsed like pugixml's as_int / as_float / as_bool for the registered type.
+ * Registered names, IcpFast (icp_fast.cc:411-418): knn_normal_estimate (int, unused),
+ * max_iteration (int, 100), dist_outlier_ratio (float, 0.7).  Added by this engine:
+ * knn_epsilon (float, 3.16 = icp_fast.cc:174), disable_convergence_check (bool, false;
+ * fixed-iteration throughput runs).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
+int sm_set_option(sm_handle* h, const char* name, const char* text);
+/* Interface::PrintOptions (interface.cc:115-137): writes "name -> value\n" lines. */
+int sm_print_options(sm_handle* h, char* buf, int64_t buf_len);
+/* Interface::GetType (interface.h:106). */
+int sm_get_type(const sm_handle* h);
+
+/* IcpFast::SetInputSource / SetInputTarget (icp_fast.cc:421-431): deep copy into the
+ * engine (host pointers are not retained).  The target must carry unit normals
+ * (CHECK(HasNormals()), icp_fast.cc:430) — the caller computed them with
+ * EigenPointCloud::CalculateNormals (map_builder.cc:286,389) or sm_calculate_normals. */
+int sm_set_input_source(sm_handle* h, const double* points_3xn, int64_t n);
+int sm_set_input_target(sm_handle* h, const double* points_3xn, const double* normals_3xn,
+                        int64_t n);
+/* Same, for clouds already resident in this device's memory (same layout). */
+int sm_set_input_source_device(sm_handle* h, const double* dev_points_3xn, int64_t n);
+int sm_set_input_target_device(sm_handle* h, const double* dev_points_3xn,
+                               const double* dev_normals_3xn, int64_t n);
+
+/* Interface::Align(const Matrix4d& guess, Matrix4d& result) (interface.h:103-104;
+ * IcpFast::Align icp_fast.cc:455-529).  Returns 1 (true) / 0 (false) like the
+ * reference's bool, or a negative sm_error. */
+int sm_align(sm_handle* h, const double* guess_4x4, double* result_4x4);
+/* Interface::GetFitnessScore (interface.h:100). */
+double sm_get_fitness_score(const sm_handle* h);
+
+typedef struct sm_align_info {
+  int32_t iterations;      /* ICP iterations executed */
+  int32_t status;          /* 0 or sm_error */
+  int32_t solve_path;      /* last 6x6 solve: 0 Cholesky, 1 rank-reduced, 2 SVD */
+  int32_t reserved;
+  int64_t kept;            /* matches kept by the 70 % trim in the last iteration */
+  double limit;            /* its squared-distance limit */
+  float ms_upload;         /* device time of the last SetInput* copies */
+  float ms_prologue;       /* centre + tree build + G0 (icp_fast.cc:456-480) */
+  float ms_iterations;     /* all ICP iterations */
+  int32_t kernel_launches; /* kernels launched by the last sm_align */
+} sm_align_info;
+int sm_get_align_info(const sm_handle* h, sm_align_info* out);
+
+const char* sm_last_error(const sm_handle* h);
+
+/* ---- building blocks exposed for parity tests and for callers that hold clouds ------- */
+
+/* libnabo-compatible tree build + 1-NN (NNS::create + knn, icp_fast.cc:466-467,177-178).
+ * ids: original target column, -1 if none; dists2: squared distances. */
+int sm_knn1(int device, const double* target_3xn, int64_t n_target, const double* query_3xn,
+            int64_t n_query, double epsilon, int bucket_size, int32_t* ids, double* dists2);
+
+int sm_device_count(void);
+const char* sm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SM_B200_H_ */

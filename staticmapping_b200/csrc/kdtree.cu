@@ -1,0 +1,308 @@
+// GPU builder for the libnabo-compatible k-d tree (KDTREE_LINEAR_HEAP semantics:
+// implicit-bounds widest-axis median split, leftCount = n - n/2, bucket size 8;
+// call site registrators/icp_fast.cc:466-467) and, with bucket 7, for the leaf
+// partition of EigenPointCloud::CalculateNormals (builder/data/cloud_types.cc:105-144).
+//
+// B200-first formulation instead of the reference's recursive std::nth_element:
+//   * the tree SHAPE depends only on (N, bucket): every node's [first, first+count) is
+//     pure integer arithmetic, so nodes live in an implicit heap layout (children of h
+//     are 2h+1 / 2h+2) and nothing about the shape is stored or communicated;
+//   * the three per-axis orderings are radix-sorted once; each level then needs only the
+//     median (an array lookup) and a stable partition of the three lists, done for ALL
+//     nodes of the level at once with a flag + prefix-scan + scatter;
+//   * ties are broken by the total order (coordinate, original index).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+namespace {
+
+struct Seg {
+  int first, count;
+  bool exists;
+};
+
+// node j of level L -> its segment; exists == false when an ancestor was already a leaf.
+__device__ __forceinline__ Seg locate_node(int j, int L, int n, int bucket) {
+  int first = 0, count = n;
+  for (int l = L - 1; l >= 0; --l) {
+    if (count <= bucket) return Seg{first, count, false};
+    const int right = count >> 1, left = count - right;
+    if ((j >> l) & 1) { first += left; count = right; } else { count = left; }
+  }
+  return Seg{first, count, true};
+}
+
+// position i -> the level-L node containing it (or the shallower leaf that does).
+// Returns true when the node is an INNER node of level L (i.e. it will be split now).
+__device__ __forceinline__ bool locate_pos(int i, int L, int n, int bucket, int* j_out,
+                                           int* first_out, int* count_out) {
+  int first = 0, count = n, j = 0;
+  for (int l = 0; l < L; ++l) {
+    if (count <= bucket) { *j_out = j; *first_out = first; *count_out = count; return false; }
+    const int right = count >> 1, left = count - right;
+    if (i < first + left) { j = 2 * j; count = left; }
+    else { j = 2 * j + 1; first += left; count = right; }
+  }
+  *j_out = j; *first_out = first; *count_out = count;
+  return count > bucket;
+}
+
+__device__ __forceinline__ int argmax3(double ex, double ey, double ez) {
+  // cloud_types.cc:41-56 / libnabo argMax: first strictly-greater-than wins, from 0.
+  double mv = 0.0; int mi = 0;
+  if (ex > mv) { mv = ex; mi = 0; }
+  if (ey > mv) { mv = ey; mi = 1; }
+  if (ez > mv) { mv = ez; mi = 2; }
+  return mi;
+}
+
+// ---- per level: node kernel -----------------------------------------------------------
+__global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride,
+                               const uint32_t* __restrict__ lists, int64_t lstride, int n,
+                               int bucket, int L, const double* __restrict__ bounds_in,
+                               double* __restrict__ bounds_out, int* __restrict__ level_dim,
+                               KdNode* __restrict__ nodes) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (1 << L)) return;
+  const Seg s = locate_node(j, L, n, bucket);
+  if (!s.exists) return;
+  const int h = (1 << L) - 1 + j;
+  if (s.count <= bucket) {
+    KdNode leaf;
+    leaf.cut = __longlong_as_double(((long long)s.count << 32) | (long long)(unsigned)s.first);
+    leaf.dim = 3; leaf.pad = 0;
+    nodes[h] = leaf;
+    level_dim[j] = 3;
+    return;
+  }
+  double mn[3], mx[3];
+  if (L == 0) {
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = coord[d * cstride + lists[d * lstride + 0]];
+      mx[d] = coord[d * cstride + lists[d * lstride + (n - 1)]];
+    }
+  } else {
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = bounds_in[(int64_t)j * 6 + d];
+      mx[d] = bounds_in[(int64_t)j * 6 + 3 + d];
+    }
+  }
+  const int dim = argmax3(dsub(mx[0], mn[0]), dsub(mx[1], mn[1]), dsub(mx[2], mn[2]));
+  const int left = s.count - (s.count >> 1);
+  const uint32_t pid = lists[dim * lstride + s.first + left];
+  const double cut = coord[dim * cstride + pid];
+  KdNode nd; nd.cut = cut; nd.dim = dim; nd.pad = 0;
+  nodes[h] = nd;
+  level_dim[j] = dim;
+  double* bl = bounds_out + (int64_t)(2 * j) * 6;
+  double* br = bounds_out + (int64_t)(2 * j + 1) * 6;
+  for (int d = 0; d < 3; ++d) {
+    bl[d] = mn[d]; bl[3 + d] = (d == dim) ? cut : mx[d];
+    br[d] = (d == dim) ? cut : mn[d]; br[3 + d] = mx[d];
+  }
+}
+
+// ---- per level: side flag per point ----------------------------------------------------
+__global__ void kd_flag_kernel(const uint32_t* __restrict__ lists, int64_t lstride, int n,
+                               int bucket, int L, const int* __restrict__ level_dim,
+                               uint8_t* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j, first, count;
+  if (!locate_pos(i, L, n, bucket, &j, &first, &count)) return;
+  const int dim = level_dim[j];
+  const int left = count - (count >> 1);
+  const uint32_t pid = lists[dim * lstride + i];
+  flag[pid] = (i - first >= left) ? 1 : 0;
+}
+
+// ---- per level: stable partition of the three lists -------------------------------------
+constexpr int kPartThreads = 256;
+constexpr int kPartItems = 8;
+constexpr int kPartTile = kPartThreads * kPartItems;
+
+__global__ void __launch_bounds__(kPartThreads)
+kd_part_count_kernel(const uint32_t* __restrict__ lists, int64_t lstride, int n, int bucket,
+                     int L, const uint8_t* __restrict__ flag, uint32_t* __restrict__ gloc,
+                     uint32_t* __restrict__ block_sum, int nblk) {
+  __shared__ uint32_t warp_sums[kPartThreads / 32];
+  const int d = blockIdx.y;
+  const uint32_t* list = lists + d * lstride;
+  const int base = blockIdx.x * kPartTile + threadIdx.x * kPartItems;
+  uint32_t isleft[kPartItems];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int r = 0; r < kPartItems; ++r) {
+    const int i = base + r;
+    uint32_t f = 0;
+    if (i < n) {
+      int j, first, count;
+      const bool inner = locate_pos(i, L, n, bucket, &j, &first, &count);
+      f = inner ? (flag[list[i]] == 0) : 1u;
+    }
+    isleft[r] = f;
+    cnt += f;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kPartThreads / 32; ++ww) {
+    const uint32_t v = warp_sums[ww];
+    if (ww < w) wbase += v;
+    total += v;
+  }
+  uint32_t run = wbase + incl - cnt;
+#pragma unroll
+  for (int r = 0; r < kPartItems; ++r) {
+    const int i = base + r;
+    if (i < n) gloc[d * lstride + i] = run;
+    run += isleft[r];
+  }
+  if (threadIdx.x == 0) block_sum[d * nblk + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kPartThreads)
+kd_part_scatter_kernel(const uint32_t* __restrict__ lists, uint32_t* __restrict__ lists_out,
+                       int64_t lstride, int n, int bucket, int L,
+                       const uint8_t* __restrict__ flag, const uint32_t* __restrict__ gloc,
+                       const uint32_t* __restrict__ block_off, int nblk) {
+  const int d = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* list = lists + d * lstride;
+  const uint32_t pid = list[i];
+  int j, first, count;
+  const bool inner = locate_pos(i, L, n, bucket, &j, &first, &count);
+  int pos = i;
+  if (inner) {
+    const uint32_t gi = gloc[d * lstride + i] + block_off[d * nblk + i / kPartTile];
+    const uint32_t gs = gloc[d * lstride + first] + block_off[d * nblk + first / kPartTile];
+    const int rank_left = (int)(gi - gs);
+    const int left = count - (count >> 1);
+    pos = (flag[pid] == 0) ? first + rank_left : first + left + ((i - first) - rank_left);
+  }
+  lists_out[d * lstride + pos] = pid;
+}
+
+// ---- leaves: canonical (ascending original index) order ---------------------------------
+__global__ void kd_leaf_kernel(const uint32_t* __restrict__ list0, int n, int bucket, int levels,
+                               KdNode* __restrict__ nodes, uint32_t* __restrict__ leaf_order) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = (1 << (levels + 1)) - 1;
+  if (h >= total) return;
+  const int L = 31 - __clz(h + 1);
+  const int j = h + 1 - (1 << L);
+  const Seg s = locate_node(j, L, n, bucket);
+  if (!s.exists || s.count > bucket) return;
+  KdNode leaf;
+  leaf.cut = __longlong_as_double(((long long)s.count << 32) | (long long)(unsigned)s.first);
+  leaf.dim = 3; leaf.pad = 0;
+  nodes[h] = leaf;
+  uint32_t ids[16];
+  for (int k = 0; k < s.count; ++k) ids[k] = list0[s.first + k];
+  for (int a = 1; a < s.count; ++a) {  // insertion sort, count <= bucket <= 16
+    const uint32_t v = ids[a];
+    int b = a - 1;
+    while (b >= 0 && ids[b] > v) { ids[b + 1] = ids[b]; --b; }
+    ids[b + 1] = v;
+  }
+  for (int k = 0; k < s.count; ++k) leaf_order[s.first + k] = ids[k];
+}
+
+__global__ void kd_keys_kernel(const double* __restrict__ coord, int64_t cstride, int n,
+                               uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                               int64_t lstride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    keys[d * lstride + i] = sortable_key(coord[d * cstride + i]);
+    vals[d * lstride + i] = (uint32_t)i;
+  }
+}
+
+}  // namespace
+
+int kd_num_levels(int n, int bucket) {
+  int L = 0;
+  int64_t c = n;
+  while (c > bucket) { c = (c + 1) / 2; ++L; }  // ceil halving: largest node of the level
+  return L;  // all nodes of level L are leaves; heap has 2^(L+1)-1 slots
+}
+
+size_t KdWorkspace::bytes_needed(int n, int bucket) {
+  const int levels = kd_num_levels(n, bucket);
+  const int64_t ls = (n + 63) & ~63;
+  size_t b = 0;
+  b += 2 * 3 * ls * sizeof(uint64_t);                // keys ping-pong
+  b += 2 * 3 * ls * sizeof(uint32_t);                // lists ping-pong
+  b += 3 * ls * sizeof(uint32_t);                    // gloc
+  b += ls;                                           // flag
+  b += radix_sort_scratch_bytes(n, 3) + 256;         // sort scratch / block sums
+  b += 2 * ((size_t)1 << levels) * 6 * sizeof(double);  // bounds ping-pong
+  b += ((size_t)1 << levels) * sizeof(int);          // level dims
+  return b + 4096;
+}
+
+void KdWorkspace::carve(void* base, int n, int bucket) {
+  const int levels = kd_num_levels(n, bucket);
+  lstride = (n + 63) & ~63;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+  keys[0] = (uint64_t*)take(3 * lstride * sizeof(uint64_t));
+  keys[1] = (uint64_t*)take(3 * lstride * sizeof(uint64_t));
+  lists[0] = (uint32_t*)take(3 * lstride * sizeof(uint32_t));
+  lists[1] = (uint32_t*)take(3 * lstride * sizeof(uint32_t));
+  gloc = (uint32_t*)take(3 * lstride * sizeof(uint32_t));
+  flag = (uint8_t*)take(lstride);
+  scratch = (uint32_t*)take(radix_sort_scratch_bytes(n, 3) + 256);
+  bounds[0] = (double*)take(((size_t)1 << levels) * 6 * sizeof(double));
+  bounds[1] = (double*)take(((size_t)1 << levels) * 6 * sizeof(double));
+  level_dim = (int*)take(((size_t)1 << levels) * sizeof(int));
+}
+
+// coord: SoA [3][cstride] doubles (already centred).  Writes nodes (heap layout,
+// 2^(levels+1)-1 entries) and leaf_order[n] (point ids in bucket order).
+int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
+             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream) {
+  if (n <= 0) return -1;
+  const int levels = kd_num_levels(n, bucket);
+  const int64_t ls = ws.lstride;
+  kd_keys_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(coord, cstride, n, ws.keys[0],
+                                                       ws.lists[0], ls);
+  int rc = radix_sort_pairs_u64(ws.keys[0], ws.lists[0], ws.keys[1], ws.lists[1], n, 3, ls,
+                                ws.scratch, stream);
+  if (rc) return rc;
+  int cur = 0;
+  const int nblk = ceil_div(n, kPartTile);
+  for (int L = 0; L < levels; ++L) {
+    const int nodes_l = 1 << L;
+    kd_node_kernel<<<ceil_div(nodes_l, 128), 128, 0, stream>>>(
+        coord, cstride, ws.lists[cur], ls, n, bucket, L, ws.bounds[L & 1], ws.bounds[(L + 1) & 1],
+        ws.level_dim, nodes);
+    kd_flag_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(ws.lists[cur], ls, n, bucket, L,
+                                                        ws.level_dim, ws.flag);
+    kd_part_count_kernel<<<dim3(nblk, 3), kPartThreads, 0, stream>>>(
+        ws.lists[cur], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
+    radix_scan_kernel_launch(ws.scratch, nblk, 3, stream);
+    kd_part_scatter_kernel<<<dim3(ceil_div(n, kPartThreads), 3), kPartThreads, 0, stream>>>(
+        ws.lists[cur], ws.lists[cur ^ 1], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
+    cur ^= 1;
+  }
+  const int total = (1 << (levels + 1)) - 1;
+  kd_leaf_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(ws.lists[cur], n, bucket, levels,
+                                                          nodes, leaf_order);
+  SMB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace smb

@@ -1,0 +1,107 @@
+// Internal host-side launch API shared by the .cu translation units of libsm_b200.
+#ifndef SM_B200_KERNELS_H_
+#define SM_B200_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace smb {
+
+// ---- radix_sort.cu ---------------------------------------------------------------------
+size_t radix_sort_scratch_bytes(int n, int batch);
+int radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
+                         int n, int batch, int64_t stride, uint32_t* scratch,
+                         cudaStream_t stream);
+// exclusive scan of `count` u32 per batch (in place), one block per batch
+void radix_scan_kernel_launch(uint32_t* data, int count, int batch, cudaStream_t stream);
+
+// ---- kdtree.cu -------------------------------------------------------------------------
+int kd_num_levels(int n, int bucket);
+struct KdWorkspace {
+  uint64_t* keys[2];
+  uint32_t* lists[2];
+  uint32_t* gloc;
+  uint8_t* flag;
+  uint32_t* scratch;
+  double* bounds[2];
+  int* level_dim;
+  int64_t lstride;
+  static size_t bytes_needed(int n, int bucket);
+  void carve(void* base, int n, int bucket);
+};
+int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
+             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream);
+
+// ---- icp.cu ----------------------------------------------------------------------------
+constexpr int kHistBins = 2048;
+
+// Device-resident state of one IcpFast::Align call (one per handle).
+struct IcpState {
+  double T_iter[16];      // column-major, accumulated iteration transform
+  double G0[16];          // T_mean^-1 * guess
+  double T_mean[16];
+  double result[16];
+  double mean[3];
+  double final_score;
+  double quat_hist[5][4]; // ring of the last 5 rotations (w,x,y,z)
+  double trans_hist[5][3];
+  double limit;           // last quantile limit (debug / parity)
+  long long kept;         // last K
+  int hist_len;           // number of entries pushed (incl. the initial identity)
+  int iteration;
+  int done;               // 1 once converged or max_iteration reached
+  int status;             // 0 ok, <0 error (-2 no finite distance, -3 nothing kept)
+  int solve_path;         // 0 LLT, 1 min-norm, 2 SVD (last iteration)
+};
+
+struct IcpParams {
+  int n_source, n_target;
+  int max_iteration;
+  float dist_outlier_ratio;
+  double max_error2;       // (1+eps)^2
+  int disable_convergence;
+};
+
+struct IcpBuffers {
+  // target (caller order, SoA, centred in place by the prologue)
+  double* tgt;            // [3][tstride]
+  double* tgt_raw;        // [3][tstride] as uploaded (un-centred)
+  double* nrm;            // [3][tstride]
+  int64_t tstride;
+  // tree
+  KdNode* nodes;
+  uint32_t* leaf_order;
+  BucketPoint* bpts;
+  BucketNormal* bnrm;
+  // source
+  double* src_raw;        // [3][sstride] as uploaded
+  double* src0;           // [3][sstride] after G0
+  int64_t sstride;
+  // per-iteration
+  int32_t* slot;          // [n_source] bucket slot of the match
+  double* d2;             // [n_source]
+  uint32_t* hist;         // [kHistBins]
+  uint32_t* cand_idx;     // [n_source] per-block compacted candidates
+  uint32_t* cand_cnt;     // [accum blocks]
+  double* partials;       // [accum blocks][32]
+  double* mean_partials;  // [blocks][4]
+  IcpState* state;
+};
+
+int icp_accum_blocks(int n_source);
+int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_dev,
+                 KdWorkspace& ws, cudaStream_t stream);
+int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
+                           cudaStream_t stream);
+// stand-alone k-NN over an already built tree (parity tests): ids = original indices
+int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
+              int nq, double max_error2, int32_t* ids, double* d2, cudaStream_t stream);
+int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
+                    const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
+                    cudaStream_t stream);
+
+}  // namespace smb
+
+#endif  // SM_B200_KERNELS_H_

@@ -1,0 +1,420 @@
+// C ABI of libsm_b200.so (include/sm_b200.h): handles, option registry, uploads, Align.
+#include "../../include/sm_b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+static thread_local std::string g_cuda_error;
+void set_cuda_error(cudaError_t e, const char* expr, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e),
+           file, line, expr);
+  g_cuda_error = buf;
+}
+const char* last_cuda_error() { return g_cuda_error.c_str(); }
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) { SMB_CUDA_OK(cudaFree(p)); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 8 + 4096;
+    SMB_CUDA_OK(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+__global__ void deinterleave3_kernel(const double* __restrict__ aos, double* __restrict__ soa,
+                                     int64_t stride, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  soa[i] = aos[3 * (int64_t)i];
+  soa[stride + i] = aos[3 * (int64_t)i + 1];
+  soa[2 * stride + i] = aos[3 * (int64_t)i + 2];
+}
+
+enum OptKind { kOptInt, kOptFloat, kOptBool };
+struct OptionDef { const char* name; OptKind kind; size_t offset; };
+
+struct IcpOptions {
+  int32_t knn_for_normal_estimate = 7;   // icp_fast.h:57
+  int32_t max_iteration = 100;           // icp_fast.h:58
+  float dist_outlier_ratio = 0.7f;       // icp_fast.h:59
+  float knn_epsilon = 3.16f;             // icp_fast.cc:174 (engine option; same default)
+  bool disable_convergence_check = false;
+};
+
+}  // namespace
+}  // namespace smb
+
+using namespace smb;
+
+struct sm_handle {
+  int type = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string error;
+  IcpOptions icp;
+  double final_score = 0.0;
+  sm_align_info info;
+  // device memory
+  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, nodes, leaf_order, bpts, bnrm, slot, d2, hist,
+      cand_idx, cand_cnt, partials, mean_partials, state, guess, kdws;
+  int64_t n_source = 0, n_target = 0, sstride = 0, tstride = 0;
+  bool has_source = false, has_target = false;
+  float ms_upload = 0.f;
+  IcpState* host_state = nullptr;  // pinned
+};
+
+namespace {
+
+const OptionDef kIcpOptions[] = {
+    {"knn_normal_estimate", kOptInt, offsetof(IcpOptions, knn_for_normal_estimate)},
+    {"max_iteration", kOptInt, offsetof(IcpOptions, max_iteration)},
+    {"dist_outlier_ratio", kOptFloat, offsetof(IcpOptions, dist_outlier_ratio)},
+    {"knn_epsilon", kOptFloat, offsetof(IcpOptions, knn_epsilon)},
+    {"disable_convergence_check", kOptBool, offsetof(IcpOptions, disable_convergence_check)},
+};
+
+int fail(sm_handle* h, int code, const std::string& msg) {
+  if (h) h->error = msg;
+  return code;
+}
+int cuda_fail(sm_handle* h) { return fail(h, SM_ERR_CUDA, last_cuda_error()); }
+
+#define H_CUDA(expr)                                                   \
+  do {                                                                 \
+    cudaError_t _e = (expr);                                           \
+    if (_e != cudaSuccess) {                                           \
+      set_cuda_error(_e, #expr, __FILE__, __LINE__);                   \
+      return cuda_fail(h);                                             \
+    }                                                                  \
+  } while (0)
+#define H_RC(expr)                                                     \
+  do {                                                                 \
+    int _rc = (expr);                                                  \
+    if (_rc == -100) return cuda_fail(h);                              \
+    if (_rc < 0) return fail(h, _rc, #expr " failed");                 \
+  } while (0)
+
+int64_t pad64(int64_t n) { return (n + 63) & ~(int64_t)63; }
+
+// upload (or adopt) an AoS 3xN cloud and de-interleave it into SoA [3][stride]
+int load_cloud(sm_handle* h, const double* pts, int64_t n, bool on_device, DevBuf& soa,
+               int64_t stride) {
+  H_RC(soa.reserve((size_t)(3 * stride) * sizeof(double)));
+  const double* src = pts;
+  if (!on_device) {
+    H_RC(h->stage.reserve((size_t)(3 * n) * sizeof(double)));
+    H_CUDA(cudaMemcpyAsync(h->stage.p, pts, (size_t)(3 * n) * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+    src = (const double*)h->stage.p;
+  }
+  deinterleave3_kernel<<<ceil_div(n, 256), 256, 0, h->stream>>>(src, (double*)soa.p, stride, (int)n);
+  H_CUDA(cudaGetLastError());
+  if (!on_device) H_CUDA(cudaStreamSynchronize(h->stream));  // stage buffer is reused
+  return 0;
+}
+
+int set_source(sm_handle* h, const double* pts, int64_t n, bool on_device) {
+  if (!h) return SM_ERR_BAD_ARGUMENT;
+  if (!pts || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInputSource: empty cloud");
+  if (n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInputSource: too many points");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  h->sstride = pad64(n);
+  H_RC(load_cloud(h, pts, n, on_device, h->src_raw, h->sstride));
+  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  H_CUDA(cudaEventSynchronize(h->ev[1]));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->ms_upload = ms;
+  h->n_source = n;
+  h->has_source = true;
+  return 0;
+}
+
+int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bool on_device) {
+  if (!h) return SM_ERR_BAD_ARGUMENT;
+  if (!pts || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInputTarget: empty cloud");
+  if (h->type == SM_TYPE_FAST_ICP && !nrm)
+    return fail(h, SM_ERR_MISSING_INPUT, "SetInputTarget: IcpFast target needs normals");
+  if (n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInputTarget: too many points");
+  H_CUDA(cudaSetDevice(h->device));
+  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  h->tstride = pad64(n);
+  H_RC(load_cloud(h, pts, n, on_device, h->tgt_raw, h->tstride));
+  if (nrm) H_RC(load_cloud(h, nrm, n, on_device, h->nrm, h->tstride));
+  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  H_CUDA(cudaEventSynchronize(h->ev[1]));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->ms_upload += ms;
+  h->n_target = n;
+  h->has_target = true;
+  return 0;
+}
+
+int icp_align(sm_handle* h, const double* guess, double* result) {
+  if (!h->has_source || !h->has_target)
+    return fail(h, SM_ERR_MISSING_INPUT, "Align: source/target not set");
+  const int ns = (int)h->n_source, nt = (int)h->n_target;
+  const int levels = kd_num_levels(nt, 8);
+  const int nb = icp_accum_blocks(ns);
+  H_RC(h->tgt.reserve((size_t)(3 * h->tstride) * sizeof(double)));
+  H_RC(h->src0.reserve((size_t)(3 * h->sstride) * sizeof(double)));
+  H_RC(h->nodes.reserve((((size_t)1 << (levels + 1))) * sizeof(KdNode)));
+  H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
+  H_RC(h->bpts.reserve((size_t)nt * sizeof(BucketPoint)));
+  H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
+  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t)));
+  H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
+  H_RC(h->hist.reserve(kHistBins * sizeof(uint32_t)));
+  H_RC(h->cand_idx.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(uint32_t)));
+  H_RC(h->cand_cnt.reserve((size_t)nb * sizeof(uint32_t)));
+  H_RC(h->partials.reserve((size_t)nb * 32 * sizeof(double)));
+  H_RC(h->mean_partials.reserve((size_t)ceil_div(nt, 1024) * 4 * sizeof(double)));
+  H_RC(h->state.reserve(sizeof(IcpState)));
+  H_RC(h->guess.reserve(16 * sizeof(double)));
+  H_RC(h->kdws.reserve(KdWorkspace::bytes_needed(nt, 8)));
+  KdWorkspace ws;
+  ws.carve(h->kdws.p, nt, 8);
+
+  IcpBuffers b;
+  b.tgt = (double*)h->tgt.p; b.tgt_raw = (double*)h->tgt_raw.p; b.nrm = (double*)h->nrm.p;
+  b.tstride = h->tstride;
+  b.nodes = (KdNode*)h->nodes.p; b.leaf_order = (uint32_t*)h->leaf_order.p;
+  b.bpts = (BucketPoint*)h->bpts.p; b.bnrm = (BucketNormal*)h->bnrm.p;
+  b.src_raw = (double*)h->src_raw.p; b.src0 = (double*)h->src0.p; b.sstride = h->sstride;
+  b.slot = (int32_t*)h->slot.p; b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
+  b.cand_idx = (uint32_t*)h->cand_idx.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
+  b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
+  b.state = (IcpState*)h->state.p;
+  IcpParams p;
+  p.n_source = ns; p.n_target = nt;
+  p.max_iteration = h->icp.max_iteration;
+  p.dist_outlier_ratio = h->icp.dist_outlier_ratio;
+  const double eps = (double)h->icp.knn_epsilon;
+  p.max_error2 = (1.0 + eps) * (1.0 + eps);
+  p.disable_convergence = h->icp.disable_convergence_check ? 1 : 0;
+
+  H_CUDA(cudaMemcpyAsync(h->guess.p, guess, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  H_RC(icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream));
+  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  int launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2;
+  int enqueued = 0;
+  const int max_it = p.max_iteration > 0 ? p.max_iteration : 1;
+  while (true) {
+    const int chunk = p.disable_convergence ? (max_it - enqueued)
+                                            : ((max_it - enqueued) < 8 ? (max_it - enqueued) : 8);
+    H_RC(icp_enqueue_iterations(b, p, chunk, h->stream));
+    enqueued += chunk;
+    launches += 3 * chunk;
+    H_CUDA(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost,
+                           h->stream));
+    H_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->host_state->done || enqueued >= max_it) break;
+  }
+  H_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  H_CUDA(cudaEventSynchronize(h->ev[2]));
+  const IcpState& st = *h->host_state;
+  h->info.iterations = st.iteration;
+  h->info.status = st.status;
+  h->info.solve_path = st.solve_path;
+  h->info.kept = st.kept;
+  h->info.limit = st.limit;
+  h->info.ms_upload = h->ms_upload;
+  cudaEventElapsedTime(&h->info.ms_prologue, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->info.ms_iterations, h->ev[1], h->ev[2]);
+  h->info.kernel_launches = launches;
+  h->ms_upload = 0.f;
+  if (st.status < 0)
+    return fail(h, st.status, st.status == -2 ? "Align: no finite match distance (icp_fast.cc:81)"
+                                              : "Align: no point to minimize (icp_fast.cc:114)");
+  memcpy(result, st.result, 16 * sizeof(double));
+  h->final_score = st.final_score;
+  return 1;  // IcpFast::Align always returns true (icp_fast.cc:528)
+}
+
+}  // namespace
+
+extern "C" {
+
+int sm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* sm_version(void) { return "sm_b200 0.1 (sm_100a)"; }
+
+int sm_create(int type, int device, sm_handle** out) {
+  if (!out) return SM_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  if (type != SM_TYPE_FAST_ICP) return SM_ERR_UNSUPPORTED_TYPE;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return SM_ERR_BAD_ARGUMENT;
+  sm_handle* h = new sm_handle();
+  h->type = type;
+  h->device = device;
+  memset(&h->info, 0, sizeof(h->info));
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess) {
+    delete h;
+    return SM_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return SM_OK;
+}
+
+int sm_destroy(sm_handle* h) {
+  if (!h) return SM_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->nodes,
+                    &h->leaf_order, &h->bpts, &h->bnrm, &h->slot, &h->d2, &h->hist, &h->cand_idx,
+                    &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->host_state) cudaFreeHost(h->host_state);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SM_OK;
+}
+
+int sm_get_type(const sm_handle* h) { return h ? h->type : 0; }
+
+int sm_set_option(sm_handle* h, const char* name, const char* text) {
+  if (!h || !name || !text) return SM_ERR_BAD_ARGUMENT;
+  for (const OptionDef& d : kIcpOptions) {
+    if (strcmp(d.name, name) != 0) continue;
+    char* base = reinterpret_cast<char*>(&h->icp) + d.offset;
+    switch (d.kind) {
+      case kOptInt: *reinterpret_cast<int32_t*>(base) = (int32_t)strtol(text, nullptr, 10); break;
+      case kOptFloat: *reinterpret_cast<float*>(base) = strtof(text, nullptr); break;
+      case kOptBool: {
+        // pugixml as_bool: first char in "1tTyY" -> true
+        const char* p = text;
+        while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+        *reinterpret_cast<bool*>(base) = (*p == '1' || *p == 't' || *p == 'T' || *p == 'y' || *p == 'Y');
+        break;
+      }
+    }
+    return SM_OK;
+  }
+  return fail(h, SM_ERR_UNKNOWN_OPTION, std::string("Init an unknown option of this matcher! ") + name);
+}
+
+int sm_print_options(sm_handle* h, char* buf, int64_t buf_len) {
+  if (!h || !buf || buf_len <= 0) return SM_ERR_BAD_ARGUMENT;
+  std::string out;
+  char line[128];
+  for (const OptionDef& d : kIcpOptions) {
+    const char* base = reinterpret_cast<const char*>(&h->icp) + d.offset;
+    switch (d.kind) {
+      case kOptInt: snprintf(line, sizeof(line), "%25s -> %d\n", d.name, *reinterpret_cast<const int32_t*>(base)); break;
+      case kOptFloat: snprintf(line, sizeof(line), "%25s -> %.6g\n", d.name, *reinterpret_cast<const float*>(base)); break;
+      case kOptBool: snprintf(line, sizeof(line), "%25s -> %s\n", d.name, *reinterpret_cast<const bool*>(base) ? "true" : "false"); break;
+    }
+    out += line;
+  }
+  strncpy(buf, out.c_str(), (size_t)buf_len - 1);
+  buf[buf_len - 1] = 0;
+  return (int)out.size();
+}
+
+int sm_set_input_source(sm_handle* h, const double* p, int64_t n) { return set_source(h, p, n, false); }
+int sm_set_input_source_device(sm_handle* h, const double* p, int64_t n) { return set_source(h, p, n, true); }
+int sm_set_input_target(sm_handle* h, const double* p, const double* nrm, int64_t n) {
+  return set_target(h, p, nrm, n, false);
+}
+int sm_set_input_target_device(sm_handle* h, const double* p, const double* nrm, int64_t n) {
+  return set_target(h, p, nrm, n, true);
+}
+
+int sm_align(sm_handle* h, const double* guess, double* result) {
+  if (!h || !guess || !result) return SM_ERR_BAD_ARGUMENT;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
+  if (h->type == SM_TYPE_FAST_ICP) return icp_align(h, guess, result);
+  return fail(h, SM_ERR_UNSUPPORTED_TYPE, "matcher type not supported");
+}
+
+double sm_get_fitness_score(const sm_handle* h) { return h ? h->final_score : 0.0; }
+
+int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
+  if (!h || !out) return SM_ERR_BAD_ARGUMENT;
+  *out = h->info;
+  return SM_OK;
+}
+
+const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
+
+int sm_knn1(int device, const double* target, int64_t nt, const double* query, int64_t nq,
+            double epsilon, int bucket, int32_t* ids, double* d2) {
+  if (!target || !query || nt <= 0 || nq < 0 || bucket < 2 || bucket > 16) return SM_ERR_BAD_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
+  SMB_CUDA_OK(cudaSetDevice(device));
+  cudaStream_t s = nullptr;
+  const int64_t ts = pad64(nt), qs = pad64(nq > 0 ? nq : 1);
+  const int levels = kd_num_levels((int)nt, bucket);
+  DevBuf stage, tgt, qry, nodes, order, bpts, kdws, ids_d, d2_d;
+  int rc = 0;
+  auto cleanup = [&]() {
+    DevBuf* bufs[] = {&stage, &tgt, &qry, &nodes, &order, &bpts, &kdws, &ids_d, &d2_d};
+    for (DevBuf* b : bufs) b->release();
+  };
+#define K_OK(expr) do { if ((rc = (expr)) != 0) { cleanup(); return rc < 0 ? rc : SM_ERR_CUDA; } } while (0)
+#define K_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_cuda_error(_e, #expr, __FILE__, __LINE__); cleanup(); return SM_ERR_CUDA; } } while (0)
+  K_OK(stage.reserve((size_t)3 * (size_t)(nt > nq ? nt : nq) * sizeof(double)));
+  K_OK(tgt.reserve((size_t)3 * ts * sizeof(double)));
+  K_OK(qry.reserve((size_t)3 * qs * sizeof(double)));
+  K_OK(nodes.reserve(((size_t)1 << (levels + 1)) * sizeof(KdNode)));
+  K_OK(order.reserve((size_t)nt * sizeof(uint32_t)));
+  K_OK(bpts.reserve((size_t)nt * sizeof(BucketPoint)));
+  K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)nt, bucket)));
+  K_OK(ids_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(int32_t)));
+  K_OK(d2_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
+  K_CUDA(cudaMemcpyAsync(stage.p, target, (size_t)3 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  deinterleave3_kernel<<<ceil_div(nt, 256), 256, 0, s>>>((const double*)stage.p, (double*)tgt.p, ts, (int)nt);
+  K_CUDA(cudaStreamSynchronize(s));
+  KdWorkspace ws;
+  ws.carve(kdws.p, (int)nt, bucket);
+  K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s));
+  K_OK(kd_fill_buckets((const double*)tgt.p, ts, nullptr, 0, (const uint32_t*)order.p, (int)nt,
+                       (BucketPoint*)bpts.p, nullptr, s));
+  if (nq > 0) {
+    K_CUDA(cudaMemcpyAsync(stage.p, query, (size_t)3 * nq * sizeof(double), cudaMemcpyHostToDevice, s));
+    deinterleave3_kernel<<<ceil_div(nq, 256), 256, 0, s>>>((const double*)stage.p, (double*)qry.p, qs, (int)nq);
+    K_OK(knn_query((const KdNode*)nodes.p, (const BucketPoint*)bpts.p, (const double*)qry.p, qs,
+                   (int)nq, (1.0 + epsilon) * (1.0 + epsilon), (int32_t*)ids_d.p, (double*)d2_d.p, s));
+    K_CUDA(cudaMemcpyAsync(ids, ids_d.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    K_CUDA(cudaMemcpyAsync(d2, d2_d.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  K_CUDA(cudaStreamSynchronize(s));
+  cleanup();
+#undef K_OK
+#undef K_CUDA
+  return SM_OK;
+}
+
+}  // extern "C"

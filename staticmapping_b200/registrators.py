@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's plugin surface, registrator::Interface
+(/root/reference/registrators/interface.h:67-119), over the C ABI of libsm_b200.so.
+
+Same member names, argument meaning and error behaviour as the reference:
+
+* ``CreateMatcher(options)``            interface.cc:139-173
+* ``Interface.InitWithXml(node)``       interface.cc:62-90  (unknown <param> -> CheckFailure,
+                                         the reference glog-CHECK-aborts)
+* ``SetInputSource / SetInputTarget``   icp_fast.cc:421-431 (deep copy; target needs normals)
+* ``Align(guess) -> (ok, result)``      icp_fast.cc:455-529 (C++: bool Align(guess, result&))
+* ``GetFitnessScore / GetType / PrintOptions / Enable/DisableInnerCompensation``
+
+Clouds are passed as the data the reference's ``InnerPointCloudData`` holds for each
+matcher: an ``EigenCloud`` (double points [+ normals]) for IcpFast.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+
+class Type(enum.IntEnum):
+    """registrator::Type (interface.h:41-50)."""
+    kNoType = 0
+    kIcpPM = 1
+    kLibicp = 2
+    kNdtWithGicp = 3
+    kLegoLoam = 4
+    kNdt = 5
+    kFastIcp = 6
+
+
+class CheckFailure(RuntimeError):
+    """Raised where the reference would glog CHECK-fail (abort)."""
+
+
+@dataclass
+class EigenCloud:
+    """data::EigenPointCloud (cloud_types.h:121-147): (N,3) float64 points, optional normals.
+    C-contiguous (N,3) == Eigen's 3xN column-major storage."""
+    points: np.ndarray
+    normals: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.points = np.ascontiguousarray(np.asarray(self.points, dtype=np.float64))
+        if self.points.ndim != 2 or self.points.shape[1] != 3:
+            raise ValueError("points must be (N,3)")
+        if self.normals is not None:
+            self.normals = np.ascontiguousarray(np.asarray(self.normals, dtype=np.float64))
+            if self.normals.shape != self.points.shape:
+                raise ValueError("normals must match points")
+
+    def HasNormals(self):
+        return self.normals is not None and self.normals.shape[0] > 0
+
+    @staticmethod
+    def FromPointCloud(xyz_f32):
+        """EigenPointCloud::FromPointCloud (cloud_types.cc:328-345): float AoS -> double."""
+        return EigenCloud(np.asarray(xyz_f32, dtype=np.float32).astype(np.float64))
+
+
+@dataclass
+class MatcherOptions:
+    """registrator::MatcherOptions (interface.h:59-65)."""
+    type: Type = Type.kIcpPM
+    accepted_min_score: float = 0.7
+    registrator_options_node: Optional[object] = None   # xml string / Element / dict
+    inner_filters_node: Optional[object] = None
+
+
+def _params_from_node(node):
+    if node is None:
+        return []
+    if isinstance(node, dict):
+        return [(k, str(v)) for k, v in node.items()]
+    if isinstance(node, (str, bytes)):
+        node = ET.fromstring(node)
+    return [(p.attrib.get("name", ""), (p.text or "").strip()) for p in node.findall("param")]
+
+
+class Interface:
+    """registrator::Interface.  One instance is used by one thread at a time; distinct
+    instances may run concurrently (each owns a CUDA stream + workspace)."""
+
+    _type = Type.kNoType
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        rc = self._lib.sm_create(int(self._type), device, C.byref(self._h))
+        if rc == -20:
+            raise RuntimeError("staticmapping_b200: no CUDA device visible and there is no CPU "
+                               "fallback (SM_ERR_NO_DEVICE)")
+        if rc != 0:
+            raise RuntimeError(f"sm_create failed with {rc}")
+        self._inner_compensation = False
+        self._source = None
+        self._target = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.sm_destroy(h)
+            self._h = C.c_void_p()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self._lib.sm_last_error(self._h)
+            raise CheckFailure(f"{what}: {msg.decode() if msg else rc} (code {rc})")
+        return rc
+
+    # --- options -------------------------------------------------------------------------
+    def InitWithXml(self, node):
+        for name, text in _params_from_node(node):
+            self._check(self._lib.sm_set_option(self._h, name.encode(), text.encode()),
+                        "InitWithXml")
+
+    def InitInnerFiltersWithXml(self, node):
+        return None  # interface.cc:92-113: a TODO in the reference, no effect
+
+    def InitWithOptions(self):
+        return None
+
+    def PrintOptions(self):
+        buf = C.create_string_buffer(4096)
+        self._lib.sm_print_options(self._h, buf, 4096)
+        text = buf.value.decode()
+        print(text, end="")
+        return text
+
+    def EnableInnerCompensation(self):
+        self._inner_compensation = True   # no caller in the reference
+
+    def DisableInnerCompensation(self):
+        self._inner_compensation = False
+
+    # --- data ----------------------------------------------------------------------------
+    def SetInputSource(self, cloud: EigenCloud):
+        raise NotImplementedError
+
+    def SetInputTarget(self, cloud: EigenCloud):
+        raise NotImplementedError
+
+    def Align(self, guess):
+        """Returns (ok, result 4x4).  C++: bool Align(const Matrix4d& guess, Matrix4d& result)."""
+        g = np.ascontiguousarray(np.asarray(guess, dtype=np.float64).T).ravel()
+        res = np.zeros(16, dtype=np.float64)
+        rc = self._check(self._lib.sm_align(self._h, g.ctypes.data_as(_lib._DP),
+                                            res.ctypes.data_as(_lib._DP)), "Align")
+        return bool(rc), res.reshape(4, 4).T.copy()
+
+    def GetFitnessScore(self):
+        return float(self._lib.sm_get_fitness_score(self._h))
+
+    def GetType(self):
+        return Type(self._lib.sm_get_type(self._h))
+
+    def GetAlignInfo(self):
+        info = _lib.AlignInfo()
+        self._lib.sm_get_align_info(self._h, C.byref(info))
+        return {k: getattr(info, k) for k, _ in _lib.AlignInfo._fields_ if k != "reserved"}
+
+
+class IcpFast(Interface):
+    """registrator::IcpFast (icp_fast.h:37-62)."""
+    _type = Type.kFastIcp
+
+    def SetInputSource(self, cloud: EigenCloud):
+        if cloud is None or cloud.points.shape[0] == 0:
+            raise CheckFailure("SetInputSource: CHECK(cloud) failed (icp_fast.cc:422-423)")
+        self._check(self._lib.sm_set_input_source(self._h, cloud.points.ctypes.data,
+                                                  cloud.points.shape[0]), "SetInputSource")
+
+    def SetInputTarget(self, cloud: EigenCloud):
+        if cloud is None or cloud.points.shape[0] == 0:
+            raise CheckFailure("SetInputTarget: CHECK(cloud) failed (icp_fast.cc:428-429)")
+        if not cloud.HasNormals():
+            raise CheckFailure("SetInputTarget: CHECK(HasNormals()) failed (icp_fast.cc:430)")
+        self._check(self._lib.sm_set_input_target(self._h, cloud.points.ctypes.data,
+                                                  cloud.normals.ctypes.data,
+                                                  cloud.points.shape[0]), "SetInputTarget")
+
+    # device-resident variants (pointers to 3xN column-major doubles in this GPU's memory)
+    def SetInputSourceDevice(self, dev_ptr: int, n: int):
+        self._check(self._lib.sm_set_input_source_device(self._h, dev_ptr, n), "SetInputSource")
+
+    def SetInputTargetDevice(self, dev_points: int, dev_normals: int, n: int):
+        self._check(self._lib.sm_set_input_target_device(self._h, dev_points, dev_normals, n),
+                    "SetInputTarget")
+
+
+def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 0) -> Interface:
+    """registrator::CreateMatcher (interface.cc:139-173)."""
+    t = Type(options.type)
+    if t == Type.kFastIcp:
+        matcher = IcpFast(device)
+    elif t in (Type.kLibicp, Type.kLegoLoam):
+        raise CheckFailure("The registrator using libicp & lego-loam is deprecated. "
+                           "please choose another type")   # LOG(FATAL), interface.cc:154-157
+    elif t in (Type.kIcpPM, Type.kNdtWithGicp, Type.kNdt):
+        raise NotImplementedError(f"matcher type {t.name} is not built yet in sm_b200")
+    else:
+        print("Wrong type")   # PRINT_ERROR + nullptr, interface.cc:158-160
+        return None
+    if options.registrator_options_node is not None:
+        matcher.InitWithXml(options.registrator_options_node)
+    if verbose:
+        matcher.PrintOptions()
+    matcher.InitWithOptions()
+    return matcher
+
+
+def knn1(target, query, epsilon=3.16, bucket_size=8, device=0):
+    """libnabo-compatible 1-NN on the GPU (NNS::create + knn, icp_fast.cc:466-467,177-178)."""
+    lib = _lib.lib()
+    t = np.ascontiguousarray(np.asarray(target, dtype=np.float64))
+    q = np.ascontiguousarray(np.asarray(query, dtype=np.float64))
+    ids = np.empty(q.shape[0], dtype=np.int32)
+    d2 = np.empty(q.shape[0], dtype=np.float64)
+    rc = lib.sm_knn1(device, t.ctypes.data, t.shape[0], q.ctypes.data, q.shape[0], float(epsilon),
+                     int(bucket_size), ids.ctypes.data, d2.ctypes.data)
+    if rc == -20:
+        raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
+    if rc != 0:
+        raise RuntimeError(f"sm_knn1 failed with {rc}")
+    return ids, d2
