@@ -60,7 +60,8 @@ int sm_destroy(sm_handle* h);
  * Registered names, IcpFast (icp_fast.cc:411-418): knn_normal_estimate (int, unused),
  * max_iteration (int, 100), dist_outlier_ratio (float, 0.7).  Added by this engine:
  * knn_epsilon (float, 3.16 = icp_fast.cc:174), disable_convergence_check (bool, false;
- * fixed-iteration throughput runs).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
+ * fixed-iteration throughput runs), profile_kernels (bool, false; CUDA events around
+ * every phase kernel, reported by sm_get_align_info).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
 int sm_set_option(sm_handle* h, const char* name, const char* text);
 /* Interface::PrintOptions (interface.cc:115-137): writes "name -> value\n" lines. */
 int sm_print_options(sm_handle* h, char* buf, int64_t buf_len);
@@ -97,8 +98,19 @@ typedef struct sm_align_info {
   float ms_prologue;       /* centre + tree build + G0 (icp_fast.cc:456-480) */
   float ms_iterations;     /* all ICP iterations */
   int32_t kernel_launches; /* kernels launched by the last sm_align */
+  /* filled only when option profile_kernels=1: summed device time of each phase kernel */
+  float ms_knn;            /* transform + k-NN + histogram        (icp_fast.cc:486-493) */
+  float ms_accum;          /* quantile bin + normal equations      (icp_fast.cc:496-503) */
+  float ms_finish;         /* exact limit, solve, pose update      (icp_fast.cc:506-523) */
+  int32_t profiled_iterations;
 } sm_align_info;
 int sm_get_align_info(const sm_handle* h, sm_align_info* out);
+
+/* Run this handle's work on the caller's CUDA stream (a cudaStream_t passed as void*;
+ * NULL restores the handle's own stream).  Lets a host that already owns a stream —
+ * e.g. the bench's torch stream — order and time the engine's kernels with its own
+ * events.  No reference counterpart (the reference is CPU-only). */
+int sm_set_stream(sm_handle* h, void* cuda_stream);
 
 const char* sm_last_error(const sm_handle* h);
 
@@ -108,6 +120,15 @@ const char* sm_last_error(const sm_handle* h);
  * ids: original target column, -1 if none; dists2: squared distances. */
 int sm_knn1(int device, const double* target_3xn, int64_t n_target, const double* query_3xn,
             int64_t n_query, double epsilon, int bucket_size, int32_t* ids, double* dists2);
+
+/* EigenPointCloud::CalculateNormals (builder/data/cloud_types.cc:347-368): median-split
+ * the cloud into leaves of <= 7 points, fit n.p = 1 per leaf, keep one point (the leaf
+ * mean) + unit normal per valid leaf, survivors in ascending order of the smallest
+ * original index of their leaf.  out_points / out_normals: capacity 3*n doubles;
+ * *m_out receives the number of survivors.  Called by the reference right before
+ * IcpFast::SetInputTarget (map_builder.cc:286,389; submap.cc:161). */
+int sm_calculate_normals(int device, const double* points_3xn, int64_t n, double* out_points,
+                         double* out_normals, int64_t* m_out);
 
 int sm_device_count(void);
 const char* sm_version(void);

@@ -64,6 +64,9 @@ struct NormalsBuilder {
   void Leaf(int first, int last) {
     const int count = last - first;
     if (count <= 0) return;
+    // tie_mode 0: canonical member order (ascending original index) so that the sums
+    // below have one defined rounding; the reference's order is whatever nth_element left.
+    if (tie_mode == 0) std::sort(indices.begin() + first, indices.begin() + last);
     double d[7][3];
     double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < count; ++i) {

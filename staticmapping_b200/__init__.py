@@ -2,8 +2,8 @@
 registrator::Interface.  The compute lives in libsm_b200.so (hand-written sm_100a CUDA,
 C ABI in include/sm_b200.h); this package is the thin host-side mirror used by the tests
 and the bench.  There is no CPU fallback."""
-from .registrators import (CheckFailure, CreateMatcher, EigenCloud, IcpFast, Interface,  # noqa: F401
+from .registrators import (CalculateNormals, CheckFailure, CreateMatcher, EigenCloud, IcpFast, Interface,  # noqa: F401
                            MatcherOptions, Type, knn1)
 
-__all__ = ["CheckFailure", "CreateMatcher", "EigenCloud", "IcpFast", "Interface",
+__all__ = ["CalculateNormals", "CheckFailure", "CreateMatcher", "EigenCloud", "IcpFast", "Interface",
            "MatcherOptions", "Type", "knn1"]

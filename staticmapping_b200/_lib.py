@@ -16,7 +16,9 @@ class AlignInfo(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("status", C.c_int32), ("solve_path", C.c_int32),
                 ("reserved", C.c_int32), ("kept", C.c_int64), ("limit", C.c_double),
                 ("ms_upload", C.c_float), ("ms_prologue", C.c_float),
-                ("ms_iterations", C.c_float), ("kernel_launches", C.c_int32)]
+                ("ms_iterations", C.c_float), ("kernel_launches", C.c_int32),
+                ("ms_knn", C.c_float), ("ms_accum", C.c_float), ("ms_finish", C.c_float),
+                ("profiled_iterations", C.c_int32)]
 
 
 _lib = None
@@ -39,8 +41,10 @@ SIGNATURES = {
     "sm_align": (C.c_int, [_VP, _DP, _DP]),
     "sm_get_fitness_score": (C.c_double, [_VP]),
     "sm_get_align_info": (C.c_int, [_VP, C.POINTER(AlignInfo)]),
+    "sm_set_stream": (C.c_int, [_VP, _VP]),
     "sm_last_error": (C.c_char_p, [_VP]),
     "sm_knn1": (C.c_int, [C.c_int, _VP, C.c_int64, _VP, C.c_int64, C.c_double, C.c_int, _VP, _VP]),
+    "sm_calculate_normals": (C.c_int, [C.c_int, _VP, C.c_int64, _VP, _VP, C.POINTER(C.c_int64)]),
     "sm_device_count": (C.c_int, []),
     "sm_version": (C.c_char_p, []),
 }

@@ -614,12 +614,16 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
 }
 
 int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, cudaEvent_t* events) {
   const int nb = icp_accum_blocks(p.n_source);
   for (int it = 0; it < count; ++it) {
+    if (events) cudaEventRecord(events[4 * it + 0], stream);
     icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(b, p);
+    if (events) cudaEventRecord(events[4 * it + 1], stream);
     icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
+    if (events) cudaEventRecord(events[4 * it + 2], stream);
     icp_finish_kernel<<<1, kFinThreads, 0, stream>>>(b, p, nb);
+    if (events) cudaEventRecord(events[4 * it + 3], stream);
   }
   SMB_CUDA_OK(cudaGetLastError());
   return 0;

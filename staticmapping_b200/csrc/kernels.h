@@ -93,14 +93,22 @@ struct IcpBuffers {
 int icp_accum_blocks(int n_source);
 int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_dev,
                  KdWorkspace& ws, cudaStream_t stream);
+// events (optional): 4 per iteration — before A, after A, after B, after C
 int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
-                           cudaStream_t stream);
+                           cudaStream_t stream, cudaEvent_t* events);
 // stand-alone k-NN over an already built tree (parity tests): ids = original indices
 int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
               int nq, double max_error2, int32_t* ids, double* d2, cudaStream_t stream);
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);
+
+// ---- normals.cu ------------------------------------------------------------------------
+int normals_scratch_blocks(int n);
+int normals_run(const double* coord, int64_t cstride, int n, KdWorkspace& ws, KdNode* nodes,
+                uint32_t* leaf_order, double* tmp_pts, double* tmp_nrm, uint32_t* keep,
+                uint32_t* block_sums, double* out_pts, double* out_nrm, uint32_t* m_dev,
+                cudaStream_t stream);
 
 }  // namespace smb
 

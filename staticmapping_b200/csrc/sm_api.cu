@@ -7,6 +7,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -56,6 +57,7 @@ struct IcpOptions {
   float dist_outlier_ratio = 0.7f;       // icp_fast.h:59
   float knn_epsilon = 3.16f;             // icp_fast.cc:174 (engine option; same default)
   bool disable_convergence_check = false;
+  bool profile_kernels = false;
 };
 
 }  // namespace
@@ -66,7 +68,8 @@ using namespace smb;
 struct sm_handle {
   int type = 0;
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by sm_create
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string error;
   IcpOptions icp;
@@ -79,6 +82,7 @@ struct sm_handle {
   bool has_source = false, has_target = false;
   float ms_upload = 0.f;
   IcpState* host_state = nullptr;  // pinned
+  std::vector<cudaEvent_t> prof_events;
 };
 
 namespace {
@@ -89,6 +93,7 @@ const OptionDef kIcpOptions[] = {
     {"dist_outlier_ratio", kOptFloat, offsetof(IcpOptions, dist_outlier_ratio)},
     {"knn_epsilon", kOptFloat, offsetof(IcpOptions, knn_epsilon)},
     {"disable_convergence_check", kOptBool, offsetof(IcpOptions, disable_convergence_check)},
+    {"profile_kernels", kOptBool, offsetof(IcpOptions, profile_kernels)},
 };
 
 int fail(sm_handle* h, int code, const std::string& msg) {
@@ -223,7 +228,14 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   while (true) {
     const int chunk = p.disable_convergence ? (max_it - enqueued)
                                             : ((max_it - enqueued) < 8 ? (max_it - enqueued) : 8);
-    H_RC(icp_enqueue_iterations(b, p, chunk, h->stream));
+    cudaEvent_t* evs = nullptr;
+    if (h->icp.profile_kernels) {
+      while ((int)h->prof_events.size() < 4 * (enqueued + chunk)) {
+        cudaEvent_t e; H_CUDA(cudaEventCreate(&e)); h->prof_events.push_back(e);
+      }
+      evs = h->prof_events.data() + 4 * enqueued;
+    }
+    H_RC(icp_enqueue_iterations(b, p, chunk, h->stream, evs));
     enqueued += chunk;
     launches += 3 * chunk;
     H_CUDA(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost,
@@ -243,6 +255,18 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   cudaEventElapsedTime(&h->info.ms_prologue, h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&h->info.ms_iterations, h->ev[1], h->ev[2]);
   h->info.kernel_launches = launches;
+  h->info.ms_knn = h->info.ms_accum = h->info.ms_finish = 0.f;
+  h->info.profiled_iterations = 0;
+  if (h->icp.profile_kernels) {
+    for (int it = 0; it < st.iteration && 4 * it + 3 < (int)h->prof_events.size(); ++it) {
+      float a = 0.f, bb = 0.f, c = 0.f;
+      cudaEventElapsedTime(&a, h->prof_events[4 * it], h->prof_events[4 * it + 1]);
+      cudaEventElapsedTime(&bb, h->prof_events[4 * it + 1], h->prof_events[4 * it + 2]);
+      cudaEventElapsedTime(&c, h->prof_events[4 * it + 2], h->prof_events[4 * it + 3]);
+      h->info.ms_knn += a; h->info.ms_accum += bb; h->info.ms_finish += c;
+      h->info.profiled_iterations++;
+    }
+  }
   h->ms_upload = 0.f;
   if (st.status < 0)
     return fail(h, st.status, st.status == -2 ? "Align: no finite match distance (icp_fast.cc:81)"
@@ -276,11 +300,12 @@ int sm_create(int type, int device, sm_handle** out) {
   h->device = device;
   memset(&h->info, 0, sizeof(h->info));
   if (cudaSetDevice(device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess) {
     delete h;
     return SM_ERR_CUDA;
   }
+  h->stream = h->own_stream;
   for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
   *out = h;
   return SM_OK;
@@ -295,13 +320,22 @@ int sm_destroy(sm_handle* h) {
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->host_state) cudaFreeHost(h->host_state);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SM_OK;
 }
 
 int sm_get_type(const sm_handle* h) { return h ? h->type : 0; }
+
+int sm_set_stream(sm_handle* h, void* cuda_stream) {
+  if (!h) return SM_ERR_BAD_ARGUMENT;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return SM_OK;
+}
 
 int sm_set_option(sm_handle* h, const char* name, const char* text) {
   if (!h || !name || !text) return SM_ERR_BAD_ARGUMENT;
@@ -367,6 +401,57 @@ int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
 }
 
 const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
+
+int sm_calculate_normals(int device, const double* points, int64_t n, double* out_points,
+                         double* out_normals, int64_t* m_out) {
+  if (!points || !out_points || !out_normals || !m_out || n <= 0 || n > (1 << 30))
+    return SM_ERR_BAD_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
+  SMB_CUDA_OK(cudaSetDevice(device));
+  cudaStream_t s = nullptr;
+  const int64_t cs = pad64(n);
+  const int levels = kd_num_levels((int)n, 7);
+  DevBuf stage, coord, nodes, order, kdws, tmp_pts, tmp_nrm, keep, bsum, outp, outn, mdev;
+  int rc = 0;
+  auto cleanup = [&]() {
+    DevBuf* bufs[] = {&stage, &coord, &nodes, &order, &kdws, &tmp_pts, &tmp_nrm, &keep, &bsum, &outp, &outn, &mdev};
+    for (DevBuf* b : bufs) b->release();
+  };
+#define K_OK(expr) do { if ((rc = (expr)) != 0) { cleanup(); return rc < 0 ? rc : SM_ERR_CUDA; } } while (0)
+#define K_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_cuda_error(_e, #expr, __FILE__, __LINE__); cleanup(); return SM_ERR_CUDA; } } while (0)
+  const size_t aos = (size_t)3 * (size_t)n * sizeof(double);
+  K_OK(stage.reserve(aos));
+  K_OK(coord.reserve((size_t)3 * cs * sizeof(double)));
+  K_OK(nodes.reserve(((size_t)1 << (levels + 1)) * sizeof(KdNode)));
+  K_OK(order.reserve((size_t)n * sizeof(uint32_t)));
+  K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)n, 7)));
+  K_OK(tmp_pts.reserve(aos)); K_OK(tmp_nrm.reserve(aos));
+  K_OK(keep.reserve((size_t)n * sizeof(uint32_t)));
+  K_OK(bsum.reserve((size_t)(normals_scratch_blocks((int)n) + 1) * sizeof(uint32_t)));
+  K_OK(outp.reserve(aos)); K_OK(outn.reserve(aos));
+  K_OK(mdev.reserve(sizeof(uint32_t)));
+  K_CUDA(cudaMemcpyAsync(stage.p, points, aos, cudaMemcpyHostToDevice, s));
+  deinterleave3_kernel<<<ceil_div(n, 256), 256, 0, s>>>((const double*)stage.p, (double*)coord.p, cs, (int)n);
+  KdWorkspace ws;
+  ws.carve(kdws.p, (int)n, 7);
+  K_OK(normals_run((const double*)coord.p, cs, (int)n, ws, (KdNode*)nodes.p, (uint32_t*)order.p,
+                   (double*)tmp_pts.p, (double*)tmp_nrm.p, (uint32_t*)keep.p, (uint32_t*)bsum.p,
+                   (double*)outp.p, (double*)outn.p, (uint32_t*)mdev.p, s));
+  uint32_t m = 0;
+  K_CUDA(cudaMemcpyAsync(&m, mdev.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  K_CUDA(cudaStreamSynchronize(s));
+  if (m > 0) {
+    K_CUDA(cudaMemcpyAsync(out_points, outp.p, (size_t)3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    K_CUDA(cudaMemcpyAsync(out_normals, outn.p, (size_t)3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    K_CUDA(cudaStreamSynchronize(s));
+  }
+  *m_out = (int64_t)m;
+  cleanup();
+#undef K_OK
+#undef K_CUDA
+  return SM_OK;
+}
 
 int sm_knn1(int device, const double* target, int64_t nt, const double* query, int64_t nq,
             double epsilon, int bucket, int32_t* ids, double* d2) {

@@ -162,6 +162,10 @@ class Interface:
     def GetType(self):
         return Type(self._lib.sm_get_type(self._h))
 
+    def SetStream(self, cuda_stream: int = 0):
+        """Run on the caller's CUDA stream (0 / None -> the handle's own stream)."""
+        self._check(self._lib.sm_set_stream(self._h, cuda_stream or None), "SetStream")
+
     def GetAlignInfo(self):
         info = _lib.AlignInfo()
         self._lib.sm_get_align_info(self._h, C.byref(info))
@@ -231,3 +235,20 @@ def knn1(target, query, epsilon=3.16, bucket_size=8, device=0):
     if rc != 0:
         raise RuntimeError(f"sm_knn1 failed with {rc}")
     return ids, d2
+
+
+def CalculateNormals(points, device=0) -> EigenCloud:
+    """EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368): returns the
+    decimated cloud (one mean point + unit normal per valid <=7-point leaf)."""
+    lib = _lib.lib()
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+    out_p = np.empty_like(p)
+    out_n = np.empty_like(p)
+    m = C.c_int64(0)
+    rc = lib.sm_calculate_normals(device, p.ctypes.data, p.shape[0], out_p.ctypes.data,
+                                  out_n.ctypes.data, C.byref(m))
+    if rc == -20:
+        raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
+    if rc != 0:
+        raise RuntimeError(f"sm_calculate_normals failed with {rc}")
+    return EigenCloud(out_p[:m.value].copy(), out_n[:m.value].copy())
