@@ -14,126 +14,12 @@
 // Nothing returns to the host between iterations; kernels early-out on state->done.
 #include "common.cuh"
 #include "kernels.h"
+#include "icp_dev.cuh"
 #include "linalg_dev.cuh"
 
 namespace smb {
+using namespace dev;
 namespace {
-
-constexpr int kKnnThreads = 256;
-constexpr int kAccThreads = 256;
-constexpr int kAccItems = 2;
-constexpr int kAccTile = kAccThreads * kAccItems;  // points per accumulate block
-constexpr int kNumSums = 29;                        // 21 (A upper) + 6 (b) + sum sqrt + count
-constexpr int kFinThreads = 1024;
-constexpr int kMaxStack = 32;
-
-// monotone bin of a non-negative finite double: 1/32-octave resolution over 2^-40..2^24
-__device__ __forceinline__ int dist_bin(double d2) {
-  const long long bits = __double_as_longlong(d2);
-  const int key = (int)(bits >> 47) - ((1023 - 40) << 5);
-  return min(max(key, 0), kHistBins - 1);
-}
-
-__device__ __forceinline__ bool finite_d2(double d) { return d < __longlong_as_double(0x7ff0000000000000ll); }
-
-// p = T (x) s with the reference's accumulation order (cloud_types.cc:288-296)
-__device__ __forceinline__ void transform_point(const double* __restrict__ T, double x, double y,
-                                                double z, double& px, double& py, double& pz) {
-  px = dadd(dadd(dadd(dmul(T[0], x), dmul(T[4], y)), dmul(T[8], z)), T[12]);
-  py = dadd(dadd(dadd(dmul(T[1], x), dmul(T[5], y)), dmul(T[9], z)), T[13]);
-  pz = dadd(dadd(dadd(dmul(T[2], x), dmul(T[6], y)), dmul(T[10], z)), T[14]);
-}
-
-__device__ __forceinline__ KdNode load_node(const KdNode* __restrict__ nodes, int h) {
-  const int4 v = __ldg(reinterpret_cast<const int4*>(nodes + h));
-  KdNode n;
-  n.cut = __hiloint2double(v.y, v.x);
-  n.dim = v.z; n.pad = v.w;
-  return n;
-}
-
-__device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, const KdNode& leaf,
-                                          double qx, double qy, double qz, double& head,
-                                          int& best) {
-  const long long packed = __double_as_longlong(leaf.cut);
-  const int first = (int)(packed & 0xffffffffll), count = (int)(packed >> 32);
-  for (int k = 0; k < count; ++k) {
-    const double2 xy = __ldg(reinterpret_cast<const double2*>(bpts + first + k));
-    const double z = __ldg(reinterpret_cast<const double*>(bpts + first + k) + 2);
-    const double dx = dsub(qx, xy.x), dy = dsub(qy, xy.y), dz = dsub(qz, z);
-    const double dist = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
-    if (dist < head) { head = dist; best = first + k; }  // strict: first visited wins
-  }
-}
-
-struct StackEntry {
-  double rd, ox, oy, oz;
-  int h;
-};
-
-// libnabo recurseKnn (k=1, allowSelfMatch, maxRadius=inf) made iterative.  A far subtree
-// is pushed only if it passes the pruning test against the head known at push time (the
-// head can only shrink, so this never drops a subtree the recursion would visit) and is
-// re-tested at pop time, which is exactly when the recursion tests it.  A read-only first
-// descent seeds the head so the stack stays almost empty for epsilon = 3.16.
-__device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
-                                     const BucketPoint* __restrict__ bpts, double qx, double qy,
-                                     double qz, double max_error2, int& best_slot, double& best_d2) {
-  double head = __longlong_as_double(0x7ff0000000000000ll);
-  int best = -1;
-  int h = 0;
-  KdNode nd = load_node(nodes, 0);
-  while (nd.dim != 3) {
-    const double q = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
-    h = 2 * h + 1 + ((dsub(q, nd.cut) > 0.0) ? 1 : 0);
-    nd = load_node(nodes, h);
-  }
-  const int leaf0 = h;
-  scan_leaf(bpts, nd, qx, qy, qz, head, best);
-
-  StackEntry stack[kMaxStack];
-  int sp = 0;
-  double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
-  h = 0;
-  while (true) {
-    while (true) {
-      nd = load_node(nodes, h);
-      if (nd.dim == 3) {
-        if (h != leaf0) scan_leaf(bpts, nd, qx, qy, qz, head, best);
-        break;
-      }
-      const int cd = nd.dim;
-      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
-      const double new_off = dsub(q, nd.cut);
-      const int right = new_off > 0.0 ? 1 : 0;
-      // rd += - old_off*old_off + new_off*new_off
-      const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
-        StackEntry e;
-        e.rd = rd_new;
-        e.ox = cd == 0 ? new_off : ox;
-        e.oy = cd == 1 ? new_off : oy;
-        e.oz = cd == 2 ? new_off : oz;
-        e.h = 2 * h + 1 + (1 - right);
-        stack[sp++] = e;
-      }
-      h = 2 * h + 1 + right;
-    }
-    bool found = false;
-    while (sp > 0) {
-      const StackEntry e = stack[--sp];
-      if (dmul(e.rd, max_error2) < head) {
-        h = e.h; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
-        found = true;
-        break;
-      }
-    }
-    if (!found) break;
-  }
-  best_slot = best;
-  best_d2 = head;
-}
 
 // ------------------------------------------------------------------------------ prologue
 __global__ void __launch_bounds__(256)
@@ -199,7 +85,7 @@ __global__ void fill_buckets_kernel(const double* __restrict__ coord, int64_t cs
 // one block: G0 = T_mean^-1 * guess, state reset, histogram clear (icp_fast.cc:460-480)
 __global__ void icp_init_kernel(IcpState* __restrict__ st, const double* __restrict__ guess,
                                 uint32_t* __restrict__ hist) {
-  for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i < 2 * kHistBins; i += blockDim.x) hist[i] = 0;  // hist + hist2
   if (threadIdx.x != 0) return;
   double Tm[16], Tmi[16];
   for (int i = 0; i < 16; ++i) { Tm[i] = (i % 5 == 0) ? 1.0 : 0.0; Tmi[i] = Tm[i]; }
@@ -255,102 +141,6 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
 }
 
 // -------------------------------------------------------------------------------- phase B
-struct BinSel { int bin; int below; int qi; int nvalid; };
-
-// every block locates the quantile bin from the global histogram (2048 bins, 8 per thread
-// on the first 256 threads; all threads of the block must call this)
-__device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist, float ratio,
-                                             uint32_t* warp_tot /*[8]*/, BinSel* out_sm) {
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const bool active = t < 256;
-  uint32_t c[8], s = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { c[k] = active ? ghist[t * 8 + k] : 0u; s += c[k]; }
-  uint32_t incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (active && lane == 31) warp_tot[w] = incl;
-  __syncthreads();
-  uint32_t base = 0, total = 0;
-#pragma unroll
-  for (int ww = 0; ww < 8; ++ww) { const uint32_t v = warp_tot[ww]; if (ww < w) base += v; total += v; }
-  const uint32_t excl = base + incl - s;
-  // icp_fast.cc:82-89: quantile == 1.0 -> max element, else index int(size * quantile)
-  const double q = (double)ratio;
-  int qi = (q == 1.0) ? (int)total - 1 : (int)((double)total * q);
-  if (qi > (int)total - 1) qi = (int)total - 1;
-  if (active && total > 0 && (uint32_t)qi >= excl && (uint32_t)qi < excl + s) {
-    uint32_t run = excl;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if ((uint32_t)qi >= run && (uint32_t)qi < run + c[k]) {
-        out_sm->bin = t * 8 + k; out_sm->below = (int)run;
-      }
-      run += c[k];
-    }
-    out_sm->qi = qi; out_sm->nvalid = (int)total;
-  }
-  if (total == 0 && t == 0) { out_sm->bin = -1; out_sm->below = 0; out_sm->qi = 0; out_sm->nvalid = 0; }
-  __syncthreads();
-  return *out_sm;
-}
-
-// contribution of one match to the normal equations (icp_fast.cc:268-302)
-__device__ __forceinline__ void accumulate_match(double* acc, double px, double py, double pz,
-                                                 const BucketPoint& q, const BucketNormal& n,
-                                                 double d2) {
-  double F[6];
-  F[0] = py * n.z - pz * n.y;
-  F[1] = pz * n.x - px * n.z;
-  F[2] = px * n.y - py * n.x;
-  F[3] = n.x; F[4] = n.y; F[5] = n.z;
-  const double dot = (px - q.x) * n.x + (py - q.y) * n.y + (pz - q.z) * n.z;
-  int k = 0;
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = r; c < 6; ++c) acc[k++] += F[r] * F[c];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) acc[21 + r] += F[r] * dot;
-  acc[27] += sqrt(d2);
-  acc[28] += 1.0;
-}
-
-__device__ __forceinline__ void load_match(const IcpBuffers& b, const double* T, int i,
-                                           double& px, double& py, double& pz, BucketPoint& q,
-                                           BucketNormal& n) {
-  transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
-  const int s = b.slot[i];
-  const double2 qxy = __ldg(reinterpret_cast<const double2*>(b.bpts + s));
-  q.x = qxy.x; q.y = qxy.y;
-  q.z = __ldg(reinterpret_cast<const double*>(b.bpts + s) + 2);
-  const double2 nxy = __ldg(reinterpret_cast<const double2*>(b.bnrm + s));
-  n.x = nxy.x; n.y = nxy.y;
-  n.z = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
-}
-
-// deterministic block reduction of kNumSums doubles (fixed shuffle tree, fixed warp order)
-template <int NT>
-__device__ __forceinline__ void block_reduce_sums(double* acc, double (*sm)[kNumSums], double* out) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sm[w][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kNumSums) {
-    double v = 0.0;
-    for (int ww = 0; ww < NT / 32; ++ww) v += sm[ww][threadIdx.x];
-    out[threadIdx.x] = v;
-  }
-}
-
 __global__ void __launch_bounds__(kAccThreads)
 icp_accum_kernel(IcpBuffers b, IcpParams p) {
   __shared__ uint32_t warp_tot[8];
@@ -380,6 +170,7 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
           accumulate_match(acc, px, py, pz, q, n, d2);
         } else if (bin == sel.bin) {
           is_cand = true;
+          atomicAdd(&b.hist2[sub_bin(d2)], 1u);
         }
       }
     }
@@ -390,175 +181,16 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
     uint32_t off = cand_base, tot = 0;
 #pragma unroll
     for (int ww = 0; ww < kAccThreads / 32; ++ww) { const uint32_t c = cand_warp[ww]; if (ww < w) off += c; tot += c; }
-    if (is_cand) b.cand_idx[tile0 + off + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    if (is_cand) {
+      const int slot = tile0 + off + __popc(m & ((1u << lane) - 1u));
+      b.cand_idx[slot] = (uint32_t)i;
+      b.cand_key[slot] = (unsigned long long)__double_as_longlong(b.d2[i]);
+    }
     cand_base += tot;
     __syncthreads();
   }
   if (threadIdx.x == 0) b.cand_cnt[blockIdx.x] = cand_base;
   block_reduce_sums<kAccThreads>(acc, red, b.partials + (int64_t)blockIdx.x * 32);
-}
-
-// -------------------------------------------------------------------------------- phase C
-__global__ void __launch_bounds__(kFinThreads)
-icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
-  __shared__ uint32_t warp_tot[8];
-  __shared__ BinSel sel_sm;
-  __shared__ uint32_t sh_hist[256];
-  __shared__ uint32_t sh_scan[kFinThreads];
-  __shared__ double red[kFinThreads / 32][kNumSums];
-  __shared__ double sums[32];
-  __shared__ double cand_sums[32];
-  __shared__ double T[16];
-  __shared__ unsigned long long sh_prefix;
-  __shared__ int sh_rank;
-  IcpState* st = b.state;
-  if (st->done) return;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t < 16) T[t] = st->T_iter[t];
-  const BinSel sel = select_bin(b.hist, p.dist_outlier_ratio, warp_tot, &sel_sm);
-  if (sel.nvalid == 0) {
-    if (t == 0) { st->status = -2; st->done = 1; }  // CHECK(!values.empty()), icp_fast.cc:81
-    return;
-  }
-  // ---- compact the per-block candidate lists (ascending point index) ---------------------
-  uint32_t* cand = b.cand_idx;            // in: per-block regions
-  uint32_t* flat = b.cand_idx + ((int64_t)nblocks_b * kAccTile);  // out: flat list
-  uint32_t total = 0;
-  for (int base = 0; base < nblocks_b; base += kFinThreads) {
-    const int blk = base + t;
-    const uint32_t c = blk < nblocks_b ? b.cand_cnt[blk] : 0;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) sh_scan[w] = incl;
-    __syncthreads();
-    uint32_t wb = 0, tot = 0;
-    for (int ww = 0; ww < kFinThreads / 32; ++ww) { const uint32_t v = sh_scan[ww]; if (ww < w) wb += v; tot += v; }
-    const uint32_t off = total + wb + incl - c;
-    for (uint32_t k = 0; k < c; ++k) flat[off + k] = cand[(int64_t)blk * kAccTile + k];
-    total += tot;
-    __syncthreads();
-  }
-  __threadfence_block();
-  __syncthreads();
-  // ---- exact radix select (MSB first, 8 x 8 bits) of rank (qi - below) -------------------
-  if (t == 0) { sh_prefix = 0ull; sh_rank = sel.qi - sel.below; }
-  __syncthreads();
-  for (int pass = 7; pass >= 0; --pass) {
-    const int shift = pass * 8;
-    if (t < 256) sh_hist[t] = 0;
-    __syncthreads();
-    const unsigned long long prefix = sh_prefix;
-    const unsigned long long mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-    for (uint32_t k = t; k < total; k += kFinThreads) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(b.d2[flat[k]]);
-      if ((key & mask) == prefix) atomicAdd(&sh_hist[(key >> shift) & 255ull], 1u);
-    }
-    __syncthreads();
-    if (t == 0) {
-      int r = sh_rank;
-      int d = 0;
-      for (; d < 255; ++d) { const int c = (int)sh_hist[d]; if (r < c) break; r -= c; }
-      sh_rank = r;
-      sh_prefix = prefix | ((unsigned long long)d << shift);
-    }
-    __syncthreads();
-  }
-  const double limit = __longlong_as_double((long long)sh_prefix);
-  // ---- candidates with d2 <= limit (icp_fast.cc:497-498), ascending-index strided order ---
-  double acc[kNumSums];
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
-  for (uint32_t k = t; k < total; k += kFinThreads) {
-    const int i = (int)flat[k];
-    const double d2 = b.d2[i];
-    if (d2 <= limit) {
-      double px, py, pz; BucketPoint q; BucketNormal n;
-      load_match(b, T, i, px, py, pz, q, n);
-      accumulate_match(acc, px, py, pz, q, n, d2);
-    }
-  }
-  block_reduce_sums<kFinThreads>(acc, red, cand_sums);
-  // ---- fixed-order reduction of the phase-B partials -------------------------------------
-  if (w < kNumSums) {
-    double v = 0.0;
-    for (int blk = lane; blk < nblocks_b; blk += 32) v += b.partials[(int64_t)blk * 32 + w];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sums[w] = v;
-  }
-  // clear the histogram for the next iteration
-  for (int k = t; k < kHistBins; k += kFinThreads) b.hist[k] = 0;
-  __syncthreads();
-  if (t != 0) return;
-  // ---- serial tail: solve, pose update, convergence (icp_fast.cc:204-254,307-321,377-405) --
-  double S[kNumSums];
-  for (int k = 0; k < kNumSums; ++k) S[k] = sums[k] + cand_sums[k];
-  const double kept = S[28];
-  st->limit = limit;
-  st->kept = (long long)kept;
-  if (!(kept > 0.0)) { st->status = -3; st->done = 1; return; }  // "no point to minimize"
-  double A[36], rhs[6], x[6];
-  {
-    int k = 0;
-    for (int r = 0; r < 6; ++r)
-      for (int c = r; c < 6; ++c) { A[r * 6 + c] = S[k]; A[c * 6 + r] = S[k]; ++k; }
-    for (int r = 0; r < 6; ++r) rhs[r] = -S[21 + r];
-  }
-  st->solve_path = la::solve_possibly_underdetermined(A, rhs, x);
-  const double sq = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
-  const double angle = sqrt(sq);
-  double axis[3] = {x[0], x[1], x[2]};
-  if (sq > 0.0) { const double nr = sqrt(sq); axis[0] = x[0] / nr; axis[1] = x[1] / nr; axis[2] = x[2] / nr; }
-  double R[9];
-  la::angle_axis_to_rotation(angle, axis, R);
-  bool has_nan = false;
-  for (int i = 0; i < 9; ++i) has_nan |= isnan(R[i]);
-  for (int i = 3; i < 6; ++i) has_nan |= isnan(x[i]);
-  if (has_nan) { for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0; }
-  double dT[16], Tn[16];
-  for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) dT[r + 4 * c] = R[r * 3 + c];
-    dT[12 + r] = x[3 + r];
-  }
-  la::mul4(dT, T, Tn);
-  for (int i = 0; i < 16; ++i) st->T_iter[i] = Tn[i];
-  const int iteration = st->iteration + 1;
-  st->iteration = iteration;
-  // rotation / translation history ring (only the last 5 entries are ever read)
-  double Rm[9], qn[4];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Rm[r * 3 + c] = Tn[r + 4 * c];
-  la::rotation_to_quaternion(Rm, qn);
-  const int len = st->hist_len;
-  for (int k = 0; k < 4; ++k) st->quat_hist[len % 5][k] = qn[k];
-  for (int k = 0; k < 3; ++k) st->trans_hist[len % 5][k] = Tn[12 + k];
-  st->hist_len = len + 1;
-  bool conv = false;
-  if (!p.disable_convergence && len + 1 > 4) {
-    double rot = 0.0, tr = 0.0;
-    for (int i = len; i >= len + 1 - 4; --i) {
-      rot += fabs(la::quaternion_angular_distance(st->quat_hist[i % 5], st->quat_hist[(i - 1) % 5]));
-      const double dx = st->trans_hist[i % 5][0] - st->trans_hist[(i - 1) % 5][0];
-      const double dy = st->trans_hist[i % 5][1] - st->trans_hist[(i - 1) % 5][1];
-      const double dz = st->trans_hist[i % 5][2] - st->trans_hist[(i - 1) % 5][2];
-      tr += fabs(sqrt(dx * dx + dy * dy + dz * dz));
-    }
-    rot /= 4.0; tr /= 4.0;
-    conv = rot < 0.001 && tr < 0.01;
-  }
-  if (conv || iteration >= p.max_iteration) {
-    st->final_score = exp(-(S[27] / kept));
-    double tmp[16], res[16];
-    la::mul4(st->T_mean, Tn, tmp);           // (T_mean * T_iter) * G0, icp_fast.cc:527
-    la::mul4(tmp, st->G0, res);
-    for (int i = 0; i < 16; ++i) st->result[i] = res[i];
-    st->done = 1;
-  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -622,7 +254,7 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
     if (events) cudaEventRecord(events[4 * it + 1], stream);
     icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
     if (events) cudaEventRecord(events[4 * it + 2], stream);
-    icp_finish_kernel<<<1, kFinThreads, 0, stream>>>(b, p, nb);
+    icp_finish_launch(b, p, nb, stream);
     if (events) cudaEventRecord(events[4 * it + 3], stream);
   }
   SMB_CUDA_OK(cudaGetLastError());

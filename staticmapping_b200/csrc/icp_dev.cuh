@@ -1,0 +1,234 @@
+// Device-side building blocks of the ICP iteration shared by icp.cu (phases A, B) and
+// icp_finish.cu (phase C).  See icp.cu for the phase structure.
+#ifndef SM_B200_ICP_DEV_CUH_
+#define SM_B200_ICP_DEV_CUH_
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+namespace dev {
+
+constexpr int kKnnThreads = 256;
+constexpr int kAccThreads = 256;
+constexpr int kAccItems = 2;
+constexpr int kAccTile = kAccThreads * kAccItems;  // points per accumulate block
+constexpr int kNumSums = 29;                        // 21 (A upper) + 6 (b) + sum sqrt + count
+constexpr int kFinThreads = 1024;
+constexpr int kMaxStack = 32;
+
+// monotone bin of a non-negative finite double: 1/32-octave resolution over 2^-40..2^24
+__device__ __forceinline__ int dist_bin(double d2) {
+  const long long bits = __double_as_longlong(d2);
+  const int key = (int)(bits >> 47) - ((1023 - 40) << 5);
+  return min(max(key, 0), kHistBins - 1);
+}
+
+// second-level bin inside one first-level bin: the next 11 bits (valid when the first-level
+// bin is not one of the two clamp bins, i.e. all its members share bits 63..47)
+__device__ __forceinline__ int sub_bin(double d2) {
+  return (int)((__double_as_longlong(d2) >> 36) & 2047ll);
+}
+__device__ __forceinline__ bool clamp_bin(int bin) { return bin <= 0 || bin >= kHistBins - 1; }
+
+__device__ __forceinline__ bool finite_d2(double d) { return d < __longlong_as_double(0x7ff0000000000000ll); }
+
+// p = T (x) s with the reference's accumulation order (cloud_types.cc:288-296)
+__device__ __forceinline__ void transform_point(const double* __restrict__ T, double x, double y,
+                                                double z, double& px, double& py, double& pz) {
+  px = dadd(dadd(dadd(dmul(T[0], x), dmul(T[4], y)), dmul(T[8], z)), T[12]);
+  py = dadd(dadd(dadd(dmul(T[1], x), dmul(T[5], y)), dmul(T[9], z)), T[13]);
+  pz = dadd(dadd(dadd(dmul(T[2], x), dmul(T[6], y)), dmul(T[10], z)), T[14]);
+}
+
+__device__ __forceinline__ KdNode load_node(const KdNode* __restrict__ nodes, int h) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(nodes + h));
+  KdNode n;
+  n.cut = __hiloint2double(v.y, v.x);
+  n.dim = v.z; n.pad = v.w;
+  return n;
+}
+
+__device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, const KdNode& leaf,
+                                          double qx, double qy, double qz, double& head,
+                                          int& best) {
+  const long long packed = __double_as_longlong(leaf.cut);
+  const int first = (int)(packed & 0xffffffffll), count = (int)(packed >> 32);
+  for (int k = 0; k < count; ++k) {
+    const double2 xy = __ldg(reinterpret_cast<const double2*>(bpts + first + k));
+    const double z = __ldg(reinterpret_cast<const double*>(bpts + first + k) + 2);
+    const double dx = dsub(qx, xy.x), dy = dsub(qy, xy.y), dz = dsub(qz, z);
+    const double dist = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    if (dist < head) { head = dist; best = first + k; }  // strict: first visited wins
+  }
+}
+
+struct StackEntry {
+  double rd, ox, oy, oz;
+  int h;
+};
+
+// libnabo recurseKnn (k=1, allowSelfMatch, maxRadius=inf) made iterative.  A far subtree
+// is pushed only if it passes the pruning test against the head known at push time (the
+// head can only shrink, so this never drops a subtree the recursion would visit) and is
+// re-tested at pop time, which is exactly when the recursion tests it.  A read-only first
+// descent seeds the head so the stack stays almost empty for epsilon = 3.16.
+__device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
+                                     const BucketPoint* __restrict__ bpts, double qx, double qy,
+                                     double qz, double max_error2, int& best_slot, double& best_d2) {
+  double head = __longlong_as_double(0x7ff0000000000000ll);
+  int best = -1;
+  int h = 0;
+  KdNode nd = load_node(nodes, 0);
+  while (nd.dim != 3) {
+    const double q = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
+    h = 2 * h + 1 + ((dsub(q, nd.cut) > 0.0) ? 1 : 0);
+    nd = load_node(nodes, h);
+  }
+  const int leaf0 = h;
+  scan_leaf(bpts, nd, qx, qy, qz, head, best);
+
+  StackEntry stack[kMaxStack];
+  int sp = 0;
+  double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
+  h = 0;
+  while (true) {
+    while (true) {
+      nd = load_node(nodes, h);
+      if (nd.dim == 3) {
+        if (h != leaf0) scan_leaf(bpts, nd, qx, qy, qz, head, best);
+        break;
+      }
+      const int cd = nd.dim;
+      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+      const double new_off = dsub(q, nd.cut);
+      const int right = new_off > 0.0 ? 1 : 0;
+      // rd += - old_off*old_off + new_off*new_off
+      const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
+        StackEntry e;
+        e.rd = rd_new;
+        e.ox = cd == 0 ? new_off : ox;
+        e.oy = cd == 1 ? new_off : oy;
+        e.oz = cd == 2 ? new_off : oz;
+        e.h = 2 * h + 1 + (1 - right);
+        stack[sp++] = e;
+      }
+      h = 2 * h + 1 + right;
+    }
+    bool found = false;
+    while (sp > 0) {
+      const StackEntry e = stack[--sp];
+      if (dmul(e.rd, max_error2) < head) {
+        h = e.h; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+  best_slot = best;
+  best_d2 = head;
+}
+
+struct BinSel { int bin; int below; int qi; int nvalid; };
+
+// every block locates the quantile bin from the global histogram (2048 bins, 8 per thread
+// on the first 256 threads; all threads of the block must call this)
+__device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist, float ratio,
+                                             uint32_t* warp_tot /*[8]*/, BinSel* out_sm) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const bool active = t < 256;
+  uint32_t c[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { c[k] = active ? ghist[t * 8 + k] : 0u; s += c[k]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (active && lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww) { const uint32_t v = warp_tot[ww]; if (ww < w) base += v; total += v; }
+  const uint32_t excl = base + incl - s;
+  // icp_fast.cc:82-89: quantile == 1.0 -> max element, else index int(size * quantile)
+  const double q = (double)ratio;
+  int qi = (q == 1.0) ? (int)total - 1 : (int)((double)total * q);
+  if (qi > (int)total - 1) qi = (int)total - 1;
+  if (active && total > 0 && (uint32_t)qi >= excl && (uint32_t)qi < excl + s) {
+    uint32_t run = excl;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if ((uint32_t)qi >= run && (uint32_t)qi < run + c[k]) {
+        out_sm->bin = t * 8 + k; out_sm->below = (int)run;
+      }
+      run += c[k];
+    }
+    out_sm->qi = qi; out_sm->nvalid = (int)total;
+  }
+  if (total == 0 && t == 0) { out_sm->bin = -1; out_sm->below = 0; out_sm->qi = 0; out_sm->nvalid = 0; }
+  __syncthreads();
+  return *out_sm;
+}
+
+// contribution of one match to the normal equations (icp_fast.cc:268-302)
+__device__ __forceinline__ void accumulate_match(double* acc, double px, double py, double pz,
+                                                 const BucketPoint& q, const BucketNormal& n,
+                                                 double d2) {
+  double F[6];
+  F[0] = py * n.z - pz * n.y;
+  F[1] = pz * n.x - px * n.z;
+  F[2] = px * n.y - py * n.x;
+  F[3] = n.x; F[4] = n.y; F[5] = n.z;
+  const double dot = (px - q.x) * n.x + (py - q.y) * n.y + (pz - q.z) * n.z;
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c) acc[k++] += F[r] * F[c];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) acc[21 + r] += F[r] * dot;
+  acc[27] += sqrt(d2);
+  acc[28] += 1.0;
+}
+
+__device__ __forceinline__ void load_match(const IcpBuffers& b, const double* T, int i,
+                                           double& px, double& py, double& pz, BucketPoint& q,
+                                           BucketNormal& n) {
+  transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+  const int s = b.slot[i];
+  const double2 qxy = __ldg(reinterpret_cast<const double2*>(b.bpts + s));
+  q.x = qxy.x; q.y = qxy.y;
+  q.z = __ldg(reinterpret_cast<const double*>(b.bpts + s) + 2);
+  const double2 nxy = __ldg(reinterpret_cast<const double2*>(b.bnrm + s));
+  n.x = nxy.x; n.y = nxy.y;
+  n.z = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
+}
+
+// deterministic block reduction of kNumSums doubles (fixed shuffle tree, fixed warp order)
+template <int NT>
+__device__ __forceinline__ void block_reduce_sums(double* acc, double (*sm)[kNumSums], double* out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    double v = 0.0;
+    for (int ww = 0; ww < NT / 32; ++ww) v += sm[ww][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+}  // namespace dev
+}  // namespace smb
+
+#endif  // SM_B200_ICP_DEV_CUH_

@@ -82,8 +82,11 @@ struct IcpBuffers {
   // per-iteration
   int32_t* slot;          // [n_source] bucket slot of the match
   double* d2;             // [n_source]
-  uint32_t* hist;         // [kHistBins]
-  uint32_t* cand_idx;     // [n_source] per-block compacted candidates
+  uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
+  uint32_t* hist2;        // [kHistBins] second-level histogram inside the quantile bin (phase B)
+  double* sums;           // [32] reduced normal-equation sums of the iteration (phase C1 -> C2)
+  uint32_t* cand_idx;     // [blocks*tile] per-block compacted candidates, then [n_source] flat
+  unsigned long long* cand_key;  // same layout: bit pattern of the candidate's dist^2
   uint32_t* cand_cnt;     // [accum blocks]
   double* partials;       // [accum blocks][32]
   double* mean_partials;  // [blocks][4]
@@ -96,6 +99,7 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
 // events (optional): 4 per iteration — before A, after A, after B, after C
 int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
                            cudaStream_t stream, cudaEvent_t* events);
+void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, cudaStream_t stream);
 // stand-alone k-NN over an already built tree (parity tests): ids = original indices
 int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
               int nq, double max_error2, int32_t* ids, double* d2, cudaStream_t stream);

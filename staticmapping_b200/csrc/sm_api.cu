@@ -77,7 +77,7 @@ struct sm_handle {
   sm_align_info info;
   // device memory
   DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, nodes, leaf_order, bpts, bnrm, slot, d2, hist,
-      cand_idx, cand_cnt, partials, mean_partials, state, guess, kdws;
+      cand_idx, cand_key, cand_cnt, partials, mean_partials, state, guess, kdws;
   int64_t n_source = 0, n_target = 0, sstride = 0, tstride = 0;
   bool has_source = false, has_target = false;
   float ms_upload = 0.f;
@@ -189,8 +189,9 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
   H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t)));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
-  H_RC(h->hist.reserve(kHistBins * sizeof(uint32_t)));
+  H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
   H_RC(h->cand_idx.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(uint32_t)));
+  H_RC(h->cand_key.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(unsigned long long)));
   H_RC(h->cand_cnt.reserve((size_t)nb * sizeof(uint32_t)));
   H_RC(h->partials.reserve((size_t)nb * 32 * sizeof(double)));
   H_RC(h->mean_partials.reserve((size_t)ceil_div(nt, 1024) * 4 * sizeof(double)));
@@ -207,7 +208,10 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   b.bpts = (BucketPoint*)h->bpts.p; b.bnrm = (BucketNormal*)h->bnrm.p;
   b.src_raw = (double*)h->src_raw.p; b.src0 = (double*)h->src0.p; b.sstride = h->sstride;
   b.slot = (int32_t*)h->slot.p; b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
-  b.cand_idx = (uint32_t*)h->cand_idx.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
+  b.hist2 = b.hist + kHistBins;
+  b.sums = (double*)(b.hist + 2 * kHistBins + 64);
+  b.cand_idx = (uint32_t*)h->cand_idx.p;
+  b.cand_key = (unsigned long long*)h->cand_key.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
   b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
   b.state = (IcpState*)h->state.p;
   IcpParams p;
@@ -316,7 +320,7 @@ int sm_destroy(sm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->nodes,
-                    &h->leaf_order, &h->bpts, &h->bnrm, &h->slot, &h->d2, &h->hist, &h->cand_idx,
+                    &h->leaf_order, &h->bpts, &h->bnrm, &h->slot, &h->d2, &h->hist, &h->cand_idx, &h->cand_key,
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

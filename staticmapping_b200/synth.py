@@ -109,7 +109,9 @@ def lidar_scan(scene, sensor_xyz=(0.0, 0.0, 0.0), seed=0, n_beams=64, n_az=1875,
     (azimuth-major, beam-minor).  Rays without a return are re-drawn."""
     rng = np.random.default_rng(seed)
     elev = np.deg2rad(np.linspace(2.0, -24.8, n_beams))
-    az = np.arange(n_az) * (2.0 * np.pi / n_az)
+    # half-step offset: no ray has an exactly zero x or y component, so no leaf of
+    # CalculateNormals lies exactly in a plane through the sensor origin (singular M)
+    az = (np.arange(n_az) + 0.5) * (2.0 * np.pi / n_az)
     A, E = np.meshgrid(az, elev, indexing="ij")
     A = A.ravel().copy()
     E = E.ravel().copy()

@@ -75,6 +75,25 @@ def test_lidar_pair_parity(pair):
     assert dt <= TOL_T and dr <= TOL_R, (dt, dr)
     assert m.GetAlignInfo()["iterations"] == o["iterations"]
     assert abs(m.GetFitnessScore() - o["score"]) < 1e-6
+    # and the alignment is real: the perturbation is recovered (noise-limited)
+    gt_t, gt_r = scenes.se3_error(P, res)
+    assert gt_t < 5e-3 and gt_r < 1e-3, (gt_t, gt_r)
+    assert m.GetAlignInfo()["solve_path"] == 0
+
+
+def test_nan_normal_in_target_matches_oracle():
+    # A leaf lying exactly in a plane through the origin gives a NaN normal in the
+    # reference (cloud_types.cc:93, singular M).  IcpFast then sees a NaN normal matrix;
+    # the restated Eigen logic (rank 0 -> min-norm -> SVD) yields x = 0.  Same on both sides.
+    src, sub, P = scenes.lidar_pair(pair=0)
+    tp, tn = O.calculate_normals(sub)
+    tn = tn.copy(); tn[5] = np.nan
+    ok, res, m, o = _align_both(src, tp, tn, max_iteration=30)
+    assert o["rc"] == 1
+    assert np.array_equal(np.isnan(res), np.isnan(o["result"]))
+    fin = ~np.isnan(res)
+    assert np.allclose(res[fin], o["result"][fin], atol=1e-9)
+    assert m.GetAlignInfo()["iterations"] == o["iterations"]
 
 
 def test_fixed_iterations_and_guess():
