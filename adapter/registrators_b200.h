@@ -1,0 +1,104 @@
+// registrators_b200.h — drop-in C++ matcher for the StaticMapping tree, backed by
+// libsm_b200.so (C ABI: include/sm_b200.h).
+//
+// Compile this header INSIDE the reference tree (it needs the reference's own headers:
+// registrators/interface.h, builder/data/cloud_types.h, Eigen, glog).  It is not compiled in
+// the sm_b200 repository, where those dependencies do not exist; tests/test_adapter_syntax.py
+// checks its syntax against minimal stand-in headers.
+//
+//   registrator::IcpFastB200 replaces registrator::IcpFast (registrators/icp_fast.h:37-62):
+//   same base class, same overrides, same option names, same CHECK behaviour.
+#ifndef ADAPTER_REGISTRATORS_B200_H_
+#define ADAPTER_REGISTRATORS_B200_H_
+
+#include <memory>
+#include <string>
+
+#include "registrators/interface.h"
+#include "sm_b200.h"
+
+namespace static_map {
+namespace registrator {
+
+class IcpFastB200 : public Interface {
+ public:
+  USE_REGISTRATOR_CLOUDS;
+
+  explicit IcpFastB200(int device = 0) : Interface() {
+    this->type_ = kFastIcp;
+    const int rc = sm_create(SM_TYPE_FAST_ICP, device, &handle_);
+    CHECK_EQ(rc, 0) << "sm_create failed (" << rc << "): no CUDA device / no CPU fallback";
+    // same registry as IcpFast::IcpFast (icp_fast.cc:411-418): InitWithXml writes through
+    // these pointers, InitWithOptions forwards the values to the engine.
+    REG_REGISTRATOR_INNER_OPTION("knn_normal_estimate", OptionItemDataType::kInt32,
+                                 options_.knn_for_normal_estimate);
+    REG_REGISTRATOR_INNER_OPTION("max_iteration", OptionItemDataType::kInt32,
+                                 options_.max_iteration);
+    REG_REGISTRATOR_INNER_OPTION("dist_outlier_ratio", OptionItemDataType::kFloat32,
+                                 options_.dist_outlier_ratio);
+  }
+  ~IcpFastB200() override { sm_destroy(handle_); }
+
+  PROHIBIT_COPY_AND_ASSIGN(IcpFastB200);
+
+  void InitWithOptions() override {
+    Check(sm_set_option(handle_, "max_iteration", std::to_string(options_.max_iteration).c_str()));
+    Check(sm_set_option(handle_, "dist_outlier_ratio",
+                        std::to_string(options_.dist_outlier_ratio).c_str()));
+  }
+
+  // icp_fast.cc:421-425
+  void SetInputSource(InnerCloudPtr cloud) override {
+    CHECK(cloud);
+    CHECK(cloud->GetEigenCloud());
+    const auto& pts = cloud->GetEigenCloud()->points;          // 3xN, column-major doubles
+    Check(sm_set_input_source(handle_, pts.data(), pts.cols()));
+  }
+
+  // icp_fast.cc:427-431
+  void SetInputTarget(InnerCloudPtr cloud) override {
+    CHECK(cloud);
+    CHECK(cloud->GetEigenCloud());
+    CHECK(cloud->GetEigenCloud()->HasNormals());
+    const auto& ec = *cloud->GetEigenCloud();
+    Check(sm_set_input_target(handle_, ec.points.data(), ec.normals.data(), ec.points.cols()));
+  }
+
+  // icp_fast.cc:455-529
+  bool Align(const Eigen::Matrix4d& guess, Eigen::Matrix4d& result) override {  // NOLINT
+    const int rc = sm_align(handle_, guess.data(), result.data());  // both column-major
+    Check(rc);
+    this->final_score_ = sm_get_fitness_score(handle_);
+    return rc == 1;
+  }
+
+ private:
+  void Check(int rc) const {
+    CHECK_GE(rc, 0) << "sm_b200: " << sm_last_error(handle_);   // reference aborts via glog
+  }
+
+  sm_handle* handle_ = nullptr;
+  struct {
+    int32_t knn_for_normal_estimate = 7;
+    int32_t max_iteration = 100;
+    float dist_outlier_ratio = 0.7;
+  } options_;
+};
+
+// EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368); call sites
+// map_builder.cc:286,389 and submap.cc:161.
+inline void CalculateNormalsB200(data::EigenPointCloud* cloud, int device = 0) {
+  CHECK(cloud);
+  const int64_t n = cloud->points.cols();
+  Eigen::MatrixXd pts(3, n), nrm(3, n);
+  int64_t m = 0;
+  const int rc = sm_calculate_normals(device, cloud->points.data(), n, pts.data(), nrm.data(), &m);
+  CHECK_EQ(rc, 0) << "sm_calculate_normals failed";
+  cloud->points = pts.leftCols(m);
+  cloud->normals = nrm.leftCols(m);
+}
+
+}  // namespace registrator
+}  // namespace static_map
+
+#endif  // ADAPTER_REGISTRATORS_B200_H_

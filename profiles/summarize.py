@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Turn ncu outputs (brought back in gpurun_out/) into the small text summaries kept here.
+
+  python profiles/summarize.py launches <launches.csv>         -> per-kernel time shares
+  python profiles/summarize.py full <report.ncu-rep> [regex]   -> key metrics of a --set full capture
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("smb::<unnamed>::", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1000 if u in ("nsecond", "ns") else v * 1000 if u in ("msecond", "ms") else v
+        agg.setdefault(name, []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    print(f"{'kernel':44s} {'launches':>8s} {'sum_us':>10s} {'avg_us':>9s} {'share':>7s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{k[:44]:44s} {len(v):8d} {sum(v):10.1f} {sum(v)/len(v):9.2f} {sum(v)/tot:7.3f}")
+    print(f"{'TOTAL':44s} {sum(len(v) for v in agg.values()):8d} {tot:10.1f}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki = hdr.index("Kernel Name")
+    for r in data:
+        print("kernel:", r[ki][:100])
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"{k:70s} {units[i]:16s} {[r[i] for r in data]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
