@@ -41,6 +41,9 @@ N_SUBMAP = 500_000
 ITERATIONS = 30
 BYTES_PER_POINT_ITER = 64           # whole iteration
 BYTES_KNN_PER_POINT = 40            # of which the k-NN kernel: 16 src + 16 matched + 8 write
+# dram__bytes_read+write of icp_knn_kernel from the committed ncu --set full capture
+# (profiles/r01_ncu_full_icp_knn_*.txt; cold caches: ncu flushes between replays)
+NCU_TRAFFIC_BYTES = 24_157_696
 METRIC = "scan-pair alignments/sec (120k->500k pts, 30 ICP iters)"
 UNIT = "alignments/s"
 
@@ -173,12 +176,104 @@ def workload_config(n_target):
             "l2": "flushed between steps (256 MiB memset, outside the per-step events)"}
 
 
+class Worker:
+    """One alignment pipeline: its own matcher handle, CUDA stream and scan pair."""
+
+    def __init__(self, smb, torch, dev, local_rank, pair):
+        self.smb, self.torch = smb, torch
+        self.src, sub, self.P = make_workload(pair)
+        tgt = smb.CalculateNormals(sub, device=local_rank)      # target prep on the GPU
+        self.tp, self.tn = tgt.points, tgt.normals
+        self.nt = self.tp.shape[0]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.m = smb.IcpFast(local_rank)
+        self.m.InitWithXml({"max_iteration": ITERATIONS, "disable_convergence_check": 1})
+        self.m.SetStream(self.stream.cuda_stream)
+        self.d_src = torch.from_numpy(self.src).to(dev)
+        self.d_tp = torch.from_numpy(self.tp).to(dev)
+        self.d_tn = torch.from_numpy(self.tn).to(dev)
+        self.h_src = torch.from_numpy(self.src).pin_memory()
+        self.h_tp = torch.from_numpy(self.tp).pin_memory()
+        self.h_tn = torch.from_numpy(self.tn).pin_memory()
+        self.guess = np.eye(4)
+        self.launches = 0
+        self.last = None
+
+    def step_device(self):
+        m = self.m
+        m.SetInputTargetDevice(self.d_tp.data_ptr(), self.d_tn.data_ptr(), self.nt)
+        m.SetInputSourceDevice(self.d_src.data_ptr(), N_SOURCE)
+        ok, res = m.Align(self.guess)
+        self.launches += m.GetAlignInfo()["kernel_launches"] + 3
+        self.last = (res, m.GetFitnessScore())
+        return res
+
+    def step_host(self):
+        m = self.m
+        m._check(m._lib.sm_set_input_target(m._h, self.h_tp.data_ptr(), self.h_tn.data_ptr(), self.nt),
+                 "SetInputTarget")
+        m._check(m._lib.sm_set_input_source(m._h, self.h_src.data_ptr(), N_SOURCE), "SetInputSource")
+        ok, res = m.Align(self.guess)
+        self.launches += m.GetAlignInfo()["kernel_launches"] + 3
+        self.last = (res, m.GetFitnessScore())
+        return res
+
+    @property
+    def h2d_bytes(self):
+        return int(self.src.nbytes + self.tp.nbytes + self.tn.nbytes + 128)
+
+
+def run_concurrent(torch, workers, steps, host):
+    """`steps` alignments spread round-robin over the workers, all in flight together.
+    Device time of the whole region: an event before (every worker stream waits on it) and
+    an event after (it waits on every worker's last kernel), both on one timing stream."""
+    share = [len(range(w, steps, len(workers))) for w in range(len(workers))]
+    tstream = torch.cuda.Stream()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    results = [[] for _ in workers]
+    gate = threading.Barrier(len(workers) + 1)
+    errors = []
+
+    def body(i):
+        w = workers[i]
+        try:
+            gate.wait()
+            for _ in range(share[i]):
+                results[i].append((w.step_host() if host else w.step_device(), w.last[1]))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+        w.done = torch.cuda.Event()
+        w.done.record(w.stream)
+
+    threads = [threading.Thread(target=body, args=(i,)) for i in range(len(workers))]
+    for t in threads:
+        t.start()
+    torch.cuda.synchronize()
+    e0.record(tstream)
+    for w in workers:
+        w.stream.wait_event(e0)
+    gate.wait()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    for w in workers:
+        tstream.wait_event(w.done)
+    e1.record(tstream)
+    e1.synchronize()
+    return e0.elapsed_time(e1), results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--inflight", type=int, default=8,
+                    help="alignments in flight per GPU (the reference runs 5-6 concurrent Align "
+                         "calls from its thread pool / TBB tasks)")
     ap.add_argument("--cpu-baseline-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -194,6 +289,7 @@ def main():
     import torch
     import torch.distributed as dist
     import staticmapping_b200 as smb
+    from staticmapping_b200 import parallel
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (staticmapping_b200 has no CPU fallback)")
@@ -203,53 +299,26 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs: each rank owns its pair; target prep runs on the GPU (product path) ------
-    src, sub, P = make_workload(rank)
-    tgt = smb.CalculateNormals(sub, device=local_rank)
-    tp, tn = tgt.points, tgt.normals
-    nt = tp.shape[0]
-    stream = torch.cuda.Stream(device=dev)
-    m = smb.IcpFast(local_rank)
-    m.InitWithXml({"max_iteration": ITERATIONS, "disable_convergence_check": 1})
-    m.SetStream(stream.cuda_stream)
-    d_src = torch.from_numpy(src).to(dev)
-    d_tp = torch.from_numpy(tp).to(dev)
-    d_tn = torch.from_numpy(tn).to(dev)
-    h_src = torch.from_numpy(src).pin_memory()
-    h_tp = torch.from_numpy(tp).pin_memory()
-    h_tn = torch.from_numpy(tn).pin_memory()
+    # ---- inputs: every worker of every rank owns a distinct scan pair -----------------------
+    P = max(1, args.inflight)
+    workers = [Worker(smb, torch, dev, local_rank, rank * P + w) for w in range(P)]
+    w0 = workers[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    guess = np.eye(4)
-    launches = [0]
 
-    def step_device():
-        m.SetInputTargetDevice(d_tp.data_ptr(), d_tn.data_ptr(), nt)
-        m.SetInputSourceDevice(d_src.data_ptr(), N_SOURCE)
-        ok, res = m.Align(guess)
-        launches[0] += m.GetAlignInfo()["kernel_launches"] + 3
-        return res
-
-    def step_host():
-        m._check(m._lib.sm_set_input_target(m._h, h_tp.data_ptr(), h_tn.data_ptr(), nt), "SetInputTarget")
-        m._check(m._lib.sm_set_input_source(m._h, h_src.data_ptr(), N_SOURCE), "SetInputSource")
-        ok, res = m.Align(guess)
-        launches[0] += m.GetAlignInfo()["kernel_launches"] + 3
-        return res
-
-    def timed(step_fn, k):
-        """K steps, each bracketed by events on the engine's stream; L2 flushed in between."""
-        total_ms, results = 0.0, []
+    def timed_serial(step_fn, k, stream):
+        """K steps, one in flight, each bracketed by events; L2 flushed before each."""
+        total_ms = 0.0
         with torch.cuda.stream(stream):
             for _ in range(k):
                 flush.zero_()
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                results.append(step_fn())
+                step_fn()
                 e1.record(stream)
                 e1.synchronize()
                 total_ms += e0.elapsed_time(e1)
-        return total_ms, results
+        return total_ms
 
     def barrier():
         if world > 1:
@@ -263,41 +332,50 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up, then the timed region ----------------------------------------------------
-    timed(step_device, args.warmup)
-    timed(step_host, args.warmup)
-    res_check = step_device()
+    # ---- warm-up ---------------------------------------------------------------------------
+    run_concurrent(torch, workers, args.warmup * P, host=False)
+    run_concurrent(torch, workers, args.warmup * P, host=True)
+    res_check = w0.step_device()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    launches[0] = 0
-    ms_dev, results = timed(step_device, args.steps)
-    gpu_launches = launches[0]
-    # the one collective of the path: all-gather of the poses (16 doubles + score per pair)
+    # ---- timed: device-resident inputs, P alignments in flight --------------------------------
+    for w in workers:
+        w.launches = 0
+    ms_dev, results = run_concurrent(torch, workers, args.steps, host=False)
+    gpu_launches = sum(w.launches for w in workers)
+    # the one collective of the path: all-gather of the poses (17 doubles per pair)
     allgather_ms = 0.0
     if world > 1:
-        poses = torch.tensor(np.stack([np.append(r.T.ravel(), 0.0) for r in results]), device=dev)
-        out = [torch.empty_like(poses) for _ in range(world)]
+        flat = [r for per in results for r in per]
+        rec = parallel.pack_poses([r[0] for r in flat], [r[1] for r in flat])
+        t = torch.from_numpy(rec).to(dev)
+        out = [torch.empty_like(t) for _ in range(world)]
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.all_gather(out, poses); e1.record(); e1.synchronize()
+        e0.record(); dist.all_gather(out, t); e1.record(); e1.synchronize()
         allgather_ms = e0.elapsed_time(e1)
     barrier()
     ms_dev_total = max_over_ranks(ms_dev + allgather_ms)
+    # ---- timed: host buffers through the public API (H2D inside) ---------------------------
     barrier()
-    ms_e2e, _ = timed(step_host, args.steps)
+    ms_e2e, _ = run_concurrent(torch, workers, args.steps, host=True)
     barrier()
     ms_e2e_total = max_over_ranks(ms_e2e)
+    # ---- latency: one alignment in flight, L2 flushed before each -----------------------------
+    lat_steps = max(3, min(10, args.steps))
+    ms_lat_dev = timed_serial(w0.step_device, lat_steps, w0.stream) / lat_steps
+    ms_lat_host = timed_serial(w0.step_host, lat_steps, w0.stream) / lat_steps
     # ---- dominant-kernel timing: extra profiled steps, events around every launch ----------
-    m.InitWithXml({"profile_kernels": 1})
-    timed(step_device, 1)
+    w0.m.InitWithXml({"profile_kernels": 1})
+    timed_serial(w0.step_device, 1, w0.stream)
     prof = {"knn": 0.0, "accum": 0.0, "finish": 0.0, "prologue": 0.0, "n": 0}
     for _ in range(3):
-        timed(step_device, 1)
-        info = m.GetAlignInfo()
+        timed_serial(w0.step_device, 1, w0.stream)
+        info = w0.m.GetAlignInfo()
         prof["knn"] += info["ms_knn"]; prof["accum"] += info["ms_accum"]
         prof["finish"] += info["ms_finish"]; prof["prologue"] += info["ms_prologue"]
         prof["n"] += 1
-    m.InitWithXml({"profile_kernels": 0})
+    w0.m.InitWithXml({"profile_kernels": 0})
     clocks = sampler.stop()
 
     value = args.steps * world / (ms_dev_total * 1e-3)
@@ -310,34 +388,40 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_KNN_PER_POINT * N_SOURCE / (knn_ms * 1e-3) / 1e9
+    iter_ms = (prof["knn"] + prof["accum"] + prof["finish"]) / prof["n"]
     roofline = {"bound": "hbm", "kernel": "icp_knn_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "avg_launch_ms": knn_ms,
                 "bytes_per_launch": BYTES_KNN_PER_POINT * N_SOURCE,
-                "how": "CUDA events around every launch of 3 extra profiled alignments run "
-                       "right after the timed region (same stream, same inputs)",
+                "how": "CUDA events around every launch of 3 extra profiled alignments (one in "
+                       "flight) run right after the timed region, same stream and inputs; the "
+                       "working set is L2-resident, so this is a latency-bound kernel",
                 "per_alignment_ms": {k: prof[k] / prof["n"] for k in ("prologue", "knn", "accum", "finish")},
-                "iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS /
-                                         ((prof["knn"] + prof["accum"] + prof["finish"]) / prof["n"] * 1e-3)
-                                         / 1e9) / peak}
+                "iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS / (iter_ms * 1e-3) / 1e9) / peak,
+                "aggregate_iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS * value / world / 1e9) / peak}
 
+    cfg = workload_config(w0.nt)
+    cfg["pairs_in_flight_per_gpu"] = P
+    cfg["l2"] = (f"{P} distinct pairs in flight per GPU (combined working set ~{25 * P} MB vs 126 MB L2); "
+                 "the latency figures flush L2 (256 MiB memset) before every step")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(nt),
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(src.nbytes + tp.nbytes + tn.nbytes + 128),
+        "data": "synthetic", "config": cfg,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w0.h2d_bytes,
                 "d2h_bytes_per_step": 128 + 400, "ms_per_step": ms_e2e_total / args.steps},
+        "latency": {"ms_per_alignment_device": ms_lat_dev, "ms_per_alignment_host_buffers": ms_lat_host,
+                    "in_flight": 1, "icp_iterations_per_s": ITERATIONS / (iter_ms * 1e-3)},
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
         "allgather_ms": allgather_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         O = oracle_module()
-        ts = cpu_time_alignment(O, src, tp, tn, args.cpu_baseline_reps)
+        ts = cpu_time_alignment(O, w0.src, w0.tp, w0.tn, args.cpu_baseline_reps)
         # parity spot check of the benchmarked configuration against the oracle
-        o = O.icp_fast_align(src, tp, tn, max_iteration=ITERATIONS, disable_convergence_check=True)
+        o = O.icp_fast_align(w0.src, w0.tp, w0.tn, max_iteration=ITERATIONS, disable_convergence_check=True)
         E = np.linalg.inv(o["result"]) @ res_check
         out["parity_vs_oracle"] = {"dt_m": float(np.linalg.norm(E[:3, 3])),
                                    "dr_rad": float(np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)))}

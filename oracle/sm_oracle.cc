@@ -195,10 +195,12 @@ struct KdTree {
   }
 
   // recurseKnn, k = 1, allowSelfMatch, maxRadius2 = inf.
+  mutable int* visit_counter = nullptr;  // optional: leaves visited by the current query
   void Recurse(const double* q, int n_idx, double rd, double off[3], double max_error2,
-               double& head, int& head_idx) const {
+               double& head, int& head_idx, int* visits = nullptr) const {
     const KdNode& node = nodes[(size_t)n_idx];
     if (node.dim == 3) {
+      if (visits) ++*visits;
       for (int i = 0; i < node.bucket_count; ++i) {
         const int index = buckets[(size_t)(node.bucket_first + i)];
         const double* p = cloud + 3 * (size_t)index;
@@ -216,24 +218,26 @@ struct KdTree {
     const double new_off = q[cd] - node.cut_val;
     const int near = (new_off > 0.0) ? node.right_child : n_idx + 1;
     const int far = (new_off > 0.0) ? n_idx + 1 : node.right_child;
-    Recurse(q, near, rd, off, max_error2, head, head_idx);
+    Recurse(q, near, rd, off, max_error2, head, head_idx, visits);
     rd += -old_off * old_off + new_off * new_off;
     if (rd <= kInf && rd * max_error2 < head) {
       off[cd] = new_off;
-      Recurse(q, far, rd, off, max_error2, head, head_idx);
+      Recurse(q, far, rd, off, max_error2, head, head_idx, visits);
       off[cd] = old_off;
     }
   }
 
   void Knn1(const double* query, int64_t nq, double epsilon, int32_t* ids,
-            double* d2) const {
+            double* d2, int32_t* visits = nullptr) const {
     const double max_error2 = (1.0 + epsilon) * (1.0 + epsilon);
 #pragma omp parallel for schedule(guided, 32)
     for (int64_t i = 0; i < nq; ++i) {
       double off[3] = {0.0, 0.0, 0.0};
       double head = kInf;
       int head_idx = -1;
-      if (!nodes.empty()) Recurse(query + 3 * i, 0, 0.0, off, max_error2, head, head_idx);
+      int nv = 0;
+      if (!nodes.empty()) Recurse(query + 3 * i, 0, 0.0, off, max_error2, head, head_idx, &nv);
+      if (visits) visits[i] = nv;
       ids[i] = head_idx;
       d2[i] = head;
     }
@@ -383,6 +387,16 @@ int sm_oracle_knn1(const double* target, int64_t n_target, const double* query,
   KdTree tree;
   tree.Build(target, n_target, bucket_size, tie_mode);
   tree.Knn1(query, n_query, epsilon, ids_out, dists2_out);
+  return 0;
+}
+
+int sm_oracle_knn1_visits(const double* target, int64_t n_target, const double* query,
+                          int64_t n_query, double epsilon, int bucket_size, int32_t* visits_out) {
+  KdTree tree;
+  tree.Build(target, n_target, bucket_size, 0);
+  std::vector<int32_t> ids((size_t)n_query);
+  std::vector<double> d2((size_t)n_query);
+  tree.Knn1(query, n_query, epsilon, ids.data(), d2.data(), visits_out);
   return 0;
 }
 

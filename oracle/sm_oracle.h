@@ -43,6 +43,10 @@ int sm_oracle_knn1(const double* target, int64_t n_target, const double* query,
                    int64_t n_query, double epsilon, int bucket_size, int tie_mode,
                    int32_t* ids_out, double* dists2_out);
 
+/* Diagnostics: number of leaf buckets each query visits (traversal cost model). */
+int sm_oracle_knn1_visits(const double* target, int64_t n_target, const double* query,
+                          int64_t n_query, double epsilon, int bucket_size, int32_t* visits_out);
+
 /* Exhaustive 1-NN (first minimum wins) — independent check for the two above. */
 int sm_oracle_knn1_brute(const double* target, int64_t n_target, const double* query,
                          int64_t n_query, int32_t* ids_out, double* dists2_out);

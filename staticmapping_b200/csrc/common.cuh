@@ -51,6 +51,26 @@ struct __align__(16) KdNode {
   int pad;
 };
 
+// Node storage order: the implicit heap (children of h are 2h+1 / 2h+2) is cut into blocks of
+// 3 levels = 7 nodes that share one 128-byte line (8 slots of 16 B, slot 7 unused); the blocks
+// themselves form an 8-ary heap.  A root-to-leaf descent of L levels touches ceil((L+1)/3)
+// lines instead of L+1.  heap index h -> slot index (block * 8 + local).
+__host__ __device__ __forceinline__ int blocked_index(int h) {
+  int l = 0;
+  while (((h + 1) >> (l + 1)) != 0) ++l;      // floor(log2(h+1))
+  const int j = h + 1 - (1 << l);
+  const int bl = l / 3, sl = l % 3;
+  const int base = ((1 << (3 * bl)) - 1) / 7;
+  const int B = base + (j >> sl);
+  const int p = (1 << sl) - 1 + (j & ((1 << sl) - 1));
+  return B * 8 + p;
+}
+// number of 16-byte node slots needed for a tree whose deepest level index is `levels`
+__host__ __device__ __forceinline__ int64_t blocked_node_slots(int levels) {
+  const int nbl = levels / 3 + 1;
+  return ((((int64_t)1 << (3 * nbl)) - 1) / 7) * 8;
+}
+
 // bucket entry: target point in leaf order (two LDG.128)
 struct __align__(32) BucketPoint {
   double x, y, z;

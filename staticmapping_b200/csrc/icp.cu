@@ -105,13 +105,40 @@ __global__ void icp_init_kernel(IcpState* __restrict__ st, const double* __restr
   st->final_score = 0.0; st->limit = 0.0; st->kept = 0;
 }
 
+// 30-bit Morton key on a 0.25 m lattice (coordinates wrap every 256 m, harmless for a key
+// that only has to make neighbouring threads spatially close)
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// init_source = G0 (x) source (icp_fast.cc:469-471) + the spatial sort key of each point
 __global__ void apply_g0_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                int64_t stride, int n, const IcpState* __restrict__ st) {
+                                int64_t stride, int n, const IcpState* __restrict__ st,
+                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double px, py, pz;
   transform_point(st->G0, in[i], in[stride + i], in[2 * stride + i], px, py, pz);
   out[i] = px; out[stride + i] = py; out[2 * stride + i] = pz;
+  const uint32_t ix = (uint32_t)(int)floor(px * 4.0), iy = (uint32_t)(int)floor(py * 4.0),
+                 iz = (uint32_t)(int)floor(pz * 4.0);
+  keys[i] = (uint64_t)(spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2));
+  vals[i] = (uint32_t)i;
+}
+
+// queries in Morton order: neighbouring threads walk the same tree lines and hit the same
+// buckets.  Only sums are formed over the source, so its order is free.
+__global__ void gather_source_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                     int64_t stride, int n, const uint32_t* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = perm[i];
+  out[i] = in[s]; out[stride + i] = in[stride + s]; out[2 * stride + i] = in[2 * stride + s];
 }
 
 // -------------------------------------------------------------------------------- phase A
@@ -240,7 +267,13 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   rc = kd_fill_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, b.bpts, b.bnrm, stream);
   if (rc) return rc;
   icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist);
-  apply_g0_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_raw, b.src0, b.sstride, ns, b.state);
+  apply_g0_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_raw, b.src_g0, b.sstride, ns, b.state,
+                                                        b.src_keys[0], b.src_vals[0]);
+  rc = radix_sort_pairs_u64(b.src_keys[0], b.src_vals[0], b.src_keys[1], b.src_vals[1], ns, 1,
+                            b.sstride, b.src_scratch, stream, 4);
+  if (rc) return rc;
+  gather_source_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_g0, b.src0, b.sstride, ns,
+                                                             b.src_vals[0]);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -49,84 +49,107 @@ __device__ __forceinline__ KdNode load_node(const KdNode* __restrict__ nodes, in
   return n;
 }
 
+// Scan one bucket.  All 8 entries are fetched up front (the bucket array is padded by 8
+// entries, so reading past `count` is safe) so the loads overlap instead of paying one L2
+// round trip per point; entries >= count are ignored.  Strict '<': first visited wins.
 __device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, const KdNode& leaf,
                                           double qx, double qy, double qz, double& head,
                                           int& best) {
   const long long packed = __double_as_longlong(leaf.cut);
   const int first = (int)(packed & 0xffffffffll), count = (int)(packed >> 32);
-  for (int k = 0; k < count; ++k) {
-    const double2 xy = __ldg(reinterpret_cast<const double2*>(bpts + first + k));
-    const double z = __ldg(reinterpret_cast<const double*>(bpts + first + k) + 2);
-    const double dx = dsub(qx, xy.x), dy = dsub(qy, xy.y), dz = dsub(qz, z);
+  double2 xy[8];
+  double z[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    xy[k] = __ldg(reinterpret_cast<const double2*>(bpts + first + k));
+    z[k] = __ldg(reinterpret_cast<const double*>(bpts + first + k) + 2);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double dx = dsub(qx, xy[k].x), dy = dsub(qy, xy[k].y), dz = dsub(qz, z[k]);
     const double dist = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
-    if (dist < head) { head = dist; best = first + k; }  // strict: first visited wins
+    if (k < count && dist < head) { head = dist; best = first + k; }
   }
 }
 
 struct StackEntry {
   double rd, ox, oy, oz;
-  int h;
+  int idx;
 };
+
+// child of the node at blocked index `idx` (see blocked_index in common.cuh): inside a
+// 7-node block the local heap rule applies; leaving a block jumps to one of its 8 child blocks.
+__device__ __forceinline__ int child_idx(int idx, int right) {
+  const int p = idx & 7, B = idx >> 3;
+  return (p < 3) ? ((B << 3) | (2 * p + 1 + right))
+                 : ((8 * B + 1 + (((p - 3) << 1) | right)) << 3);
+}
 
 // libnabo recurseKnn (k=1, allowSelfMatch, maxRadius=inf) made iterative.  A far subtree
 // is pushed only if it passes the pruning test against the head known at push time (the
 // head can only shrink, so this never drops a subtree the recursion would visit) and is
 // re-tested at pop time, which is exactly when the recursion tests it.  A read-only first
-// descent seeds the head so the stack stays almost empty for epsilon = 3.16.
+// descent seeds the head; along it rd_new == new_off^2 exactly (rd = 0, all offsets 0), so
+// if min(new_off^2)*(1+eps)^2 >= head no far subtree can ever qualify and we are done.
 __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
                                      const BucketPoint* __restrict__ bpts, double qx, double qy,
                                      double qz, double max_error2, int& best_slot, double& best_d2) {
-  double head = __longlong_as_double(0x7ff0000000000000ll);
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double head = inf;
   int best = -1;
-  int h = 0;
+  int idx = 0;
+  double min_off2 = inf;
   KdNode nd = load_node(nodes, 0);
   while (nd.dim != 3) {
     const double q = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
-    h = 2 * h + 1 + ((dsub(q, nd.cut) > 0.0) ? 1 : 0);
-    nd = load_node(nodes, h);
+    const double off = dsub(q, nd.cut);
+    min_off2 = fmin(min_off2, dmul(off, off));
+    idx = child_idx(idx, (off > 0.0) ? 1 : 0);
+    nd = load_node(nodes, idx);
   }
-  const int leaf0 = h;
+  const int leaf0 = idx;
   scan_leaf(bpts, nd, qx, qy, qz, head, best);
-
-  StackEntry stack[kMaxStack];
-  int sp = 0;
-  double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
-  h = 0;
-  while (true) {
+  if (dmul(min_off2, max_error2) < head) {
+    StackEntry stack[kMaxStack];
+    int sp = 0;
+    double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
+    idx = 0;
     while (true) {
-      nd = load_node(nodes, h);
-      if (nd.dim == 3) {
-        if (h != leaf0) scan_leaf(bpts, nd, qx, qy, qz, head, best);
-        break;
+      // descend to a leaf; every lane leaves this loop before any lane scans its bucket, so
+      // the bucket scan is executed once per round by the whole warp
+      nd = load_node(nodes, idx);
+      while (nd.dim != 3) {
+        const int cd = nd.dim;
+        const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+        const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+        const double new_off = dsub(q, nd.cut);
+        const int right = new_off > 0.0 ? 1 : 0;
+        // rd += - old_off*old_off + new_off*new_off
+        const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+        if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
+          StackEntry e;
+          e.rd = rd_new;
+          e.ox = cd == 0 ? new_off : ox;
+          e.oy = cd == 1 ? new_off : oy;
+          e.oz = cd == 2 ? new_off : oz;
+          e.idx = child_idx(idx, 1 - right);
+          stack[sp++] = e;
+        }
+        idx = child_idx(idx, right);
+        nd = load_node(nodes, idx);
       }
-      const int cd = nd.dim;
-      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
-      const double new_off = dsub(q, nd.cut);
-      const int right = new_off > 0.0 ? 1 : 0;
-      // rd += - old_off*old_off + new_off*new_off
-      const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
-        StackEntry e;
-        e.rd = rd_new;
-        e.ox = cd == 0 ? new_off : ox;
-        e.oy = cd == 1 ? new_off : oy;
-        e.oz = cd == 2 ? new_off : oz;
-        e.h = 2 * h + 1 + (1 - right);
-        stack[sp++] = e;
+      if (idx != leaf0) scan_leaf(bpts, nd, qx, qy, qz, head, best);
+      bool found = false;
+      while (sp > 0) {
+        const StackEntry e = stack[--sp];
+        if (dmul(e.rd, max_error2) < head) {
+          idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+          found = true;
+          break;
+        }
       }
-      h = 2 * h + 1 + right;
+      if (!found) break;
     }
-    bool found = false;
-    while (sp > 0) {
-      const StackEntry e = stack[--sp];
-      if (dmul(e.rd, max_error2) < head) {
-        h = e.h; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
-        found = true;
-        break;
-      }
-    }
-    if (!found) break;
   }
   best_slot = best;
   best_d2 = head;

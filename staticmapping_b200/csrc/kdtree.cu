@@ -72,7 +72,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
     KdNode leaf;
     leaf.cut = __longlong_as_double(((long long)s.count << 32) | (long long)(unsigned)s.first);
     leaf.dim = 3; leaf.pad = 0;
-    nodes[h] = leaf;
+    nodes[blocked_index(h)] = leaf;
     level_dim[j] = 3;
     return;
   }
@@ -93,7 +93,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
   const uint32_t pid = lists[dim * lstride + s.first + left];
   const double cut = coord[dim * cstride + pid];
   KdNode nd; nd.cut = cut; nd.dim = dim; nd.pad = 0;
-  nodes[h] = nd;
+  nodes[blocked_index(h)] = nd;
   level_dim[j] = dim;
   double* bl = bounds_out + (int64_t)(2 * j) * 6;
   double* br = bounds_out + (int64_t)(2 * j + 1) * 6;
@@ -206,7 +206,7 @@ __global__ void kd_leaf_kernel(const uint32_t* __restrict__ list0, int n, int bu
   KdNode leaf;
   leaf.cut = __longlong_as_double(((long long)s.count << 32) | (long long)(unsigned)s.first);
   leaf.dim = 3; leaf.pad = 0;
-  nodes[h] = leaf;
+  nodes[blocked_index(h)] = leaf;
   uint32_t ids[16];
   for (int k = 0; k < s.count; ++k) ids[k] = list0[s.first + k];
   for (int a = 1; a < s.count; ++a) {  // insertion sort, count <= bucket <= 16

@@ -13,7 +13,7 @@ namespace smb {
 size_t radix_sort_scratch_bytes(int n, int batch);
 int radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                          int n, int batch, int64_t stride, uint32_t* scratch,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int passes = 8);
 // exclusive scan of `count` u32 per batch (in place), one block per batch
 void radix_scan_kernel_launch(uint32_t* data, int count, int batch, cudaStream_t stream);
 
@@ -77,7 +77,11 @@ struct IcpBuffers {
   BucketNormal* bnrm;
   // source
   double* src_raw;        // [3][sstride] as uploaded
-  double* src0;           // [3][sstride] after G0
+  double* src_g0;         // [3][sstride] after G0, caller order
+  double* src0;           // [3][sstride] after G0, Morton order (what the iterations read)
+  uint64_t* src_keys[2];  // Morton keys (ping-pong)
+  uint32_t* src_vals[2];  // permutation (ping-pong)
+  uint32_t* src_scratch;  // radix scratch
   int64_t sstride;
   // per-iteration
   int32_t* slot;          // [n_source] bucket slot of the match

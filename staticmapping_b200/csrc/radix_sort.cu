@@ -137,16 +137,17 @@ size_t radix_sort_scratch_bytes(int n, int batch) {
 }
 
 // Sorts keys_a/vals_a (layout [batch][stride]); keys_b/vals_b are ping-pong buffers.
-// After the 8 passes the sorted data is back in the *_a buffers.
+// `passes` 8-bit digits are sorted starting from bit 0 (8 = full 64-bit keys); for an even
+// number of passes the sorted data ends in the *_a buffers, otherwise in *_b.
 int radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                          int n, int batch, int64_t stride, uint32_t* scratch,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int passes) {
   if (n <= 0) return 0;
   const int nblk = ceil_div(n, kTile);
   const dim3 grid(nblk, batch);
   uint64_t* kin = keys_a; uint32_t* vin = vals_a;
   uint64_t* kout = keys_b; uint32_t* vout = vals_b;
-  for (int pass = 0; pass < 8; ++pass) {
+  for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * 8;
     radix_hist_kernel<<<grid, kThreads, 0, stream>>>(kin, n, stride, shift, scratch, nblk);
     radix_scan_kernel<<<batch, 1024, 0, stream>>>(scratch, 256 * nblk);

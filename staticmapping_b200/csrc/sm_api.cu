@@ -76,7 +76,7 @@ struct sm_handle {
   double final_score = 0.0;
   sm_align_info info;
   // device memory
-  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, nodes, leaf_order, bpts, bnrm, slot, d2, hist,
+  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, src_g0, src_sort, nodes, leaf_order, bpts, bnrm, slot, d2, hist,
       cand_idx, cand_key, cand_cnt, partials, mean_partials, state, guess, kdws;
   int64_t n_source = 0, n_target = 0, sstride = 0, tstride = 0;
   bool has_source = false, has_target = false;
@@ -183,9 +183,11 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   const int nb = icp_accum_blocks(ns);
   H_RC(h->tgt.reserve((size_t)(3 * h->tstride) * sizeof(double)));
   H_RC(h->src0.reserve((size_t)(3 * h->sstride) * sizeof(double)));
-  H_RC(h->nodes.reserve((((size_t)1 << (levels + 1))) * sizeof(KdNode)));
+  H_RC(h->src_g0.reserve((size_t)(3 * h->sstride) * sizeof(double)));
+  H_RC(h->src_sort.reserve((size_t)h->sstride * 24 + radix_sort_scratch_bytes(ns, 1) + 1024));
+  H_RC(h->nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
-  H_RC(h->bpts.reserve((size_t)nt * sizeof(BucketPoint)));
+  H_RC(h->bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
   H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
   H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t)));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
@@ -207,6 +209,10 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   b.nodes = (KdNode*)h->nodes.p; b.leaf_order = (uint32_t*)h->leaf_order.p;
   b.bpts = (BucketPoint*)h->bpts.p; b.bnrm = (BucketNormal*)h->bnrm.p;
   b.src_raw = (double*)h->src_raw.p; b.src0 = (double*)h->src0.p; b.sstride = h->sstride;
+  b.src_g0 = (double*)h->src_g0.p;
+  b.src_keys[0] = (uint64_t*)h->src_sort.p; b.src_keys[1] = b.src_keys[0] + h->sstride;
+  b.src_vals[0] = (uint32_t*)(b.src_keys[1] + h->sstride); b.src_vals[1] = b.src_vals[0] + h->sstride;
+  b.src_scratch = b.src_vals[1] + h->sstride;
   b.slot = (int32_t*)h->slot.p; b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
@@ -226,7 +232,7 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   H_CUDA(cudaEventRecord(h->ev[0], h->stream));
   H_RC(icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream));
   H_CUDA(cudaEventRecord(h->ev[1], h->stream));
-  int launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2;
+  int launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2 + 13;
   int enqueued = 0;
   const int max_it = p.max_iteration > 0 ? p.max_iteration : 1;
   while (true) {
@@ -319,7 +325,7 @@ int sm_destroy(sm_handle* h) {
   if (!h) return SM_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->nodes,
+  DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->src_g0, &h->src_sort, &h->nodes,
                     &h->leaf_order, &h->bpts, &h->bnrm, &h->slot, &h->d2, &h->hist, &h->cand_idx, &h->cand_key,
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
@@ -427,7 +433,7 @@ int sm_calculate_normals(int device, const double* points, int64_t n, double* ou
   const size_t aos = (size_t)3 * (size_t)n * sizeof(double);
   K_OK(stage.reserve(aos));
   K_OK(coord.reserve((size_t)3 * cs * sizeof(double)));
-  K_OK(nodes.reserve(((size_t)1 << (levels + 1)) * sizeof(KdNode)));
+  K_OK(nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   K_OK(order.reserve((size_t)n * sizeof(uint32_t)));
   K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)n, 7)));
   K_OK(tmp_pts.reserve(aos)); K_OK(tmp_nrm.reserve(aos));
@@ -477,9 +483,9 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_OK(stage.reserve((size_t)3 * (size_t)(nt > nq ? nt : nq) * sizeof(double)));
   K_OK(tgt.reserve((size_t)3 * ts * sizeof(double)));
   K_OK(qry.reserve((size_t)3 * qs * sizeof(double)));
-  K_OK(nodes.reserve(((size_t)1 << (levels + 1)) * sizeof(KdNode)));
+  K_OK(nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   K_OK(order.reserve((size_t)nt * sizeof(uint32_t)));
-  K_OK(bpts.reserve((size_t)nt * sizeof(BucketPoint)));
+  K_OK(bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
   K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)nt, bucket)));
   K_OK(ids_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(int32_t)));
   K_OK(d2_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
