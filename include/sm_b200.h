@@ -61,7 +61,8 @@ int sm_destroy(sm_handle* h);
  * max_iteration (int, 100), dist_outlier_ratio (float, 0.7).  Added by this engine:
  * knn_epsilon (float, 3.16 = icp_fast.cc:174), disable_convergence_check (bool, false;
  * fixed-iteration throughput runs), profile_kernels (bool, false; CUDA events around
- * every phase kernel, reported by sm_get_align_info).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
+ * every phase kernel, reported by sm_get_align_info), use_graphs (bool, true; replay the
+ * launch sequence of an Align as CUDA graphs).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
 int sm_set_option(sm_handle* h, const char* name, const char* text);
 /* Interface::PrintOptions (interface.cc:115-137): writes "name -> value\n" lines. */
 int sm_print_options(sm_handle* h, char* buf, int64_t buf_len);

@@ -155,7 +155,27 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
     double px, py, pz;
     transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
     int slot; double d2;
-    knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2);
+    if (p.debug_knn_mode == 0 || p.debug_knn_mode >= 10) {
+      knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2,
+           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30));
+    } else {   // profiling aid: truncated variants (results are NOT the k-NN)
+      slot = 0; d2 = px * px + py * py + pz * pz + 1.0;
+      if (p.debug_knn_mode >= 2) {
+        int idx = 0;
+        KdNode nd = load_node(b.nodes, 0);
+        while (nd.dim != 3) {
+          const double q = nd.dim == 0 ? px : (nd.dim == 1 ? py : pz);
+          idx = child_idx(idx, (dsub(q, nd.cut) > 0.0) ? 1 : 0);
+          nd = load_node(b.nodes, idx);
+        }
+        slot = (int)(__double_as_longlong(nd.cut) & 0xffffffffll);
+        if (p.debug_knn_mode >= 3) {
+          double head = __longlong_as_double(0x7ff0000000000000ll);
+          scan_leaf(b.bpts, nd, px, py, pz, head, slot);
+          d2 = head;
+        }
+      }
+    }
     b.slot[i] = slot;
     b.d2[i] = d2;
     if (finite_d2(d2)) atomicAdd(&hist[dist_bin(d2)], 1u);
@@ -223,7 +243,7 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
 __global__ void __launch_bounds__(256)
 knn_query_kernel(const KdNode* __restrict__ nodes, const BucketPoint* __restrict__ bpts,
                  const double* __restrict__ query, int64_t qstride, int nq, double max_error2,
-                 int32_t* __restrict__ ids, double* __restrict__ d2) {
+                 int tree_levels, int32_t* __restrict__ ids, double* __restrict__ d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   int slot; double d;
@@ -245,11 +265,14 @@ int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int
   return 0;
 }
 
+int knn_configure() { return 0; }
+
 int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
-              int nq, double max_error2, int32_t* ids, double* d2, cudaStream_t stream) {
+              int nq, double max_error2, int tree_levels, int32_t* ids, double* d2,
+              cudaStream_t stream) {
   if (nq <= 0) return 0;
-  knn_query_kernel<<<ceil_div(nq, 256), 256, 0, stream>>>(nodes, bpts, query, qstride, nq,
-                                                          max_error2, ids, d2);
+  knn_query_kernel<<<ceil_div(nq, 256), 256, 0, stream>>>(
+      nodes, bpts, query, qstride, nq, max_error2, tree_levels, ids, d2);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -9,7 +9,10 @@
 namespace smb {
 namespace dev {
 
-constexpr int kKnnThreads = 256;
+#ifndef SMB_KNN_THREADS
+#define SMB_KNN_THREADS 256
+#endif
+constexpr int kKnnThreads = SMB_KNN_THREADS;
 constexpr int kAccThreads = 256;
 constexpr int kAccItems = 2;
 constexpr int kAccTile = kAccThreads * kAccItems;  // points per accumulate block
@@ -49,9 +52,22 @@ __device__ __forceinline__ KdNode load_node(const KdNode* __restrict__ nodes, in
   return n;
 }
 
+// 16-byte / 8-byte read-only loads as volatile asm: issued in program order, so the 16 loads
+// of a bucket go out back to back (one L2 round trip per bucket instead of eight).
+__device__ __forceinline__ double2 ldg_f64x2(const void* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldg_f64(const void* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 // Scan one bucket.  All 8 entries are fetched up front (the bucket array is padded by 8
-// entries, so reading past `count` is safe) so the loads overlap instead of paying one L2
-// round trip per point; entries >= count are ignored.  Strict '<': first visited wins.
+// entries, so reading past `count` is safe); entries >= count are ignored.
+// Strict '<': first visited wins.
 __device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, const KdNode& leaf,
                                           double qx, double qy, double qz, double& head,
                                           int& best) {
@@ -59,10 +75,11 @@ __device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, 
   const int first = (int)(packed & 0xffffffffll), count = (int)(packed >> 32);
   double2 xy[8];
   double z[8];
+  const char* base = reinterpret_cast<const char*>(bpts + first);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    xy[k] = __ldg(reinterpret_cast<const double2*>(bpts + first + k));
-    z[k] = __ldg(reinterpret_cast<const double*>(bpts + first + k) + 2);
+    xy[k] = ldg_f64x2(base + 32 * k);
+    z[k] = ldg_f64(base + 32 * k + 16);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -85,15 +102,64 @@ __device__ __forceinline__ int child_idx(int idx, int right) {
                  : ((8 * B + 1 + (((p - 3) << 1) | right)) << 3);
 }
 
-// libnabo recurseKnn (k=1, allowSelfMatch, maxRadius=inf) made iterative.  A far subtree
-// is pushed only if it passes the pruning test against the head known at push time (the
-// head can only shrink, so this never drops a subtree the recursion would visit) and is
-// re-tested at pop time, which is exactly when the recursion tests it.  A read-only first
-// descent seeds the head; along it rd_new == new_off^2 exactly (rd = 0, all offsets 0), so
-// if min(new_off^2)*(1+eps)^2 >= head no far subtree can ever qualify and we are done.
+// Visit the subtree rooted at `idx` exactly like libnabo's recurseKnn would (near child
+// first, far child if rd*(1+eps)^2 < head at that moment).  Far subtrees are pushed only if
+// they pass the test against the head known at push time (the head only shrinks, so nothing
+// the recursion would visit is dropped) and re-tested when popped, which is when the
+// recursion tests them.
+__device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
+                                              const BucketPoint* __restrict__ bpts, double qx,
+                                              double qy, double qz, double max_error2, int idx,
+                                              double rd, double ox, double oy, double oz,
+                                              double& head, int& best, int max_rounds = 1 << 30) {
+  StackEntry stack[kMaxStack];
+  int sp = 0;
+  while (max_rounds-- > 0) {
+    KdNode nd = load_node(nodes, idx);
+    while (nd.dim != 3) {
+      const int cd = nd.dim;
+      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+      const double new_off = dsub(q, nd.cut);
+      const int right = new_off > 0.0 ? 1 : 0;
+      // rd += - old_off*old_off + new_off*new_off
+      const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
+        StackEntry e;
+        e.rd = rd_new;
+        e.ox = cd == 0 ? new_off : ox;
+        e.oy = cd == 1 ? new_off : oy;
+        e.oz = cd == 2 ? new_off : oz;
+        e.idx = child_idx(idx, 1 - right);
+        stack[sp++] = e;
+      }
+      idx = child_idx(idx, right);
+      nd = load_node(nodes, idx);
+    }
+    scan_leaf(bpts, nd, qx, qy, qz, head, best);
+    bool found = false;
+    while (sp > 0) {
+      const StackEntry e = stack[--sp];
+      if (dmul(e.rd, max_error2) < head) {
+        idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+}
+
+// libnabo knn, k = 1, allowSelfMatch, maxRadius = inf (icp_fast.cc:177-178), one query per
+// thread.  A read-only first descent seeds the head; along it rd_new == new_off^2 exactly
+// (rd = 0, all offsets 0), so if min(new_off^2)*(1+eps)^2 >= head no far subtree can ever
+// qualify and the query is done after one bucket.  Otherwise the recursion is replayed from
+// the root by visit_subtree (ONE loop for all far visits: the k-th bucket visit of every lane
+// of a warp happens in the same round, so a warp costs max-over-lanes rounds).
 __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
                                      const BucketPoint* __restrict__ bpts, double qx, double qy,
-                                     double qz, double max_error2, int& best_slot, double& best_d2) {
+                                     double qz, double max_error2, int& best_slot, double& best_d2,
+                                     int max_rounds = 1 << 30) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double head = inf;
   int best = -1;
@@ -107,50 +173,10 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
     idx = child_idx(idx, (off > 0.0) ? 1 : 0);
     nd = load_node(nodes, idx);
   }
-  const int leaf0 = idx;
   scan_leaf(bpts, nd, qx, qy, qz, head, best);
-  if (dmul(min_off2, max_error2) < head) {
-    StackEntry stack[kMaxStack];
-    int sp = 0;
-    double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
-    idx = 0;
-    while (true) {
-      // descend to a leaf; every lane leaves this loop before any lane scans its bucket, so
-      // the bucket scan is executed once per round by the whole warp
-      nd = load_node(nodes, idx);
-      while (nd.dim != 3) {
-        const int cd = nd.dim;
-        const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-        const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
-        const double new_off = dsub(q, nd.cut);
-        const int right = new_off > 0.0 ? 1 : 0;
-        // rd += - old_off*old_off + new_off*new_off
-        const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-        if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
-          StackEntry e;
-          e.rd = rd_new;
-          e.ox = cd == 0 ? new_off : ox;
-          e.oy = cd == 1 ? new_off : oy;
-          e.oz = cd == 2 ? new_off : oz;
-          e.idx = child_idx(idx, 1 - right);
-          stack[sp++] = e;
-        }
-        idx = child_idx(idx, right);
-        nd = load_node(nodes, idx);
-      }
-      if (idx != leaf0) scan_leaf(bpts, nd, qx, qy, qz, head, best);
-      bool found = false;
-      while (sp > 0) {
-        const StackEntry e = stack[--sp];
-        if (dmul(e.rd, max_error2) < head) {
-          idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
-          found = true;
-          break;
-        }
-      }
-      if (!found) break;
-    }
-  }
+  // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
+  if (dmul(min_off2, max_error2) < head)
+    visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds);
   best_slot = best;
   best_d2 = head;
 }

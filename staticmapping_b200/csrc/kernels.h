@@ -62,6 +62,8 @@ struct IcpParams {
   float dist_outlier_ratio;
   double max_error2;       // (1+eps)^2
   int disable_convergence;
+  int tree_levels;         // kd_num_levels(n_target, 8): depth of the root-to-leaf path
+  int debug_knn_mode;      // 0 = normal; 1..3 = truncated k-NN kernel variants (profiling aid only)
 };
 
 struct IcpBuffers {
@@ -106,7 +108,9 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
 void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, cudaStream_t stream);
 // stand-alone k-NN over an already built tree (parity tests): ids = original indices
 int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
-              int nq, double max_error2, int32_t* ids, double* d2, cudaStream_t stream);
+              int nq, double max_error2, int tree_levels, int32_t* ids, double* d2,
+              cudaStream_t stream);
+int knn_configure();
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);

@@ -58,12 +58,22 @@ struct IcpOptions {
   float knn_epsilon = 3.16f;             // icp_fast.cc:174 (engine option; same default)
   bool disable_convergence_check = false;
   bool profile_kernels = false;
+  bool use_graphs = true;
+  int32_t debug_knn_mode = 0;
 };
 
 }  // namespace
 }  // namespace smb
 
 using namespace smb;
+
+// A captured launch sequence, replayed while the key (all pointers and sizes baked into the
+// kernel arguments) is unchanged: one cudaGraphLaunch instead of ~100 kernel launches.
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr;
+  std::string key;
+  void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key.clear(); }
+};
 
 struct sm_handle {
   int type = 0;
@@ -83,6 +93,7 @@ struct sm_handle {
   float ms_upload = 0.f;
   IcpState* host_state = nullptr;  // pinned
   std::vector<cudaEvent_t> prof_events;
+  GraphCache g_prologue, g_iterations;
 };
 
 namespace {
@@ -94,6 +105,8 @@ const OptionDef kIcpOptions[] = {
     {"knn_epsilon", kOptFloat, offsetof(IcpOptions, knn_epsilon)},
     {"disable_convergence_check", kOptBool, offsetof(IcpOptions, disable_convergence_check)},
     {"profile_kernels", kOptBool, offsetof(IcpOptions, profile_kernels)},
+    {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
+    {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
 };
 
 int fail(sm_handle* h, int code, const std::string& msg) {
@@ -118,6 +131,31 @@ int cuda_fail(sm_handle* h) { return fail(h, SM_ERR_CUDA, last_cuda_error()); }
   } while (0)
 
 int64_t pad64(int64_t n) { return (n + 63) & ~(int64_t)63; }
+
+template <typename F>
+int run_graphed(sm_handle* h, GraphCache& gc, const std::string& key, F enqueue) {
+  if (gc.exec == nullptr || gc.key != key) {
+    gc.reset();
+    H_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc < 0 || e != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      if (e != cudaSuccess) set_cuda_error(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+      return rc < 0 ? rc : cuda_fail(h);
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&gc.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { gc.exec = nullptr; set_cuda_error(e2, "cudaGraphInstantiate", __FILE__, __LINE__); return cuda_fail(h); }
+    gc.key = key;
+  }
+  H_CUDA(cudaGraphLaunch(gc.exec, h->stream));
+  return 0;
+}
+
+template <typename T>
+void key_append(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
 
 // upload (or adopt) an AoS 3xN cloud and de-interleave it into SoA [3][stride]
 int load_cloud(sm_handle* h, const double* pts, int64_t n, bool on_device, DevBuf& soa,
@@ -227,10 +265,22 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   const double eps = (double)h->icp.knn_epsilon;
   p.max_error2 = (1.0 + eps) * (1.0 + eps);
   p.disable_convergence = h->icp.disable_convergence_check ? 1 : 0;
+  p.debug_knn_mode = h->icp.debug_knn_mode;
+  p.tree_levels = levels;
+  if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large (tree deeper than 24 levels)");
 
   H_CUDA(cudaMemcpyAsync(h->guess.p, guess, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   H_CUDA(cudaEventRecord(h->ev[0], h->stream));
-  H_RC(icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream));
+  const bool graphs = h->icp.use_graphs && !h->icp.profile_kernels;
+  std::string key;
+  key_append(key, b); key_append(key, p); key_append(key, h->guess.p); key_append(key, h->kdws.p);
+  if (graphs) {
+    H_RC(run_graphed(h, h->g_prologue, key, [&]() {
+      return icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream);
+    }));
+  } else {
+    H_RC(icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream));
+  }
   H_CUDA(cudaEventRecord(h->ev[1], h->stream));
   int launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2 + 13;
   int enqueued = 0;
@@ -245,7 +295,15 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
       }
       evs = h->prof_events.data() + 4 * enqueued;
     }
-    H_RC(icp_enqueue_iterations(b, p, chunk, h->stream, evs));
+    if (graphs) {
+      std::string ikey = key;
+      key_append(ikey, chunk);
+      H_RC(run_graphed(h, h->g_iterations, ikey, [&]() {
+        return icp_enqueue_iterations(b, p, chunk, h->stream, nullptr);
+      }));
+    } else {
+      H_RC(icp_enqueue_iterations(b, p, chunk, h->stream, evs));
+    }
     enqueued += chunk;
     launches += 3 * chunk;
     H_CUDA(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost,
@@ -316,6 +374,7 @@ int sm_create(int type, int device, sm_handle** out) {
     return SM_ERR_CUDA;
   }
   h->stream = h->own_stream;
+  if (knn_configure() != 0) { sm_destroy(h); return SM_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
   *out = h;
   return SM_OK;
@@ -330,6 +389,7 @@ int sm_destroy(sm_handle* h) {
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  h->g_prologue.reset(); h->g_iterations.reset();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->host_state) cudaFreeHost(h->host_state);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -492,6 +552,7 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_CUDA(cudaMemcpyAsync(stage.p, target, (size_t)3 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
   deinterleave3_kernel<<<ceil_div(nt, 256), 256, 0, s>>>((const double*)stage.p, (double*)tgt.p, ts, (int)nt);
   K_CUDA(cudaStreamSynchronize(s));
+  K_OK(knn_configure());
   KdWorkspace ws;
   ws.carve(kdws.p, (int)nt, bucket);
   K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s));
@@ -501,7 +562,7 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
     K_CUDA(cudaMemcpyAsync(stage.p, query, (size_t)3 * nq * sizeof(double), cudaMemcpyHostToDevice, s));
     deinterleave3_kernel<<<ceil_div(nq, 256), 256, 0, s>>>((const double*)stage.p, (double*)qry.p, qs, (int)nq);
     K_OK(knn_query((const KdNode*)nodes.p, (const BucketPoint*)bpts.p, (const double*)qry.p, qs,
-                   (int)nq, (1.0 + epsilon) * (1.0 + epsilon), (int32_t*)ids_d.p, (double*)d2_d.p, s));
+                   (int)nq, (1.0 + epsilon) * (1.0 + epsilon), levels, (int32_t*)ids_d.p, (double*)d2_d.p, s));
     K_CUDA(cudaMemcpyAsync(ids, ids_d.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     K_CUDA(cudaMemcpyAsync(d2, d2_d.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
