@@ -62,7 +62,11 @@ int sm_destroy(sm_handle* h);
  * knn_epsilon (float, 3.16 = icp_fast.cc:174), disable_convergence_check (bool, false;
  * fixed-iteration throughput runs), profile_kernels (bool, false; CUDA events around
  * every phase kernel, reported by sm_get_align_info), use_graphs (bool, true; replay the
- * launch sequence of an Align as CUDA graphs).  Unknown name -> SM_ERR_UNKNOWN_OPTION. */
+ * launch sequence of an Align as CUDA graphs).  Unknown name -> SM_ERR_UNKNOWN_OPTION.
+ * registrator::Ndt registers NO option (ndt.cc:28-34) — the reference-facing mirrors reject
+ * every <param> for type 5; the engine itself accepts the pclomp setters hard-coded by the
+ * reference: resolution (1.0), step_size (0.1), outlier_ratio (0.55),
+ * transformation_epsilon (0.1), max_iterations (35). */
 int sm_set_option(sm_handle* h, const char* name, const char* text);
 /* Interface::PrintOptions (interface.cc:115-137): writes "name -> value\n" lines. */
 int sm_print_options(sm_handle* h, char* buf, int64_t buf_len);
@@ -76,6 +80,15 @@ int sm_get_type(const sm_handle* h);
 int sm_set_input_source(sm_handle* h, const double* points_3xn, int64_t n);
 int sm_set_input_target(sm_handle* h, const double* points_3xn, const double* normals_3xn,
                         int64_t n);
+/* Ndt / NdtWithGicp keep the caller's float cloud (Interface::SetInputSource/Target,
+ * interface.cc:38-60, converted by ToPclPointCloud at Align, ndt.cc:48-51).  `xyz` points at
+ * the first x; consecutive points are `stride_bytes` apart (sizeof(InnerPointType) == 20 for
+ * the reference's std::vector<InnerPointType>, 12 for packed xyz). */
+int sm_set_input_source_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride_bytes);
+int sm_set_input_target_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride_bytes);
+int sm_set_input_source_f32_device(sm_handle* h, const float* dev_xyz, int64_t n, int64_t stride_bytes);
+int sm_set_input_target_f32_device(sm_handle* h, const float* dev_xyz, int64_t n, int64_t stride_bytes);
+
 /* Same, for clouds already resident in this device's memory (same layout). */
 int sm_set_input_source_device(sm_handle* h, const double* dev_points_3xn, int64_t n);
 int sm_set_input_target_device(sm_handle* h, const double* dev_points_3xn,
@@ -104,6 +117,10 @@ typedef struct sm_align_info {
   float ms_accum;          /* quantile bin + normal equations      (icp_fast.cc:496-503) */
   float ms_finish;         /* exact limit, solve, pose update      (icp_fast.cc:506-523) */
   int32_t profiled_iterations;
+  /* NDT only */
+  int32_t evaluations;        /* computeDerivatives calls (ndt_omp_impl.hpp:180) */
+  double trans_probability;   /* score / N_source (ndt_omp_impl.hpp:170) */
+  double mean_neighbors;      /* mean number of neighbour voxels per source point */
 } sm_align_info;
 int sm_get_align_info(const sm_handle* h, sm_align_info* out);
 

@@ -347,6 +347,21 @@ inline bool CheckConvergence(const std::vector<double>& quats,
 }  // namespace
 }  // namespace sm_oracle
 
+namespace sm_oracle {
+// Exact 1-NN of float points (converted to double; the k-d tree with eps = 0 is exact).
+// Used for pcl::Registration::getFitnessScore (ndt.cc:60), whose FLANN search is exact.
+int ExactNn1Float(const float* target_xyz, int64_t nt, const float* query_xyz, int64_t nq,
+                  int32_t* ids_out) {
+  std::vector<double> t((size_t)(3 * nt)), q((size_t)(3 * nq)), d2((size_t)nq);
+  for (int64_t i = 0; i < 3 * nt; ++i) t[(size_t)i] = (double)target_xyz[i];
+  for (int64_t i = 0; i < 3 * nq; ++i) q[(size_t)i] = (double)query_xyz[i];
+  KdTree tree;
+  tree.Build(t.data(), nt, 8, 0);
+  tree.Knn1(q.data(), nq, 0.0, ids_out, d2.data());
+  return 0;
+}
+}  // namespace sm_oracle
+
 using namespace sm_oracle;
 
 extern "C" {

@@ -77,6 +77,29 @@ int sm_oracle_icp_fast_align(const double* source, int64_t n_source, const doubl
                              double* result, double* final_score, int32_t* iterations,
                              sm_oracle_icp_trace* trace, int32_t trace_capacity);
 
+/* ---- NDT (registrators/ndt.cc + registrators/pclomp/, see oracle/ndt_oracle.cc) ---------- */
+typedef struct sm_oracle_ndt_options {
+  float resolution;              /* ndt.cc:31, 1.0 */
+  double step_size;              /* ndt_omp_impl.hpp:49, 0.1 */
+  double outlier_ratio;          /* :50, 0.55 */
+  double transformation_epsilon; /* :71, 0.1 */
+  int32_t max_iterations;        /* :72, 35 */
+} sm_oracle_ndt_options;
+
+/* Clouds here are packed float xyz (n x 3), i.e. pcl::PointXYZ without padding. */
+int64_t sm_oracle_ndt_voxels(const float* target, int64_t n, float resolution, int64_t capacity,
+                             int32_t* idx_out, int32_t* npts_out, double* mean_out,
+                             double* icov_out, float* centroid_out, int32_t* searchable_out);
+int sm_oracle_ndt_derivatives(const float* source, int64_t ns, const float* target, int64_t nt,
+                              const sm_oracle_ndt_options* opt, const double* p, double* score,
+                              double* grad6, double* hess36, double* mean_neighbors);
+/* Ndt::Align (ndt.cc:38-64); returns 1 / 0 like the reference's bool. fitness = PCL
+ * getFitnessScore (mean squared NN distance, lower is better). */
+int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, int64_t nt,
+                        const double* guess, const sm_oracle_ndt_options* opt, double* result,
+                        double* fitness, int32_t* iterations, double* trans_probability,
+                        double* mean_neighbors);
+
 /* Pieces exposed for unit tests of the restatement itself. */
 int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
 int sm_oracle_quantile_index(int64_t n, float ratio);

@@ -18,7 +18,8 @@ class AlignInfo(C.Structure):
                 ("ms_upload", C.c_float), ("ms_prologue", C.c_float),
                 ("ms_iterations", C.c_float), ("kernel_launches", C.c_int32),
                 ("ms_knn", C.c_float), ("ms_accum", C.c_float), ("ms_finish", C.c_float),
-                ("profiled_iterations", C.c_int32)]
+                ("profiled_iterations", C.c_int32), ("evaluations", C.c_int32),
+                ("trans_probability", C.c_double), ("mean_neighbors", C.c_double)]
 
 
 _lib = None
@@ -36,6 +37,10 @@ SIGNATURES = {
     "sm_get_type": (C.c_int, [_VP]),
     "sm_set_input_source": (C.c_int, [_VP, _VP, C.c_int64]),
     "sm_set_input_target": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
+    "sm_set_input_source_f32": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64]),
+    "sm_set_input_target_f32": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64]),
+    "sm_set_input_source_f32_device": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64]),
+    "sm_set_input_target_f32_device": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64]),
     "sm_set_input_source_device": (C.c_int, [_VP, _VP, C.c_int64]),
     "sm_set_input_target_device": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sm_align": (C.c_int, [_VP, _DP, _DP]),

@@ -115,6 +115,53 @@ int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);
 
+// ---- ndt.cu ------------------------------------------------------------------------------
+struct NdtGrid {            // VoxelGridCovariance bookkeeping (_impl.hpp:88-103)
+  float inv_leaf;
+  int min_b[3], div_b[3], mul[3];
+  int n_voxels;
+};
+struct NdtLeaf {            // VoxelGridCovariance::Leaf (voxel_grid_covariance_omp.h:92-186)
+  double mean[3];
+  double icov[9];           // zero for leaves that failed the eigenvalue test
+  float centroid[3];
+  int nr_points;            // -1: invalid covariance (still searchable, like the reference)
+  int searchable;           // >= min_points_per_voxel: centroid is in the search cloud
+  int pad;
+};
+struct NdtEvalParams {      // everything one computeDerivatives call needs, by value
+  float T[16];              // final_transformation_, column-major
+  float j_ang[8][3];        // computeAngleDerivatives (ndt_omp_impl.hpp:288-393)
+  float h_ang[15][3];
+  double gauss_d1, gauss_d2;
+  float radius;             // resolution_
+};
+uint32_t ndt_table_size(int nt);
+int ndt_blocks(int n);
+struct NdtWorkspace {
+  uint64_t* keys[2];
+  uint32_t* order[2];
+  uint32_t* scratch;
+  uint32_t* voxel_start;
+  int* voxel_key;
+  NdtLeaf* leaves;
+  int* table_key;
+  int* table_val;
+  uint32_t table_size;
+  double* partials;
+  double* sums;             // [64] reduced outputs
+  float* minmax;
+  NdtGrid* grid;
+  int64_t stride;
+  static size_t bytes_needed(int nt, int ns);
+  void carve(void* base, int nt, int ns);
+};
+int ndt_build_grid(const float* tgt, int nt, float resolution, NdtWorkspace& ws, cudaStream_t stream);
+int ndt_eval(const float* src, int ns, const NdtEvalParams& P, NdtWorkspace& ws, cudaStream_t stream);
+int ndt_float_to_soa(const float* pts, int n, double* soa, int64_t stride, cudaStream_t stream);
+int ndt_fitness(const float* src, int ns, const NdtEvalParams& P, const KdNode* nodes,
+                const BucketPoint* bpts, const float* tgt, NdtWorkspace& ws, cudaStream_t stream);
+
 // ---- normals.cu ------------------------------------------------------------------------
 int normals_scratch_blocks(int n);
 int normals_run(const double* coord, int64_t cstride, int n, KdWorkspace& ws, KdNode* nodes,

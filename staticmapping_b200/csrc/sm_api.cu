@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ndt_host.h"
 
 namespace smb {
 
@@ -94,6 +95,10 @@ struct sm_handle {
   IcpState* host_state = nullptr;  // pinned
   std::vector<cudaEvent_t> prof_events;
   GraphCache g_prologue, g_iterations;
+  // NDT
+  ndt::Options ndt;
+  DevBuf src_f32, tgt_f32, ndt_ws, tgt_soa;
+  double* host_sums = nullptr;     // pinned, 64 doubles
 };
 
 namespace {
@@ -107,6 +112,18 @@ const OptionDef kIcpOptions[] = {
     {"profile_kernels", kOptBool, offsetof(IcpOptions, profile_kernels)},
     {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
     {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
+};
+
+const OptionDef kNdtOptions[] = {
+    {"max_iterations", kOptInt, offsetof(ndt::Options, max_iterations)},
+    {"resolution", kOptFloat, offsetof(ndt::Options, resolution)},
+};
+// double-typed NDT options are parsed separately (the table only knows int/float/bool)
+struct NdtDoubleOpt { const char* name; size_t offset; };
+const NdtDoubleOpt kNdtDoubleOptions[] = {
+    {"step_size", offsetof(ndt::Options, step_size)},
+    {"outlier_ratio", offsetof(ndt::Options, outlier_ratio)},
+    {"transformation_epsilon", offsetof(ndt::Options, transformation_epsilon)},
 };
 
 int fail(sm_handle* h, int code, const std::string& msg) {
@@ -212,6 +229,8 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
   h->has_target = true;
   return 0;
 }
+
+int ndt_align(sm_handle* h, const double* guess, double* result);
 
 int icp_align(sm_handle* h, const double* guess, double* result) {
   if (!h->has_source || !h->has_target)
@@ -344,6 +363,144 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   return 1;  // IcpFast::Align always returns true (icp_fast.cc:528)
 }
 
+
+// ---- Ndt ---------------------------------------------------------------------------------
+int load_cloud_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride, bool on_device, DevBuf& dst) {
+  if (!h) return SM_ERR_BAD_ARGUMENT;
+  if (!xyz || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInput: empty cloud");
+  if (stride < 12 || n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInput: bad stride / size");
+  H_CUDA(cudaSetDevice(h->device));
+  H_RC(dst.reserve((size_t)n * 12 + 64));
+  H_CUDA(cudaMemcpy2DAsync(dst.p, 12, xyz, (size_t)stride, 12, (size_t)n,
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  if (!on_device) H_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ndt_eval_sync(sm_handle* h, const float* src, int ns, const NdtEvalParams& P, NdtWorkspace& ws) {
+  H_RC(ndt_eval(src, ns, P, ws, h->stream));
+  H_CUDA(cudaMemcpyAsync(h->host_sums, ws.sums, 44 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Ndt::Align (ndt.cc:38-64) -> pcl::Registration::align -> computeTransformation
+// (ndt_omp_impl.hpp:81-171) -> getFitnessScore.
+int ndt_align(sm_handle* h, const double* guess, double* result) {
+  if (!h->has_source || !h->has_target) {       // ndt.cc:40-42: return false
+    for (int i = 0; i < 16; ++i) result[i] = guess[i];
+    return 0;
+  }
+  const int ns = (int)h->n_source, nt = (int)h->n_target;
+  const ndt::Options& o = h->ndt;
+  const float* src = (const float*)h->src_f32.p;
+  const float* tgt = (const float*)h->tgt_f32.p;
+  H_RC(h->ndt_ws.reserve(NdtWorkspace::bytes_needed(nt, ns)));
+  NdtWorkspace ws;
+  ws.carve(h->ndt_ws.p, nt, ns);
+  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  H_RC(ndt_build_grid(tgt, nt, o.resolution, ws, h->stream));        // setInputTarget -> init()
+  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  NdtEvalParams P;
+  ndt::gauss_constants(o, &P.gauss_d1, &P.gauss_d2);
+  P.radius = o.resolution;
+  float final_T[16];
+  bool guess_is_identity = true;
+  for (int i = 0; i < 16; ++i) {
+    final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    if ((float)guess[i] != final_T[i]) guess_is_identity = false;
+  }
+  if (!guess_is_identity) for (int i = 0; i < 16; ++i) final_T[i] = (float)guess[i];   // :95-101
+  double p[6];
+  ndt::p_from_transform(final_T, p);                                  // :103-111
+  for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
+  ndt::angle_tables(p, &P);
+  double score, grad[6], hess[36], nb_sum = 0.0;
+  int evals = 0, launches = 12 + 12;
+  auto read_sums = [&]() {
+    score = h->host_sums[0];
+    for (int i = 0; i < 6; ++i) grad[i] = h->host_sums[1 + i];
+    for (int i = 0; i < 36; ++i) hess[i] = h->host_sums[7 + i];
+    nb_sum += h->host_sums[43] / (double)ns;
+    ++evals; launches += 2;
+  };
+  H_RC(ndt_eval_sync(h, src, ns, P, ws));                             // :119
+  read_sums();
+  int nr_iterations = 0;
+  bool converged = false;
+  while (!converged) {
+    double neg_grad[6], delta[6];
+    for (int i = 0; i < 6; ++i) neg_grad[i] = -grad[i];
+    ndt::svd_solve6(hess, neg_grad, delta);                           // :127-129
+    double norm = 0.0;
+    for (int i = 0; i < 6; ++i) norm += delta[i] * delta[i];
+    norm = sqrt(norm);
+    if (norm == 0.0 || norm != norm) break;                           // :134-139
+    for (int i = 0; i < 6; ++i) delta[i] /= norm;
+    // computeStepLengthMT (:757-916); its More-Thuente loop never runs because
+    // interval_converged starts as (step_max - step_min) > 0 == true (:802)
+    double d_phi_0 = 0.0;
+    for (int i = 0; i < 6; ++i) d_phi_0 += grad[i] * delta[i];
+    d_phi_0 = -d_phi_0;
+    double a_t = 0.0;
+    bool evaluate = true;
+    if (d_phi_0 >= 0.0) {
+      if (d_phi_0 == 0.0) evaluate = false;
+      else for (int i = 0; i < 6; ++i) delta[i] = -delta[i];
+    }
+    if (evaluate) {
+      a_t = std::max(std::min(norm, o.step_size), o.transformation_epsilon / 2.0);
+      double x_t[6];
+      for (int i = 0; i < 6; ++i) x_t[i] = p[i] + delta[i] * a_t;
+      ndt::transform_from_p(x_t, final_T);                            // :809-812
+      for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
+      ndt::angle_tables(x_t, &P);
+      H_RC(ndt_eval_sync(h, src, ns, P, ws));                         // :818
+      read_sums();
+    }
+    for (int i = 0; i < 6; ++i) p[i] += delta[i] * a_t;               // :143,152
+    if (nr_iterations > o.max_iterations ||
+        (nr_iterations && fabs(a_t) < o.transformation_epsilon))
+      converged = true;                                                // :158-162
+    ++nr_iterations;
+  }
+  H_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  // getFitnessScore (ndt.cc:60): exact 1-NN over the full target (PCL builds this search
+  // tree in setInputTarget; the reference calls that on every Align)
+  const int levels = kd_num_levels(nt, 8);
+  if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large");
+  h->tstride = pad64(nt);
+  H_RC(h->tgt_soa.reserve((size_t)(3 * h->tstride) * sizeof(double)));
+  H_RC(h->nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
+  H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
+  H_RC(h->bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
+  H_RC(h->kdws.reserve(KdWorkspace::bytes_needed(nt, 8)));
+  KdWorkspace kws;
+  kws.carve(h->kdws.p, nt, 8);
+  H_RC(ndt_float_to_soa(tgt, nt, (double*)h->tgt_soa.p, h->tstride, h->stream));
+  H_RC(kd_build((const double*)h->tgt_soa.p, h->tstride, nt, 8, kws, (KdNode*)h->nodes.p,
+                (uint32_t*)h->leaf_order.p, h->stream));
+  H_RC(kd_fill_buckets((const double*)h->tgt_soa.p, h->tstride, nullptr, 0, (const uint32_t*)h->leaf_order.p,
+                       nt, (BucketPoint*)h->bpts.p, nullptr, h->stream));
+  H_RC(ndt_fitness(src, ns, P, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p, tgt, ws, h->stream));
+  H_CUDA(cudaMemcpyAsync(h->host_sums, ws.sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  h->final_score = h->host_sums[1] > 0.0 ? h->host_sums[0] / h->host_sums[1]
+                                         : std::numeric_limits<double>::max();
+  for (int i = 0; i < 16; ++i) result[i] = (double)final_T[i];        // .cast<double>() (ndt.cc:61)
+  memset(&h->info, 0, sizeof(h->info));
+  h->info.iterations = nr_iterations;
+  h->info.evaluations = evals;
+  h->info.trans_probability = score / (double)ns;
+  h->info.mean_neighbors = evals ? nb_sum / evals : 0.0;
+  h->info.kernel_launches = launches + 24 + levels * 5 + 6;
+  cudaEventElapsedTime(&h->info.ms_prologue, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->info.ms_iterations, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&h->info.ms_finish, h->ev[2], h->ev[3]);      // fitness score
+  return 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -359,7 +516,7 @@ const char* sm_version(void) { return "sm_b200 0.1 (sm_100a)"; }
 int sm_create(int type, int device, sm_handle** out) {
   if (!out) return SM_ERR_BAD_ARGUMENT;
   *out = nullptr;
-  if (type != SM_TYPE_FAST_ICP) return SM_ERR_UNSUPPORTED_TYPE;
+  if (type != SM_TYPE_FAST_ICP && type != SM_TYPE_NDT) return SM_ERR_UNSUPPORTED_TYPE;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
   if (device < 0 || device >= ndev) return SM_ERR_BAD_ARGUMENT;
@@ -369,7 +526,8 @@ int sm_create(int type, int device, sm_handle** out) {
   memset(&h->info, 0, sizeof(h->info));
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess) {
+      cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->host_sums, 64 * sizeof(double)) != cudaSuccess) {
     delete h;
     return SM_ERR_CUDA;
   }
@@ -392,6 +550,8 @@ int sm_destroy(sm_handle* h) {
   h->g_prologue.reset(); h->g_iterations.reset();
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->host_state) cudaFreeHost(h->host_state);
+  if (h->host_sums) cudaFreeHost(h->host_sums);
+  h->src_f32.release(); h->tgt_f32.release(); h->ndt_ws.release(); h->tgt_soa.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SM_OK;
@@ -409,6 +569,21 @@ int sm_set_stream(sm_handle* h, void* cuda_stream) {
 
 int sm_set_option(sm_handle* h, const char* name, const char* text) {
   if (!h || !name || !text) return SM_ERR_BAD_ARGUMENT;
+  if (h->type == SM_TYPE_NDT) {
+    for (const NdtDoubleOpt& d : kNdtDoubleOptions)
+      if (strcmp(d.name, name) == 0) {
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(&h->ndt) + d.offset) = strtod(text, nullptr);
+        return SM_OK;
+      }
+    for (const OptionDef& d : kNdtOptions)
+      if (strcmp(d.name, name) == 0) {
+        char* base = reinterpret_cast<char*>(&h->ndt) + d.offset;
+        if (d.kind == kOptInt) *reinterpret_cast<int32_t*>(base) = (int32_t)strtol(text, nullptr, 10);
+        else *reinterpret_cast<float*>(base) = strtof(text, nullptr);
+        return SM_OK;
+      }
+    return fail(h, SM_ERR_UNKNOWN_OPTION, std::string("Init an unknown option of this matcher! ") + name);
+  }
   for (const OptionDef& d : kIcpOptions) {
     if (strcmp(d.name, name) != 0) continue;
     char* base = reinterpret_cast<char*>(&h->icp) + d.offset;
@@ -455,10 +630,32 @@ int sm_set_input_target_device(sm_handle* h, const double* p, const double* nrm,
   return set_target(h, p, nrm, n, true);
 }
 
+int sm_set_input_source_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
+  int rc = load_cloud_f32(h, xyz, n, stride, false, h->src_f32);
+  if (rc == 0) { h->n_source = n; h->has_source = true; }
+  return rc;
+}
+int sm_set_input_target_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
+  int rc = load_cloud_f32(h, xyz, n, stride, false, h->tgt_f32);
+  if (rc == 0) { h->n_target = n; h->has_target = true; }
+  return rc;
+}
+int sm_set_input_source_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
+  int rc = load_cloud_f32(h, xyz, n, stride, true, h->src_f32);
+  if (rc == 0) { h->n_source = n; h->has_source = true; }
+  return rc;
+}
+int sm_set_input_target_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
+  int rc = load_cloud_f32(h, xyz, n, stride, true, h->tgt_f32);
+  if (rc == 0) { h->n_target = n; h->has_target = true; }
+  return rc;
+}
+
 int sm_align(sm_handle* h, const double* guess, double* result) {
   if (!h || !guess || !result) return SM_ERR_BAD_ARGUMENT;
   if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
   if (h->type == SM_TYPE_FAST_ICP) return icp_align(h, guess, result);
+  if (h->type == SM_TYPE_NDT) return ndt_align(h, guess, result);
   return fail(h, SM_ERR_UNSUPPORTED_TYPE, "matcher type not supported");
 }
 

@@ -67,6 +67,26 @@ class EigenCloud:
 
 
 @dataclass
+class InnerCloud:
+    """data::InnerCloudType (cloud_types.h:59-77): the float cloud `Ndt` / `NdtWithGicp` keep
+    (x, y, z of InnerPointType; intensity / factor are not used by the matchers).
+    points: (N,3) float32, or (N,5) float32 rows laid out like InnerPointType (20-byte stride)."""
+    points: np.ndarray
+
+    def __post_init__(self):
+        self.points = np.ascontiguousarray(np.asarray(self.points, dtype=np.float32))
+        if self.points.ndim != 2 or self.points.shape[1] not in (3, 5):
+            raise ValueError("points must be (N,3) or (N,5) float32")
+
+    def Empty(self):
+        return self.points.shape[0] == 0
+
+    @property
+    def stride_bytes(self):
+        return 4 * self.points.shape[1]
+
+
+@dataclass
 class MatcherOptions:
     """registrator::MatcherOptions (interface.h:59-65)."""
     type: Type = Type.kIcpPM
@@ -200,6 +220,54 @@ class IcpFast(Interface):
                     "SetInputTarget")
 
 
+class Ndt(Interface):
+    """registrator::Ndt (ndt.h / ndt.cc:28-64): pclomp NDT, resolution 1.0, KDTREE neighbour
+    search.  GetFitnessScore() is PCL's mean squared NN distance (LOWER is better), unlike the
+    ICP matchers' exp(-distance)."""
+    _type = Type.kNdt
+
+    def InitWithXml(self, node):
+        # Ndt registers no option (ndt.cc:28-34): any <param> hits the CHECK in interface.cc:66
+        for name, _ in _params_from_node(node):
+            raise CheckFailure(f"Init an unknown option of this matcher! ({name})")
+
+    def SetEngineOptions(self, **kw):
+        """pclomp setters the reference hard-codes (resolution, step_size, outlier_ratio,
+        transformation_epsilon, max_iterations); not reachable from the reference's XML."""
+        for k, v in kw.items():
+            self._check(self._lib.sm_set_option(self._h, k.encode(), str(v).encode()), "option")
+
+    def SetInputSource(self, cloud: InnerCloud):
+        # Interface::SetInputSource (interface.cc:38-48): null resets, empty only warns
+        self._source = None
+        if cloud is None:
+            return
+        if cloud.Empty():
+            print("cloud is empty.")
+            return
+        self._check(self._lib.sm_set_input_source_f32(self._h, cloud.points.ctypes.data,
+                                                      cloud.points.shape[0], cloud.stride_bytes),
+                    "SetInputSource")
+        self._source = cloud
+
+    def SetInputTarget(self, cloud: InnerCloud):
+        self._target = None
+        if cloud is None:
+            return
+        if cloud.Empty():
+            print("cloud is empty.")
+            return
+        self._check(self._lib.sm_set_input_target_f32(self._h, cloud.points.ctypes.data,
+                                                      cloud.points.shape[0], cloud.stride_bytes),
+                    "SetInputTarget")
+        self._target = cloud
+
+    def Align(self, guess):
+        if self._source is None or self._target is None:   # ndt.cc:40-42
+            return False, np.asarray(guess, dtype=np.float64).copy()
+        return super().Align(guess)
+
+
 def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 0) -> Interface:
     """registrator::CreateMatcher (interface.cc:139-173)."""
     t = Type(options.type)
@@ -208,7 +276,9 @@ def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 
     elif t in (Type.kLibicp, Type.kLegoLoam):
         raise CheckFailure("The registrator using libicp & lego-loam is deprecated. "
                            "please choose another type")   # LOG(FATAL), interface.cc:154-157
-    elif t in (Type.kIcpPM, Type.kNdtWithGicp, Type.kNdt):
+    elif t == Type.kNdt:
+        matcher = Ndt(device)
+    elif t in (Type.kIcpPM, Type.kNdtWithGicp):
         raise NotImplementedError(f"matcher type {t.name} is not built yet in sm_b200")
     else:
         print("Wrong type")   # PRINT_ERROR + nullptr, interface.cc:158-160

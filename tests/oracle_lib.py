@@ -25,6 +25,11 @@ class IcpTrace(C.Structure):
                 ("A", C.c_double * 36), ("b", C.c_double * 6)]
 
 
+class NdtOptions(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+                ("transformation_epsilon", C.c_double), ("max_iterations", C.c_int32)]
+
+
 _lib = None
 
 
@@ -52,7 +57,63 @@ def lib():
         _lib.sm_oracle_solve6.argtypes = [dp, dp, dp, C.POINTER(C.c_int)]
         _lib.sm_oracle_quantile_index.argtypes = [C.c_int64, C.c_float]
         _lib.sm_oracle_check_convergence_inputs.argtypes = [dp, C.c_int, C.POINTER(C.c_int)]
+        fp, i64 = C.POINTER(C.c_float), C.c_int64
+        _lib.sm_oracle_ndt_voxels.restype = C.c_int64
+        _lib.sm_oracle_ndt_voxels.argtypes = [fp, i64, C.c_float, i64, ip, ip, dp, dp, fp, ip]
+        _lib.sm_oracle_ndt_derivatives.argtypes = [fp, i64, fp, i64, C.POINTER(NdtOptions), dp, dp, dp, dp, dp]
+        _lib.sm_oracle_ndt_align.argtypes = [fp, i64, fp, i64, dp, C.POINTER(NdtOptions), dp, dp, ip, dp, dp]
     return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _fcloud(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    assert a.ndim == 2 and a.shape[1] == 3
+    return a
+
+
+def ndt_options(**kw):
+    o = NdtOptions(1.0, 0.1, 0.55, 0.1, 35)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def ndt_voxels(target, resolution=1.0):
+    t = _fcloud(target)
+    cap = t.shape[0]
+    idx = np.zeros(cap, np.int32); npts = np.zeros(cap, np.int32); srch = np.zeros(cap, np.int32)
+    mean = np.zeros((cap, 3)); icov = np.zeros((cap, 9)); cen = np.zeros((cap, 3), np.float32)
+    k = lib().sm_oracle_ndt_voxels(_f(t), t.shape[0], resolution, cap, _i(idx), _i(npts), _d(mean), _d(icov),
+                                   _f(cen), _i(srch))
+    return {"idx": idx[:k], "n": npts[:k], "mean": mean[:k], "icov": icov[:k].reshape(-1, 3, 3),
+            "centroid": cen[:k], "searchable": srch[:k]}
+
+
+def ndt_derivatives(source, target, p, **opts):
+    s, t = _fcloud(source), _fcloud(target)
+    o = ndt_options(**opts)
+    pp = np.ascontiguousarray(np.asarray(p, dtype=np.float64))
+    score = C.c_double(); nb = C.c_double()
+    g = np.zeros(6); H = np.zeros(36)
+    lib().sm_oracle_ndt_derivatives(_f(s), s.shape[0], _f(t), t.shape[0], C.byref(o), _d(pp), C.byref(score),
+                                    _d(g), _d(H), C.byref(nb))
+    return score.value, g, H.reshape(6, 6), nb.value
+
+
+def ndt_align(source, target, guess=None, **opts):
+    s, t = _fcloud(source), _fcloud(target)
+    o = ndt_options(**opts)
+    g = np.eye(4) if guess is None else np.asarray(guess, dtype=np.float64)
+    g_cm = np.ascontiguousarray(g.T).ravel()
+    res = np.zeros(16); fit = C.c_double(); it = C.c_int32(); tp = C.c_double(); nb = C.c_double()
+    rc = lib().sm_oracle_ndt_align(_f(s), s.shape[0], _f(t), t.shape[0], _d(g_cm), C.byref(o), _d(res),
+                                   C.byref(fit), C.byref(it), C.byref(tp), C.byref(nb))
+    return {"rc": rc, "result": res.reshape(4, 4).T.copy(), "fitness": fit.value, "iterations": it.value,
+            "trans_probability": tp.value, "mean_neighbors": nb.value}
 
 
 def _d(a):
