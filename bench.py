@@ -223,30 +223,64 @@ class Worker:
         return int(self.src.nbytes + self.tp.nbytes + self.tn.nbytes + 128)
 
 
-def run_concurrent(torch, workers, steps, host):
-    """`steps` alignments spread round-robin over the workers, all in flight together.
+def run_concurrent(torch, workers, steps, host, n_threads=4):
+    """`steps` alignments over len(workers) pipelines.  Each of `n_threads` host threads owns a
+    slice of the workers and keeps all of them in flight with sm_align_async / sm_align_wait
+    (the reference gets the same concurrency from its thread pool / TBB tasks).
     Device time of the whole region: an event before (every worker stream waits on it) and
     an event after (it waits on every worker's last kernel), both on one timing stream."""
-    share = [len(range(w, steps, len(workers))) for w in range(len(workers))]
+    n_threads = max(1, min(n_threads, len(workers)))
     tstream = torch.cuda.Stream()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     results = [[] for _ in workers]
-    gate = threading.Barrier(len(workers) + 1)
+    share = [len(range(w, steps, len(workers))) for w in range(len(workers))]
     errors = []
+    gate = threading.Barrier(n_threads + 1)
 
-    def body(i):
+    def collect(i):
         w = workers[i]
+        ok, res = w.m.AlignWait()
+        w.launches += w.m.GetAlignInfo()["kernel_launches"] + 3
+        w.last = (res, w.m.GetFitnessScore())
+        results[i].append((res, w.last[1]))
+        w.busy = False
+
+    def body(t):
+        mine = list(range(t, len(workers), n_threads))
+        left = {i: share[i] for i in mine}
         try:
             gate.wait()
-            for _ in range(share[i]):
-                results[i].append((w.step_host() if host else w.step_device(), w.last[1]))
+            while any(left[i] > 0 for i in mine):
+                for i in mine:
+                    if left[i] <= 0:
+                        continue
+                    w = workers[i]
+                    if w.busy:
+                        collect(i)
+                    m = w.m
+                    if host:
+                        m._check(m._lib.sm_set_input_target(m._h, w.h_tp.data_ptr(), w.h_tn.data_ptr(), w.nt),
+                                 "SetInputTarget")
+                        m._check(m._lib.sm_set_input_source(m._h, w.h_src.data_ptr(), N_SOURCE), "SetInputSource")
+                    else:
+                        m.SetInputTargetDevice(w.d_tp.data_ptr(), w.d_tn.data_ptr(), w.nt)
+                        m.SetInputSourceDevice(w.d_src.data_ptr(), N_SOURCE)
+                    m.AlignAsync(w.guess)
+                    w.busy = True
+                    left[i] -= 1
+            for i in mine:
+                if workers[i].busy:
+                    collect(i)
         except Exception as e:  # noqa: BLE001
             errors.append(e)
-        w.done = torch.cuda.Event()
-        w.done.record(w.stream)
+        for i in mine:
+            workers[i].done = torch.cuda.Event()
+            workers[i].done.record(workers[i].stream)
 
-    threads = [threading.Thread(target=body, args=(i,)) for i in range(len(workers))]
+    threads = [threading.Thread(target=body, args=(t,)) for t in range(n_threads)]
+    for w in workers:
+        w.busy = False
     for t in threads:
         t.start()
     torch.cuda.synchronize()
@@ -274,6 +308,8 @@ def main():
     ap.add_argument("--inflight", type=int, default=8,
                     help="alignments in flight per GPU (the reference runs 5-6 concurrent Align "
                          "calls from its thread pool / TBB tasks)")
+    ap.add_argument("--host-threads", type=int, default=4,
+                    help="host threads that share the in-flight pipelines")
     ap.add_argument("--cpu-baseline-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -333,8 +369,8 @@ def main():
         return float(t.item())
 
     # ---- warm-up ---------------------------------------------------------------------------
-    run_concurrent(torch, workers, args.warmup * P, host=False)
-    run_concurrent(torch, workers, args.warmup * P, host=True)
+    run_concurrent(torch, workers, args.warmup * P, False, args.host_threads)
+    run_concurrent(torch, workers, args.warmup * P, True, args.host_threads)
     res_check = w0.step_device()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -342,7 +378,7 @@ def main():
     # ---- timed: device-resident inputs, P alignments in flight --------------------------------
     for w in workers:
         w.launches = 0
-    ms_dev, results = run_concurrent(torch, workers, args.steps, host=False)
+    ms_dev, results = run_concurrent(torch, workers, args.steps, False, args.host_threads)
     gpu_launches = sum(w.launches for w in workers)
     # the one collective of the path: all-gather of the poses (17 doubles per pair)
     allgather_ms = 0.0
@@ -358,7 +394,7 @@ def main():
     ms_dev_total = max_over_ranks(ms_dev + allgather_ms)
     # ---- timed: host buffers through the public API (H2D inside) ---------------------------
     barrier()
-    ms_e2e, _ = run_concurrent(torch, workers, args.steps, host=True)
+    ms_e2e, _ = run_concurrent(torch, workers, args.steps, True, args.host_threads)
     barrier()
     ms_e2e_total = max_over_ranks(ms_e2e)
     # ---- latency: one alignment in flight, L2 flushed before each -----------------------------
@@ -403,6 +439,7 @@ def main():
 
     cfg = workload_config(w0.nt)
     cfg["pairs_in_flight_per_gpu"] = P
+    cfg["host_threads"] = args.host_threads
     cfg["l2"] = (f"{P} distinct pairs in flight per GPU (combined working set ~{25 * P} MB vs 126 MB L2); "
                  "the latency figures flush L2 (256 MiB memset) before every step")
     out = {
@@ -432,6 +469,14 @@ def main():
                       f"rebuilt each time), OpenMP over queries with {cores} threads"}
     if rank == 0:
         print(json.dumps(out), flush=True)
+    # orderly teardown: drain the GPU and destroy the engine handles before the interpreter
+    # (and torch's CUDA context) goes away
+    torch.cuda.synchronize()
+    for w in workers:
+        w.m.SetStream(0)
+        w.m.__del__()
+    del workers, w0
+    torch.cuda.synchronize()
     if world > 1:
         dist.destroy_process_group()
 

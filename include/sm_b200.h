@@ -98,6 +98,14 @@ int sm_set_input_target_device(sm_handle* h, const double* dev_points_3xn,
  * IcpFast::Align icp_fast.cc:455-529).  Returns 1 (true) / 0 (false) like the
  * reference's bool, or a negative sm_error. */
 int sm_align(sm_handle* h, const double* guess_4x4, double* result_4x4);
+/* The same Align in two halves, so ONE host thread can keep several matcher instances in
+ * flight (the reference gets its concurrency from a thread pool / TBB tasks calling Align on
+ * distinct instances: map_builder.cc:655,706-708; loop_detector.cc:224-228):
+ * sm_align_async enqueues everything and returns; sm_align_wait blocks for the result (and,
+ * with the convergence test enabled, keeps enqueuing 8-iteration chunks until it fires).
+ * IcpFast only; sm_align == async + wait. */
+int sm_align_async(sm_handle* h, const double* guess_4x4);
+int sm_align_wait(sm_handle* h, double* result_4x4);
 /* Interface::GetFitnessScore (interface.h:100). */
 double sm_get_fitness_score(const sm_handle* h);
 

@@ -44,6 +44,8 @@ SIGNATURES = {
     "sm_set_input_source_device": (C.c_int, [_VP, _VP, C.c_int64]),
     "sm_set_input_target_device": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sm_align": (C.c_int, [_VP, _DP, _DP]),
+    "sm_align_async": (C.c_int, [_VP, _DP]),
+    "sm_align_wait": (C.c_int, [_VP, _DP]),
     "sm_get_fitness_score": (C.c_double, [_VP]),
     "sm_get_align_info": (C.c_int, [_VP, C.POINTER(AlignInfo)]),
     "sm_set_stream": (C.c_int, [_VP, _VP]),

@@ -144,10 +144,8 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 // -------------------------------------------------------------------------------- phase A
 __global__ void __launch_bounds__(kKnnThreads)
 icp_knn_kernel(IcpBuffers b, IcpParams p) {
-  __shared__ uint32_t hist[kHistBins];
   __shared__ double T[16];
   if (b.state->done) return;
-  for (int i = threadIdx.x; i < kHistBins; i += kKnnThreads) hist[i] = 0;
   if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
   __syncthreads();
   const int i = blockIdx.x * kKnnThreads + threadIdx.x;
@@ -178,12 +176,9 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
     }
     b.slot[i] = slot;
     b.d2[i] = d2;
-    if (finite_d2(d2)) atomicAdd(&hist[dist_bin(d2)], 1u);
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < kHistBins; k += kKnnThreads) {
-    const uint32_t c = hist[k];
-    if (c) atomicAdd(&b.hist[k], c);
+    // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident);
+    // no block-level staging, so a warp retires as soon as its own queries are done
+    if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
   }
 }
 

@@ -111,12 +111,13 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
                                               const BucketPoint* __restrict__ bpts, double qx,
                                               double qy, double qz, double max_error2, int idx,
                                               double rd, double ox, double oy, double oz,
-                                              double& head, int& best, int max_rounds = 1 << 30) {
+                                              double& head, int& best, int max_rounds = 1 << 20) {
   StackEntry stack[kMaxStack];
   int sp = 0;
   while (max_rounds-- > 0) {
     KdNode nd = load_node(nodes, idx);
-    while (nd.dim != 3) {
+    int guard = 0;
+    while (nd.dim != 3 && ++guard < 64) {   // a valid tree is at most 25 levels deep
       const int cd = nd.dim;
       const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
       const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
@@ -136,7 +137,7 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
       idx = child_idx(idx, right);
       nd = load_node(nodes, idx);
     }
-    scan_leaf(bpts, nd, qx, qy, qz, head, best);
+    if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
     bool found = false;
     while (sp > 0) {
       const StackEntry e = stack[--sp];
@@ -166,14 +167,15 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
   int idx = 0;
   double min_off2 = inf;
   KdNode nd = load_node(nodes, 0);
-  while (nd.dim != 3) {
+  int guard = 0;
+  while (nd.dim != 3 && ++guard < 64) {
     const double q = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
     const double off = dsub(q, nd.cut);
     min_off2 = fmin(min_off2, dmul(off, off));
     idx = child_idx(idx, (off > 0.0) ? 1 : 0);
     nd = load_node(nodes, idx);
   }
-  scan_leaf(bpts, nd, qx, qy, qz, head, best);
+  if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
   // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
   if (dmul(min_off2, max_error2) < head)
     visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds);

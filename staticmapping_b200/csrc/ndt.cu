@@ -227,7 +227,7 @@ __global__ void ndt_hash_insert_kernel(const int* __restrict__ voxel_key, const 
   if (v >= grid->n_voxels || !leaves[v].searchable) return;
   const int key = voxel_key[v];
   uint32_t h = hash_voxel(key) & table_mask;
-  while (true) {
+  for (uint32_t probes = 0; probes <= table_mask; ++probes) {
     const int prev = atomicCAS(&table_key[h], -1, key);
     if (prev == -1 || prev == key) { table_val[h] = v; return; }
     h = (h + 1) & table_mask;
@@ -237,12 +237,13 @@ __global__ void ndt_hash_insert_kernel(const int* __restrict__ voxel_key, const 
 __device__ __forceinline__ int hash_lookup(const int* __restrict__ table_key, const int* __restrict__ table_val,
                                            uint32_t mask, int key) {
   uint32_t h = hash_voxel(key) & mask;
-  while (true) {
+  for (uint32_t probes = 0; probes <= mask; ++probes) {   // bounded: never spins on a bad table
     const int k = __ldg(table_key + h);
     if (k == key) return __ldg(table_val + h);
     if (k == -1) return -1;
     h = (h + 1) & mask;
   }
+  return -1;
 }
 
 // ---- derivatives ----------------------------------------------------------------------------

@@ -95,6 +95,15 @@ struct sm_handle {
   IcpState* host_state = nullptr;  // pinned
   std::vector<cudaEvent_t> prof_events;
   GraphCache g_prologue, g_iterations;
+  // in-flight Align (sm_align_async .. sm_align_wait)
+  struct IcpRun {
+    IcpBuffers b; IcpParams p; KdWorkspace ws; std::string key;
+    bool graphs = false, active = false;
+    int enqueued = 0, launches = 0, max_it = 0;
+  } run;
+  double* host_guess = nullptr;    // pinned, 16 doubles
+  cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool up_src = false, up_tgt = false;
   // NDT
   ndt::Options ndt;
   DevBuf src_f32, tgt_f32, ndt_ws, tgt_soa;
@@ -196,14 +205,11 @@ int set_source(sm_handle* h, const double* pts, int64_t n, bool on_device) {
   if (!pts || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInputSource: empty cloud");
   if (n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInputSource: too many points");
   H_CUDA(cudaSetDevice(h->device));
-  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  H_CUDA(cudaEventRecord(h->ev_up[0], h->stream));
   h->sstride = pad64(n);
   H_RC(load_cloud(h, pts, n, on_device, h->src_raw, h->sstride));
-  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
-  H_CUDA(cudaEventSynchronize(h->ev[1]));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-  h->ms_upload = ms;
+  H_CUDA(cudaEventRecord(h->ev_up[1], h->stream));
+  h->up_src = true;
   h->n_source = n;
   h->has_source = true;
   return 0;
@@ -216,15 +222,12 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
     return fail(h, SM_ERR_MISSING_INPUT, "SetInputTarget: IcpFast target needs normals");
   if (n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInputTarget: too many points");
   H_CUDA(cudaSetDevice(h->device));
-  H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  H_CUDA(cudaEventRecord(h->ev_up[2], h->stream));
   h->tstride = pad64(n);
   H_RC(load_cloud(h, pts, n, on_device, h->tgt_raw, h->tstride));
   if (nrm) H_RC(load_cloud(h, nrm, n, on_device, h->nrm, h->tstride));
-  H_CUDA(cudaEventRecord(h->ev[1], h->stream));
-  H_CUDA(cudaEventSynchronize(h->ev[1]));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-  h->ms_upload += ms;
+  H_CUDA(cudaEventRecord(h->ev_up[3], h->stream));
+  h->up_tgt = true;
   h->n_target = n;
   h->has_target = true;
   return 0;
@@ -232,7 +235,38 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
 
 int ndt_align(sm_handle* h, const double* guess, double* result);
 
-int icp_align(sm_handle* h, const double* guess, double* result) {
+// one chunk of iterations + the asynchronous read-back of the state record
+int icp_enqueue_chunk(sm_handle* h) {
+  sm_handle::IcpRun& r = h->run;
+  const IcpParams& p = r.p;
+  const int chunk = p.disable_convergence ? (r.max_it - r.enqueued)
+                                          : ((r.max_it - r.enqueued) < 8 ? (r.max_it - r.enqueued) : 8);
+  cudaEvent_t* evs = nullptr;
+  if (h->icp.profile_kernels) {
+    while ((int)h->prof_events.size() < 4 * (r.enqueued + chunk)) {
+      cudaEvent_t e; H_CUDA(cudaEventCreate(&e)); h->prof_events.push_back(e);
+    }
+    evs = h->prof_events.data() + 4 * r.enqueued;
+  }
+  if (r.graphs) {
+    std::string ikey = r.key;
+    key_append(ikey, chunk);
+    H_RC(run_graphed(h, h->g_iterations, ikey, [&]() {
+      return icp_enqueue_iterations(r.b, p, chunk, h->stream, nullptr);
+    }));
+  } else {
+    H_RC(icp_enqueue_iterations(r.b, p, chunk, h->stream, evs));
+  }
+  r.enqueued += chunk;
+  r.launches += 3 * chunk;
+  H_CUDA(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+// IcpFast::Align, first half: everything is enqueued, nothing is waited for
+int icp_begin(sm_handle* h, const double* guess) {
+  sm_handle::IcpRun& r = h->run;
+  r.active = false;
   if (!h->has_source || !h->has_target)
     return fail(h, SM_ERR_MISSING_INPUT, "Align: source/target not set");
   const int ns = (int)h->n_source, nt = (int)h->n_target;
@@ -257,10 +291,10 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   H_RC(h->state.reserve(sizeof(IcpState)));
   H_RC(h->guess.reserve(16 * sizeof(double)));
   H_RC(h->kdws.reserve(KdWorkspace::bytes_needed(nt, 8)));
-  KdWorkspace ws;
+  KdWorkspace& ws = r.ws;
   ws.carve(h->kdws.p, nt, 8);
 
-  IcpBuffers b;
+  IcpBuffers& b = r.b;
   b.tgt = (double*)h->tgt.p; b.tgt_raw = (double*)h->tgt_raw.p; b.nrm = (double*)h->nrm.p;
   b.tstride = h->tstride;
   b.nodes = (KdNode*)h->nodes.p; b.leaf_order = (uint32_t*)h->leaf_order.p;
@@ -277,7 +311,7 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   b.cand_key = (unsigned long long*)h->cand_key.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
   b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
   b.state = (IcpState*)h->state.p;
-  IcpParams p;
+  IcpParams& p = r.p;
   p.n_source = ns; p.n_target = nt;
   p.max_iteration = h->icp.max_iteration;
   p.dist_outlier_ratio = h->icp.dist_outlier_ratio;
@@ -288,47 +322,37 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   p.tree_levels = levels;
   if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large (tree deeper than 24 levels)");
 
-  H_CUDA(cudaMemcpyAsync(h->guess.p, guess, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  memcpy(h->host_guess, guess, 16 * sizeof(double));   // pinned: the caller's array may go away
+  H_CUDA(cudaMemcpyAsync(h->guess.p, h->host_guess, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   H_CUDA(cudaEventRecord(h->ev[0], h->stream));
-  const bool graphs = h->icp.use_graphs && !h->icp.profile_kernels;
-  std::string key;
-  key_append(key, b); key_append(key, p); key_append(key, h->guess.p); key_append(key, h->kdws.p);
-  if (graphs) {
-    H_RC(run_graphed(h, h->g_prologue, key, [&]() {
+  r.graphs = h->icp.use_graphs && !h->icp.profile_kernels;
+  r.key.clear();
+  key_append(r.key, b); key_append(r.key, p); key_append(r.key, h->guess.p); key_append(r.key, h->kdws.p);
+  if (r.graphs) {
+    H_RC(run_graphed(h, h->g_prologue, r.key, [&]() {
       return icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream);
     }));
   } else {
     H_RC(icp_prologue(b, p, (const double*)h->guess.p, ws, h->stream));
   }
   H_CUDA(cudaEventRecord(h->ev[1], h->stream));
-  int launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2 + 13;
-  int enqueued = 0;
-  const int max_it = p.max_iteration > 0 ? p.max_iteration : 1;
+  r.launches = 2 + 1 + 24 + levels * 5 + 1 + 1 + 2 + 13;
+  r.enqueued = 0;
+  r.max_it = p.max_iteration > 0 ? p.max_iteration : 1;
+  H_RC(icp_enqueue_chunk(h));
+  r.active = true;
+  return 0;
+}
+
+// second half: wait, continue in chunks while the convergence test has not fired, report
+int icp_end(sm_handle* h, double* result) {
+  sm_handle::IcpRun& r = h->run;
+  if (!r.active) return fail(h, SM_ERR_BAD_ARGUMENT, "sm_align_wait without sm_align_async");
+  r.active = false;
   while (true) {
-    const int chunk = p.disable_convergence ? (max_it - enqueued)
-                                            : ((max_it - enqueued) < 8 ? (max_it - enqueued) : 8);
-    cudaEvent_t* evs = nullptr;
-    if (h->icp.profile_kernels) {
-      while ((int)h->prof_events.size() < 4 * (enqueued + chunk)) {
-        cudaEvent_t e; H_CUDA(cudaEventCreate(&e)); h->prof_events.push_back(e);
-      }
-      evs = h->prof_events.data() + 4 * enqueued;
-    }
-    if (graphs) {
-      std::string ikey = key;
-      key_append(ikey, chunk);
-      H_RC(run_graphed(h, h->g_iterations, ikey, [&]() {
-        return icp_enqueue_iterations(b, p, chunk, h->stream, nullptr);
-      }));
-    } else {
-      H_RC(icp_enqueue_iterations(b, p, chunk, h->stream, evs));
-    }
-    enqueued += chunk;
-    launches += 3 * chunk;
-    H_CUDA(cudaMemcpyAsync(h->host_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost,
-                           h->stream));
     H_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->host_state->done || enqueued >= max_it) break;
+    if (h->host_state->done || r.enqueued >= r.max_it) break;
+    H_RC(icp_enqueue_chunk(h));
   }
   H_CUDA(cudaEventRecord(h->ev[2], h->stream));
   H_CUDA(cudaEventSynchronize(h->ev[2]));
@@ -338,10 +362,14 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   h->info.solve_path = st.solve_path;
   h->info.kept = st.kept;
   h->info.limit = st.limit;
-  h->info.ms_upload = h->ms_upload;
+  h->info.ms_upload = 0.f;
+  float ms = 0.f;
+  if (h->up_src && cudaEventElapsedTime(&ms, h->ev_up[0], h->ev_up[1]) == cudaSuccess) h->info.ms_upload += ms;
+  if (h->up_tgt && cudaEventElapsedTime(&ms, h->ev_up[2], h->ev_up[3]) == cudaSuccess) h->info.ms_upload += ms;
+  h->up_src = h->up_tgt = false;
   cudaEventElapsedTime(&h->info.ms_prologue, h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&h->info.ms_iterations, h->ev[1], h->ev[2]);
-  h->info.kernel_launches = launches;
+  h->info.kernel_launches = r.launches;
   h->info.ms_knn = h->info.ms_accum = h->info.ms_finish = 0.f;
   h->info.profiled_iterations = 0;
   if (h->icp.profile_kernels) {
@@ -354,7 +382,6 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
       h->info.profiled_iterations++;
     }
   }
-  h->ms_upload = 0.f;
   if (st.status < 0)
     return fail(h, st.status, st.status == -2 ? "Align: no finite match distance (icp_fast.cc:81)"
                                               : "Align: no point to minimize (icp_fast.cc:114)");
@@ -363,6 +390,10 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
   return 1;  // IcpFast::Align always returns true (icp_fast.cc:528)
 }
 
+int icp_align(sm_handle* h, const double* guess, double* result) {
+  H_RC(icp_begin(h, guess));
+  return icp_end(h, result);
+}
 
 // ---- Ndt ---------------------------------------------------------------------------------
 int load_cloud_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride, bool on_device, DevBuf& dst) {
@@ -527,13 +558,14 @@ int sm_create(int type, int device, sm_handle** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->host_sums, 64 * sizeof(double)) != cudaSuccess) {
+      cudaMallocHost((void**)&h->host_sums, 64 * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->host_guess, 16 * sizeof(double)) != cudaSuccess) {
     delete h;
     return SM_ERR_CUDA;
   }
   h->stream = h->own_stream;
   if (knn_configure() != 0) { sm_destroy(h); return SM_ERR_CUDA; }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 4; ++i) { cudaEventCreate(&h->ev[i]); cudaEventCreate(&h->ev_up[i]); }
   *out = h;
   return SM_OK;
 }
@@ -551,6 +583,8 @@ int sm_destroy(sm_handle* h) {
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->host_state) cudaFreeHost(h->host_state);
   if (h->host_sums) cudaFreeHost(h->host_sums);
+  if (h->host_guess) cudaFreeHost(h->host_guess);
+  for (int i = 0; i < 4; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
   h->src_f32.release(); h->tgt_f32.release(); h->ndt_ws.release(); h->tgt_soa.release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -657,6 +691,19 @@ int sm_align(sm_handle* h, const double* guess, double* result) {
   if (h->type == SM_TYPE_FAST_ICP) return icp_align(h, guess, result);
   if (h->type == SM_TYPE_NDT) return ndt_align(h, guess, result);
   return fail(h, SM_ERR_UNSUPPORTED_TYPE, "matcher type not supported");
+}
+
+int sm_align_async(sm_handle* h, const double* guess) {
+  if (!h || !guess) return SM_ERR_BAD_ARGUMENT;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
+  if (h->type != SM_TYPE_FAST_ICP) return fail(h, SM_ERR_UNSUPPORTED_TYPE, "sm_align_async: IcpFast only");
+  return icp_begin(h, guess);
+}
+
+int sm_align_wait(sm_handle* h, double* result) {
+  if (!h || !result) return SM_ERR_BAD_ARGUMENT;
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
+  return icp_end(h, result);
 }
 
 double sm_get_fitness_score(const sm_handle* h) { return h ? h->final_score : 0.0; }

@@ -176,6 +176,17 @@ class Interface:
                                             res.ctypes.data_as(_lib._DP)), "Align")
         return bool(rc), res.reshape(4, 4).T.copy()
 
+    def AlignAsync(self, guess):
+        """First half of Align: enqueue and return (engine extension, see sm_align_async)."""
+        g = np.ascontiguousarray(np.asarray(guess, dtype=np.float64).T).ravel()
+        self._check(self._lib.sm_align_async(self._h, g.ctypes.data_as(_lib._DP)), "AlignAsync")
+
+    def AlignWait(self):
+        """Second half of Align: returns (ok, result 4x4)."""
+        res = np.zeros(16, dtype=np.float64)
+        rc = self._check(self._lib.sm_align_wait(self._h, res.ctypes.data_as(_lib._DP)), "AlignWait")
+        return bool(rc), res.reshape(4, 4).T.copy()
+
     def GetFitnessScore(self):
         return float(self._lib.sm_get_fitness_score(self._h))
 
