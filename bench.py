@@ -42,8 +42,9 @@ ITERATIONS = 30
 BYTES_PER_POINT_ITER = 64           # whole iteration
 BYTES_KNN_PER_POINT = 40            # of which the k-NN kernel: 16 src + 16 matched + 8 write
 # dram__bytes_read+write of icp_knn_kernel from the committed ncu --set full capture
-# (profiles/r01_ncu_full_icp_knn_*.txt; cold caches: ncu flushes between replays)
-NCU_TRAFFIC_BYTES = 24_157_696
+# (profiles/r01_ncu_full_icp_knn_v2.txt, --cache-control none: warm L2, the steady state of an
+# alignment; with ncu's default cache flush the same kernel reads 19.7 MB cold)
+NCU_TRAFFIC_BYTES = 2_062_848
 METRIC = "scan-pair alignments/sec (120k->500k pts, 30 ICP iters)"
 UNIT = "alignments/s"
 
