@@ -35,6 +35,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# more hardware work queues than the default 8, so that the per-pipeline streams do not alias
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SOURCE = 120_000
 N_SUBMAP = 500_000
@@ -306,10 +308,10 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--inflight", type=int, default=8,
+    ap.add_argument("--inflight", type=int, default=16,
                     help="alignments in flight per GPU (the reference runs 5-6 concurrent Align "
                          "calls from its thread pool / TBB tasks)")
-    ap.add_argument("--host-threads", type=int, default=4,
+    ap.add_argument("--host-threads", type=int, default=8,
                     help="host threads that share the in-flight pipelines")
     ap.add_argument("--cpu-baseline-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
