@@ -129,6 +129,10 @@ typedef struct sm_align_info {
   int32_t evaluations;        /* computeDerivatives calls (ndt_omp_impl.hpp:180) */
   double trans_probability;   /* score / N_source (ndt_omp_impl.hpp:170) */
   double mean_neighbors;      /* mean number of neighbour voxels per source point */
+  /* NdtWithGicp only: [0] NDT fitness (the <= 1.0 gate, ndt_gicp.cc:92), [1] GICP fitness,
+   * [2] source points after ApproximateVoxelGrid, [3] target points after it;
+   * iterations = GICP outer iterations, profiled_iterations = BFGS cost evaluations */
+  double aux[4];
 } sm_align_info;
 int sm_get_align_info(const sm_handle* h, sm_align_info* out);
 

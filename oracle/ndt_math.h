@@ -211,6 +211,91 @@ inline double ndt_update_derivatives(const NdtAngular* ang, const NdtGauss* g, c
   return (double)score_inc;
 }
 
+// ---- stock pcl::NormalDistributionsTransform (PCL 1.8 ndt.hpp): the same derivatives with
+// double Eigen matrices (the in-tree double overloads ndt_omp_impl.hpp:441-481 and
+// updateHessian :596-629 are that code).  Used by NdtWithGicp (ndt_gicp.h:62-68).
+struct NdtAngularD {
+  double j[8][3];
+  double h[15][3];
+};
+inline void ndt_angle_derivatives_f64(const double* p, NdtAngularD* a) {
+  NdtAngular tmp;   // same formulas; recompute in double instead of copying the float casts
+  (void)tmp;
+  double cx, cy, cz, sx, sy, sz;
+  if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
+  if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
+  if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
+  const double J[8][3] = {
+      {(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
+      {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
+      {(-sy * cz), sy * sz, cy},
+      {sx * cy * cz, (-sx * cy * sz), sx * sy},
+      {(-cx * cy * cz), cx * cy * sz, (-cx * sy)},
+      {(-cy * sz), (-cy * cz), 0},
+      {(cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0},
+      {(sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0}};
+  const double H[15][3] = {
+      {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy},
+      {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy)},
+      {(cx * cy * cz), (-cx * cy * sz), (cx * sy)},
+      {(sx * cy * cz), (-sx * cy * sz), (sx * sy)},
+      {(-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0},
+      {(cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0},
+      {(-cy * cz), (cy * sz), (sy)},
+      {(-sx * sy * cz), (sx * sy * sz), (sx * cy)},
+      {(cx * sy * cz), (-cx * sy * sz), (-cx * cy)},
+      {(sy * sz), (sy * cz), 0},
+      {(-sx * cy * sz), (-sx * cy * cz), 0},
+      {(cx * cy * sz), (cx * cy * cz), 0},
+      {(-cy * cz), (cy * sz), 0},
+      {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},
+      {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};
+  for (int r = 0; r < 8; ++r) for (int c = 0; c < 3; ++c) a->j[r][c] = J[r][c];
+  for (int r = 0; r < 15; ++r) for (int c = 0; c < 3; ++c) a->h[r][c] = H[r][c];
+}
+
+inline double ndt_update_derivatives_f64(const NdtAngularD* ang, const NdtGauss* g, const float* x_orig,
+                                         const float* x_trans_f, const double* mean, const double* icov,
+                                         double* grad_pt, double* hess_pt) {
+  const double x[3] = {(double)x_orig[0], (double)x_orig[1], (double)x_orig[2]};
+  double xj[8], xh[15];
+  for (int r = 0; r < 8; ++r) xj[r] = (x[0] * ang->j[r][0] + x[1] * ang->j[r][1]) + x[2] * ang->j[r][2];
+  for (int r = 0; r < 15; ++r) xh[r] = (x[0] * ang->h[r][0] + x[1] * ang->h[r][1]) + x[2] * ang->h[r][2];
+  const double pg[3][6] = {{1, 0, 0, 0, xj[2], xj[5]}, {0, 1, 0, xj[0], xj[3], xj[6]}, {0, 0, 1, xj[1], xj[4], xj[7]}};
+  const double va[3] = {0, xh[0], xh[1]}, vb[3] = {0, xh[2], xh[3]}, vc[3] = {0, xh[4], xh[5]};
+  const double vd[3] = {xh[6], xh[7], xh[8]}, ve[3] = {xh[9], xh[10], xh[11]}, vf[3] = {xh[12], xh[13], xh[14]};
+  const double* ph[3][3] = {{va, vb, vc}, {vb, vd, ve}, {vc, ve, vf}};
+  double xt[3];
+  for (int d = 0; d < 3; ++d) xt[d] = (double)x_trans_f[d] - mean[d];
+  double cx[3];   // c_inv * x_trans
+  for (int r = 0; r < 3; ++r) cx[r] = (icov[r * 3] * xt[0] + icov[r * 3 + 1] * xt[1]) + icov[r * 3 + 2] * xt[2];
+  double e = std::exp(-g->d2 * ((xt[0] * cx[0] + xt[1] * cx[1]) + xt[2] * cx[2]) / 2);
+  const double score_inc = -g->d1 * e;
+  e = g->d2 * e;
+  if (e > 1 || e < 0 || e != e) return 0.0;
+  e *= g->d1;
+  double cdp[6][3], xdot[6];   // c_inv * point_gradient.col(i), x_trans . that
+  for (int i = 0; i < 6; ++i) {
+    for (int r = 0; r < 3; ++r) cdp[i][r] = (icov[r * 3] * pg[0][i] + icov[r * 3 + 1] * pg[1][i]) + icov[r * 3 + 2] * pg[2][i];
+    xdot[i] = (xt[0] * cdp[i][0] + xt[1] * cdp[i][1]) + xt[2] * cdp[i][2];
+  }
+  for (int i = 0; i < 6; ++i) {
+    grad_pt[i] += xdot[i] * e;
+    for (int j = 0; j < 6; ++j) {
+      double hterm = 0.0;   // x_trans . (c_inv * point_hessian.block<3,1>(3i, j))
+      if (i >= 3 && j >= 3) {
+        const double* v = ph[i - 3][j - 3];
+        double cv[3];
+        for (int r = 0; r < 3; ++r) cv[r] = (icov[r * 3] * v[0] + icov[r * 3 + 1] * v[1]) + icov[r * 3 + 2] * v[2];
+        hterm = (xt[0] * cv[0] + xt[1] * cv[1]) + xt[2] * cv[2];
+      }
+      const double gdot = (pg[0][j] * cdp[i][0] + pg[1][j] * cdp[i][1]) + pg[2][j] * cdp[i][2];
+      hess_pt[i * 6 + j] += e * ((-g->d2 * xdot[i] * xdot[j] + hterm) + gdot);
+    }
+  }
+  return score_inc;
+}
+
 // Translation(p0..2) * AngleAxis(p3, X) * AngleAxis(p4, Y) * AngleAxis(p5, Z), single
 // precision (ndt_omp_impl.hpp:146-149, 809-812).  T: 4x4 column-major floats.
 inline void axis_rotation_f(float angle, int axis, float* R) {   // AngleAxis::toRotationMatrix

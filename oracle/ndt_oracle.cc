@@ -32,6 +32,9 @@
 
 namespace sm_oracle {
 
+int NdtAlignCore(const float* source, int64_t ns, const float* target, int64_t nt, const double* guess,
+                 const sm_oracle_ndt_options* opt, bool f64_math, double* result, double* fitness,
+                 int32_t* iterations, double* trans_probability, double* mean_neighbors);
 // implemented in sm_oracle.cc
 int ExactNn1Float(const float* target_xyz, int64_t nt, const float* query_xyz, int64_t nq,
                   int32_t* ids_out);
@@ -124,9 +127,11 @@ struct VoxelGrid {
 // computeDerivatives (ndt_omp_impl.hpp:180-284), serial, points in index order.
 void ComputeDerivatives(const VoxelGrid& grid, const float* src, const float* trans, int64_t n,
                         const double p[6], const NdtGauss& g, float resolution, double* score_out,
-                        double grad[6], double hess[36], double* mean_neighbors) {
+                        double grad[6], double hess[36], double* mean_neighbors, bool f64_math = false) {
   NdtAngular ang;
+  NdtAngularD angd;
   ndt_angle_derivatives(p, &ang);
+  ndt_angle_derivatives_f64(p, &angd);
   double score = 0.0;
   for (int i = 0; i < 6; ++i) grad[i] = 0.0;
   for (int i = 0; i < 36; ++i) hess[i] = 0.0;
@@ -138,8 +143,11 @@ void ComputeDerivatives(const VoxelGrid& grid, const float* src, const float* tr
     double score_pt = 0.0, grad_pt[6] = {0, 0, 0, 0, 0, 0}, hess_pt[36];
     for (int q = 0; q < 36; ++q) hess_pt[q] = 0.0;
     for (int j = 0; j < k; ++j)
-      score_pt += ndt_update_derivatives(&ang, &g, src + 3 * i, trans + 3 * i, nb[j]->mean, nb[j]->icov,
-                                         grad_pt, hess_pt);
+      score_pt += f64_math
+                      ? ndt_update_derivatives_f64(&angd, &g, src + 3 * i, trans + 3 * i, nb[j]->mean, nb[j]->icov,
+                                                   grad_pt, hess_pt)
+                      : ndt_update_derivatives(&ang, &g, src + 3 * i, trans + 3 * i, nb[j]->mean, nb[j]->icov,
+                                               grad_pt, hess_pt);
     score += score_pt;
     for (int q = 0; q < 6; ++q) grad[q] += grad_pt[q];
     for (int q = 0; q < 36; ++q) hess[q] += hess_pt[q];
@@ -238,6 +246,19 @@ int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, in
                         const double* guess, const sm_oracle_ndt_options* opt, double* result,
                         double* fitness, int32_t* iterations, double* trans_probability,
                         double* mean_neighbors) {
+  return sm_oracle::NdtAlignCore(source, ns, target, nt, guess, opt, false, result, fitness, iterations,
+                                 trans_probability, mean_neighbors);
+}
+
+}  // extern "C"
+
+namespace sm_oracle {
+// f64_math = false: the vendored pclomp NDT (single-precision term math);
+// f64_math = true : stock pcl::NormalDistributionsTransform (double Eigen matrices), the class
+//                   NdtWithGicp uses (registrators/ndt_gicp.h:62-68) — same algorithm otherwise.
+int NdtAlignCore(const float* source, int64_t ns, const float* target, int64_t nt, const double* guess,
+                 const sm_oracle_ndt_options* opt, bool f64_math, double* result, double* fitness,
+                 int32_t* iterations, double* trans_probability, double* mean_neighbors) {
   if (ns <= 0 || nt <= 0) return 0;   // ndt.cc:40-42 returns false when a cloud is missing
   VoxelGrid grid;
   grid.Build(target, nt, opt->resolution);
@@ -259,7 +280,7 @@ int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, in
   ndt_p_from_transform(final_T, p);                      // :103-111
   double score = 0.0, grad[6], hess[36], nbm = 0.0, nb_sum = 0.0;
   int evals = 0;
-  ComputeDerivatives(grid, source, trans.data(), ns, p, g, opt->resolution, &score, grad, hess, &nbm);
+  ComputeDerivatives(grid, source, trans.data(), ns, p, g, opt->resolution, &score, grad, hess, &nbm, f64_math);
   nb_sum += nbm; ++evals;
   int nr_iterations = 0;
   bool converged = false;
@@ -287,7 +308,7 @@ int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, in
       for (int i = 0; i < 6; ++i) x_t[i] = p[i] + delta[i] * a_t;
       ndt_transform_from_p(x_t, final_T);                // :809-812
       for (int64_t i = 0; i < ns; ++i) ndt_transform_point(final_T, source + 3 * i, &trans[(size_t)(3 * i)]);
-      ComputeDerivatives(grid, source, trans.data(), ns, x_t, g, opt->resolution, &score, grad, hess, &nbm);
+      ComputeDerivatives(grid, source, trans.data(), ns, x_t, g, opt->resolution, &score, grad, hess, &nbm, f64_math);
       nb_sum += nbm; ++evals;
     }
   step_done:
@@ -319,4 +340,4 @@ int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, in
   return 1;
 }
 
-}  // extern "C"
+}  // namespace sm_oracle

@@ -227,6 +227,57 @@ struct KdTree {
     }
   }
 
+  // exact k nearest neighbours, result sorted by (squared distance, index) — the unique
+  // k smallest under that total order, so the answer does not depend on the visiting order
+  struct Cand { double d; int idx; };
+  static bool CandLess(const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.idx < b.idx); }
+  void RecurseK(const double* q, int n_idx, double rd, double off[3], std::vector<Cand>& best,
+                int k) const {
+    const KdNode& node = nodes[(size_t)n_idx];
+    if (node.dim == 3) {
+      for (int i = 0; i < node.bucket_count; ++i) {
+        const int index = buckets[(size_t)(node.bucket_first + i)];
+        const double* p = cloud + 3 * (size_t)index;
+        double dist = 0.0;
+        for (int r = 0; r < 3; ++r) { const double diff = q[r] - p[r]; dist += diff * diff; }
+        const Cand c{dist, index};
+        if ((int)best.size() < k) { best.push_back(c); std::push_heap(best.begin(), best.end(), CandLess); }
+        else if (CandLess(c, best.front())) {
+          std::pop_heap(best.begin(), best.end(), CandLess);
+          best.back() = c;
+          std::push_heap(best.begin(), best.end(), CandLess);
+        }
+      }
+      return;
+    }
+    const int cd = node.dim;
+    const double old_off = off[cd];
+    const double new_off = q[cd] - node.cut_val;
+    const int near = (new_off > 0.0) ? node.right_child : n_idx + 1;
+    const int far = (new_off > 0.0) ? n_idx + 1 : node.right_child;
+    RecurseK(q, near, rd, off, best, k);
+    rd += -old_off * old_off + new_off * new_off;
+    if ((int)best.size() < k || rd <= best.front().d) {
+      off[cd] = new_off;
+      RecurseK(q, far, rd, off, best, k);
+      off[cd] = old_off;
+    }
+  }
+  void KnnK(const double* query, int64_t nq, int k, int32_t* ids, double* d2) const {
+#pragma omp parallel for schedule(guided, 32)
+    for (int64_t i = 0; i < nq; ++i) {
+      double off[3] = {0.0, 0.0, 0.0};
+      std::vector<Cand> best;
+      best.reserve((size_t)k + 1);
+      if (!nodes.empty()) RecurseK(query + 3 * i, 0, 0.0, off, best, k);
+      std::sort(best.begin(), best.end(), CandLess);
+      for (int j = 0; j < k; ++j) {
+        ids[i * k + j] = j < (int)best.size() ? best[(size_t)j].idx : -1;
+        d2[i * k + j] = j < (int)best.size() ? best[(size_t)j].d : kInf;
+      }
+    }
+  }
+
   void Knn1(const double* query, int64_t nq, double epsilon, int32_t* ids,
             double* d2, int32_t* visits = nullptr) const {
     const double max_error2 = (1.0 + epsilon) * (1.0 + epsilon);
@@ -358,6 +409,17 @@ int ExactNn1Float(const float* target_xyz, int64_t nt, const float* query_xyz, i
   KdTree tree;
   tree.Build(t.data(), nt, 8, 0);
   tree.Knn1(q.data(), nq, 0.0, ids_out, d2.data());
+  return 0;
+}
+// Exact k-NN of float points (pcl::search::KdTree::nearestKSearch, gicp_omp_impl.hpp:88).
+int ExactKnnFloat(const float* target_xyz, int64_t nt, const float* query_xyz, int64_t nq, int k,
+                  int32_t* ids_out, double* d2_out) {
+  std::vector<double> t((size_t)(3 * nt)), q((size_t)(3 * nq));
+  for (int64_t i = 0; i < 3 * nt; ++i) t[(size_t)i] = (double)target_xyz[i];
+  for (int64_t i = 0; i < 3 * nq; ++i) q[(size_t)i] = (double)query_xyz[i];
+  KdTree tree;
+  tree.Build(t.data(), nt, 8, 0);
+  tree.KnnK(q.data(), nq, k, ids_out, d2_out);
   return 0;
 }
 }  // namespace sm_oracle

@@ -100,6 +100,23 @@ int sm_oracle_ndt_align(const float* source, int64_t ns, const float* target, in
                         double* fitness, int32_t* iterations, double* trans_probability,
                         double* mean_neighbors);
 
+/* ---- NdtWithGicp (registrators/ndt_gicp.cc:28-112, see oracle/gicp_oracle.cc) ------------ */
+typedef struct sm_oracle_ndt_gicp_options {
+  float voxel_resolution;        /* ndt_gicp.h:72, 0.2 */
+  int32_t using_voxel_filter;    /* :73, true */
+  int32_t use_ndt;               /* :74, true */
+} sm_oracle_ndt_gicp_options;
+typedef struct sm_oracle_ndt_gicp_info {
+  int64_t n_source_filtered, n_target_filtered;
+  int32_t ndt_iterations, gicp_iterations, bfgs_evaluations, pad;
+  double ndt_score, gicp_fitness;
+} sm_oracle_ndt_gicp_info;
+int64_t sm_oracle_approx_voxel_grid(const float* pts, int64_t n, float leaf, float* out, int64_t capacity);
+int sm_oracle_gicp_covariances(const float* pts, int64_t n, int k, double eps, double* cov_out);
+int sm_oracle_ndt_gicp_align(const float* source, int64_t ns, const float* target, int64_t nt,
+                             const double* guess, const sm_oracle_ndt_gicp_options* opt, double* result,
+                             double* final_score, sm_oracle_ndt_gicp_info* info);
+
 /* Pieces exposed for unit tests of the restatement itself. */
 int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
 int sm_oracle_quantile_index(int64_t n, float ratio);

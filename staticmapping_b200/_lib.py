@@ -19,7 +19,8 @@ class AlignInfo(C.Structure):
                 ("ms_iterations", C.c_float), ("kernel_launches", C.c_int32),
                 ("ms_knn", C.c_float), ("ms_accum", C.c_float), ("ms_finish", C.c_float),
                 ("profiled_iterations", C.c_int32), ("evaluations", C.c_int32),
-                ("trans_probability", C.c_double), ("mean_neighbors", C.c_double)]
+                ("trans_probability", C.c_double), ("mean_neighbors", C.c_double),
+                ("aux", C.c_double * 4)]
 
 
 _lib = None

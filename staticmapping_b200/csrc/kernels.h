@@ -135,6 +135,10 @@ struct NdtEvalParams {      // everything one computeDerivatives call needs, by 
   float h_ang[15][3];
   double gauss_d1, gauss_d2;
   float radius;             // resolution_
+  int f64_math;             // 1: stock pcl::NormalDistributionsTransform term math (double), the
+                            //    class NdtWithGicp uses; 0: pclomp's single-precision math
+  double j_ang_d[8][3];     // the same tables in double (stock PCL keeps them as Vector3d)
+  double h_ang_d[15][3];
 };
 uint32_t ndt_table_size(int nt);
 int ndt_blocks(int n);
@@ -161,6 +165,31 @@ int ndt_eval(const float* src, int ns, const NdtEvalParams& P, NdtWorkspace& ws,
 int ndt_float_to_soa(const float* pts, int n, double* soa, int64_t stride, cudaStream_t stream);
 int ndt_fitness(const float* src, int ns, const NdtEvalParams& P, const KdNode* nodes,
                 const BucketPoint* bpts, const float* tgt, NdtWorkspace& ws, cudaStream_t stream);
+
+// ---- gicp.cu -----------------------------------------------------------------------------
+struct GicpIterParams {     // one outer GICP iteration (gicp_omp_impl.hpp:414-461)
+  float guess[16];          // base transformation (NDT result), column-major
+  float transformation[16]; // transformation_ of this iteration
+  double R[9];              // rotation of transformation_ * guess, row-major, double
+  double dist_threshold;    // corr_dist_threshold_^2
+};
+struct GicpCostParams {     // one BFGS function evaluation (:255-377)
+  float T[16];              // base with applyState(x)
+  float base[16];
+};
+size_t approx_ws_bytes(int n);
+int approx_voxel_grid(const float* pts, int n, float leaf, void* ws_base, float* out, uint32_t* n_out_dev,
+                      cudaStream_t stream);
+int approx_voxel_grid_emit(int n, int n_runs, void* ws_base, float* out, const uint32_t* n_out_dev,
+                           cudaStream_t stream);
+int gicp_covariances(const float* cloud, int n, const KdNode* nodes, const BucketPoint* bpts, double eps,
+                     double* covs, cudaStream_t stream);
+int gicp_correspond(const float* src, int ns, const float* tgt, const GicpIterParams& P, const KdNode* nodes,
+                    const BucketPoint* bpts, const double* cov_s, const double* cov_t, int32_t* match,
+                    double* maha, uint32_t* count, cudaStream_t stream);
+int gicp_cost_blocks(int ns);
+int gicp_cost(const float* src, int ns, const float* tgt, const GicpCostParams& P, const int32_t* match,
+              const double* maha, double* partials, double* sums, cudaStream_t stream);
 
 // ---- normals.cu ------------------------------------------------------------------------
 int normals_scratch_blocks(int n);

@@ -312,6 +312,62 @@ __device__ __forceinline__ double update_derivatives(const NdtEvalParams& P, con
   return (double)score_inc;
 }
 
+// the same term with double Eigen matrices: stock pcl::NormalDistributionsTransform
+// (computePointDerivatives / updateDerivatives of PCL's ndt.hpp; the in-tree double overloads
+// ndt_omp_impl.hpp:441-481 and updateHessian :596-629 are that code).  Used by NdtWithGicp.
+__device__ __forceinline__ double update_derivatives_f64(const NdtEvalParams& P, const float* x_orig,
+                                                         const float* x_trans_f, const NdtLeaf& leaf,
+                                                         double* grad_pt, double* hess_pt) {
+  const double x[3] = {(double)x_orig[0], (double)x_orig[1], (double)x_orig[2]};
+  double xj[8], xh[15];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) xj[r] = (x[0] * P.j_ang_d[r][0] + x[1] * P.j_ang_d[r][1]) + x[2] * P.j_ang_d[r][2];
+#pragma unroll
+  for (int r = 0; r < 15; ++r) xh[r] = (x[0] * P.h_ang_d[r][0] + x[1] * P.h_ang_d[r][1]) + x[2] * P.h_ang_d[r][2];
+  const double pg[3][6] = {{1, 0, 0, 0, xj[2], xj[5]}, {0, 1, 0, xj[0], xj[3], xj[6]}, {0, 0, 1, xj[1], xj[4], xj[7]}};
+  const double* ic = leaf.icov;
+  double xt[3], cx[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) xt[d] = (double)x_trans_f[d] - leaf.mean[d];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) cx[r] = (ic[r * 3] * xt[0] + ic[r * 3 + 1] * xt[1]) + ic[r * 3 + 2] * xt[2];
+  double e = exp(-P.gauss_d2 * ((xt[0] * cx[0] + xt[1] * cx[1]) + xt[2] * cx[2]) / 2);
+  const double score_inc = -P.gauss_d1 * e;
+  e = P.gauss_d2 * e;
+  if (e > 1 || e < 0 || e != e) return 0.0;
+  e *= P.gauss_d1;
+  double cdp[6][3], xdot[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) cdp[i][r] = (ic[r * 3] * pg[0][i] + ic[r * 3 + 1] * pg[1][i]) + ic[r * 3 + 2] * pg[2][i];
+    xdot[i] = (xt[0] * cdp[i][0] + xt[1] * cdp[i][1]) + xt[2] * cdp[i][2];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    grad_pt[i] += xdot[i] * e;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double hterm = 0.0;
+      if (i >= 3 && j >= 3) {
+        const int a = i - 3, b = j - 3;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int blk = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+        double v0, v1, v2;
+        if (blk < 3) { v0 = 0.0; v1 = xh[2 * blk]; v2 = xh[2 * blk + 1]; }
+        else { v0 = xh[6 + 3 * (blk - 3)]; v1 = xh[7 + 3 * (blk - 3)]; v2 = xh[8 + 3 * (blk - 3)]; }
+        double cv[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) cv[r] = (ic[r * 3] * v0 + ic[r * 3 + 1] * v1) + ic[r * 3 + 2] * v2;
+        hterm = (xt[0] * cv[0] + xt[1] * cv[1]) + xt[2] * cv[2];
+      }
+      const double gdot = (pg[0][j] * cdp[i][0] + pg[1][j] * cdp[i][1]) + pg[2][j] * cdp[i][2];
+      hess_pt[i * 6 + j] += e * ((-P.gauss_d2 * xdot[i] * xdot[j] + hterm) + gdot);
+    }
+  }
+  return score_inc;
+}
+
 __global__ void __launch_bounds__(kNdtThreads)
 ndt_derivatives_kernel(const float* __restrict__ src, int n, NdtEvalParams P,
                        const NdtGrid* __restrict__ grid, const NdtLeaf* __restrict__ leaves,
@@ -359,7 +415,8 @@ ndt_derivatives_kernel(const float* __restrict__ src, int n, NdtEvalParams P,
     for (int q = 0; q < 36; ++q) hess_pt[q] = 0.0;
     for (int j = 0; j < nc; ++j) {
       const NdtLeaf leaf = leaves[cv[j]];
-      score_pt += update_derivatives(P, xo, xt, leaf, grad_pt, hess_pt);
+      score_pt += P.f64_math ? update_derivatives_f64(P, xo, xt, leaf, grad_pt, hess_pt)
+                             : update_derivatives(P, xo, xt, leaf, grad_pt, hess_pt);
     }
     acc[0] = score_pt;
 #pragma unroll

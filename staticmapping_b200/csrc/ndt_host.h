@@ -62,8 +62,8 @@ inline void angle_tables(const double* p, NdtEvalParams* P) {
       {(-cy * cz), (cy * sz), 0},
       {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},
       {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};
-  for (int r = 0; r < 8; ++r) for (int c = 0; c < 3; ++c) P->j_ang[r][c] = (float)J[r][c];
-  for (int r = 0; r < 15; ++r) for (int c = 0; c < 3; ++c) P->h_ang[r][c] = (float)H[r][c];
+  for (int r = 0; r < 8; ++r) for (int c = 0; c < 3; ++c) { P->j_ang[r][c] = (float)J[r][c]; P->j_ang_d[r][c] = J[r][c]; }
+  for (int r = 0; r < 15; ++r) for (int c = 0; c < 3; ++c) { P->h_ang[r][c] = (float)H[r][c]; P->h_ang_d[r][c] = H[r][c]; }
 }
 
 inline void axis_rotation(float angle, int axis, float* R) {   // AngleAxis<float>::toRotationMatrix

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "gicp_host.h"
 #include "ndt_host.h"
 
 namespace smb {
@@ -108,6 +109,9 @@ struct sm_handle {
   ndt::Options ndt;
   DevBuf src_f32, tgt_f32, ndt_ws, tgt_soa;
   double* host_sums = nullptr;     // pinned, 64 doubles
+  // NdtWithGicp
+  struct { float voxel_resolution = 0.2f; bool using_voxel_filter = true; bool use_ndt = true; } ng;   // ndt_gicp.h:71-75
+  DevBuf src_filt, tgt_filt, approx_ws, src_soa, nodes2, leaf_order2, bpts2, cov_s, cov_t, maha, match, gicp_partials, counter;
 };
 
 namespace {
@@ -134,6 +138,8 @@ const NdtDoubleOpt kNdtDoubleOptions[] = {
     {"outlier_ratio", offsetof(ndt::Options, outlier_ratio)},
     {"transformation_epsilon", offsetof(ndt::Options, transformation_epsilon)},
 };
+
+struct NdtGicpOptionsView { float voxel_resolution; bool using_voxel_filter; bool use_ndt; };
 
 int fail(sm_handle* h, int code, const std::string& msg) {
   if (h) h->error = msg;
@@ -234,6 +240,7 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
 }
 
 int ndt_align(sm_handle* h, const double* guess, double* result);
+int ndt_gicp_align(sm_handle* h, const double* guess, double* result);
 
 // one chunk of iterations + the asynchronous read-back of the state record
 int icp_enqueue_chunk(sm_handle* h) {
@@ -415,17 +422,49 @@ int ndt_eval_sync(sm_handle* h, const float* src, int ns, const NdtEvalParams& P
   return 0;
 }
 
-// Ndt::Align (ndt.cc:38-64) -> pcl::Registration::align -> computeTransformation
-// (ndt_omp_impl.hpp:81-171) -> getFitnessScore.
-int ndt_align(sm_handle* h, const double* guess, double* result) {
-  if (!h->has_source || !h->has_target) {       // ndt.cc:40-42: return false
-    for (int i = 0; i < 16; ++i) result[i] = guess[i];
-    return 0;
-  }
-  const int ns = (int)h->n_source, nt = (int)h->n_target;
-  const ndt::Options& o = h->ndt;
-  const float* src = (const float*)h->src_f32.p;
-  const float* tgt = (const float*)h->tgt_f32.p;
+struct NdtRunOut {
+  float final_T[16];
+  double fitness = 0, trans_probability = 0, mean_neighbors = 0;
+  int iterations = 0, evaluations = 0, launches = 0;
+  float ms_grid = 0, ms_iter = 0, ms_fit = 0;
+};
+
+// k-d tree over a packed float cloud (as doubles) into the given buffers
+int build_tree_f32(sm_handle* h, const float* pts, int n, DevBuf& soa, DevBuf& nodes, DevBuf& order, DevBuf& bpts) {
+  const int levels = kd_num_levels(n, 8);
+  if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "cloud too large");
+  const int64_t stride = pad64(n);
+  H_RC(soa.reserve((size_t)(3 * stride) * sizeof(double)));
+  H_RC(nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
+  H_RC(order.reserve((size_t)n * sizeof(uint32_t)));
+  H_RC(bpts.reserve((size_t)(n + 8) * sizeof(BucketPoint)));
+  H_RC(h->kdws.reserve(KdWorkspace::bytes_needed(n, 8)));
+  KdWorkspace kws;
+  kws.carve(h->kdws.p, n, 8);
+  H_RC(ndt_float_to_soa(pts, n, (double*)soa.p, stride, h->stream));
+  H_RC(kd_build((const double*)soa.p, stride, n, 8, kws, (KdNode*)nodes.p, (uint32_t*)order.p, h->stream));
+  H_RC(kd_fill_buckets((const double*)soa.p, stride, nullptr, 0, (const uint32_t*)order.p, n,
+                       (BucketPoint*)bpts.p, nullptr, h->stream));
+  return 0;
+}
+
+// pcl::Registration::getFitnessScore with the target tree in h->nodes / h->bpts
+int fitness_score(sm_handle* h, const float* src, int ns, const float* tgt, const float* T, NdtWorkspace& ws,
+                  double* out) {
+  NdtEvalParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < 16; ++i) P.T[i] = T[i];
+  H_RC(ndt_fitness(src, ns, P, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p, tgt, ws, h->stream));
+  H_CUDA(cudaMemcpyAsync(h->host_sums, ws.sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  *out = h->host_sums[1] > 0.0 ? h->host_sums[0] / h->host_sums[1] : std::numeric_limits<double>::max();
+  return 0;
+}
+
+// pcl::Registration::align -> NormalDistributionsTransform::computeTransformation
+// (ndt_omp_impl.hpp:81-171) -> getFitnessScore, on device clouds src/tgt (packed float xyz).
+int ndt_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, const ndt::Options& o,
+            bool f64_math, const double* guess, NdtRunOut* out) {
   H_RC(h->ndt_ws.reserve(NdtWorkspace::bytes_needed(nt, ns)));
   NdtWorkspace ws;
   ws.carve(h->ndt_ws.p, nt, ns);
@@ -433,9 +472,11 @@ int ndt_align(sm_handle* h, const double* guess, double* result) {
   H_RC(ndt_build_grid(tgt, nt, o.resolution, ws, h->stream));        // setInputTarget -> init()
   H_CUDA(cudaEventRecord(h->ev[1], h->stream));
   NdtEvalParams P;
+  memset(&P, 0, sizeof(P));
   ndt::gauss_constants(o, &P.gauss_d1, &P.gauss_d2);
   P.radius = o.resolution;
-  float final_T[16];
+  P.f64_math = f64_math ? 1 : 0;
+  float* final_T = out->final_T;
   bool guess_is_identity = true;
   for (int i = 0; i < 16; ++i) {
     final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
@@ -446,7 +487,7 @@ int ndt_align(sm_handle* h, const double* guess, double* result) {
   ndt::p_from_transform(final_T, p);                                  // :103-111
   for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
   ndt::angle_tables(p, &P);
-  double score, grad[6], hess[36], nb_sum = 0.0;
+  double score = 0, grad[6], hess[36], nb_sum = 0.0;
   int evals = 0, launches = 12 + 12;
   auto read_sums = [&]() {
     score = h->host_sums[0];
@@ -498,38 +539,222 @@ int ndt_align(sm_handle* h, const double* guess, double* result) {
   H_CUDA(cudaEventRecord(h->ev[2], h->stream));
   // getFitnessScore (ndt.cc:60): exact 1-NN over the full target (PCL builds this search
   // tree in setInputTarget; the reference calls that on every Align)
-  const int levels = kd_num_levels(nt, 8);
-  if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large");
-  h->tstride = pad64(nt);
-  H_RC(h->tgt_soa.reserve((size_t)(3 * h->tstride) * sizeof(double)));
-  H_RC(h->nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
-  H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
-  H_RC(h->bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
-  H_RC(h->kdws.reserve(KdWorkspace::bytes_needed(nt, 8)));
-  KdWorkspace kws;
-  kws.carve(h->kdws.p, nt, 8);
-  H_RC(ndt_float_to_soa(tgt, nt, (double*)h->tgt_soa.p, h->tstride, h->stream));
-  H_RC(kd_build((const double*)h->tgt_soa.p, h->tstride, nt, 8, kws, (KdNode*)h->nodes.p,
-                (uint32_t*)h->leaf_order.p, h->stream));
-  H_RC(kd_fill_buckets((const double*)h->tgt_soa.p, h->tstride, nullptr, 0, (const uint32_t*)h->leaf_order.p,
-                       nt, (BucketPoint*)h->bpts.p, nullptr, h->stream));
-  H_RC(ndt_fitness(src, ns, P, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p, tgt, ws, h->stream));
-  H_CUDA(cudaMemcpyAsync(h->host_sums, ws.sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  H_RC(build_tree_f32(h, tgt, nt, h->tgt_soa, h->nodes, h->leaf_order, h->bpts));
+  H_RC(fitness_score(h, src, ns, tgt, final_T, ws, &out->fitness));
   H_CUDA(cudaEventRecord(h->ev[3], h->stream));
-  H_CUDA(cudaStreamSynchronize(h->stream));
-  h->final_score = h->host_sums[1] > 0.0 ? h->host_sums[0] / h->host_sums[1]
-                                         : std::numeric_limits<double>::max();
-  for (int i = 0; i < 16; ++i) result[i] = (double)final_T[i];        // .cast<double>() (ndt.cc:61)
+  H_CUDA(cudaEventSynchronize(h->ev[3]));
+  out->iterations = nr_iterations;
+  out->evaluations = evals;
+  out->trans_probability = score / (double)ns;
+  out->mean_neighbors = evals ? nb_sum / evals : 0.0;
+  out->launches = launches + 24 + kd_num_levels(nt, 8) * 5 + 6;
+  cudaEventElapsedTime(&out->ms_grid, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&out->ms_iter, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&out->ms_fit, h->ev[2], h->ev[3]);
+  return 0;
+}
+
+// Ndt::Align (ndt.cc:38-64)
+int ndt_align(sm_handle* h, const double* guess, double* result) {
+  if (!h->has_source || !h->has_target) {       // ndt.cc:40-42: return false
+    for (int i = 0; i < 16; ++i) result[i] = guess[i];
+    return 0;
+  }
+  NdtRunOut r;
+  H_RC(ndt_run(h, (const float*)h->src_f32.p, (int)h->n_source, (const float*)h->tgt_f32.p, (int)h->n_target,
+               h->ndt, false, guess, &r));
+  h->final_score = r.fitness;
+  for (int i = 0; i < 16; ++i) result[i] = (double)r.final_T[i];     // .cast<double>() (ndt.cc:61)
   memset(&h->info, 0, sizeof(h->info));
-  h->info.iterations = nr_iterations;
-  h->info.evaluations = evals;
-  h->info.trans_probability = score / (double)ns;
-  h->info.mean_neighbors = evals ? nb_sum / evals : 0.0;
-  h->info.kernel_launches = launches + 24 + levels * 5 + 6;
-  cudaEventElapsedTime(&h->info.ms_prologue, h->ev[0], h->ev[1]);
-  cudaEventElapsedTime(&h->info.ms_iterations, h->ev[1], h->ev[2]);
-  cudaEventElapsedTime(&h->info.ms_finish, h->ev[2], h->ev[3]);      // fitness score
+  h->info.iterations = r.iterations;
+  h->info.evaluations = r.evaluations;
+  h->info.trans_probability = r.trans_probability;
+  h->info.mean_neighbors = r.mean_neighbors;
+  h->info.kernel_launches = r.launches;
+  h->info.ms_prologue = r.ms_grid; h->info.ms_iterations = r.ms_iter; h->info.ms_finish = r.ms_fit;
   return 1;
+}
+
+// ---- NdtWithGicp ---------------------------------------------------------------------------
+// pcl::ApproximateVoxelGrid::filter (ndt_gicp.cc:59-70)
+int approx_filter(sm_handle* h, const float* pts, int n, float leaf, DevBuf& out, int* m_out) {
+  H_RC(h->approx_ws.reserve(approx_ws_bytes(n)));
+  H_RC(out.reserve((size_t)n * 12 + 64));
+  H_RC(h->counter.reserve(64));
+  uint32_t* cnt = (uint32_t*)h->counter.p;
+  H_RC(approx_voxel_grid(pts, n, leaf, h->approx_ws.p, (float*)out.p, cnt, h->stream));
+  uint32_t m = 0;
+  H_CUDA(cudaMemcpyAsync(&m, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  H_CUDA(cudaStreamSynchronize(h->stream));
+  H_RC(approx_voxel_grid_emit(n, (int)m, h->approx_ws.p, (float*)out.p, cnt, h->stream));
+  *m_out = (int)m;
+  return 0;
+}
+
+// GeneralizedIterativeClosestPoint::computeTransformation (gicp_omp_impl.hpp:381-514) with the
+// BFGS inner solver on the host; target tree must be in h->nodes / h->bpts.
+int gicp_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, const float* guess,
+             const gicp::Options& o, float* final_T, int* iterations, int* bfgs_evals) {
+  H_RC(build_tree_f32(h, src, ns, h->src_soa, h->nodes2, h->leaf_order2, h->bpts2));
+  H_RC(h->cov_s.reserve((size_t)ns * 9 * sizeof(double)));
+  H_RC(h->cov_t.reserve((size_t)nt * 9 * sizeof(double)));
+  H_RC(h->maha.reserve((size_t)ns * 9 * sizeof(double)));
+  H_RC(h->match.reserve((size_t)ns * sizeof(int32_t)));
+  H_RC(h->gicp_partials.reserve((size_t)(gicp_cost_blocks(ns) + 1) * 13 * sizeof(double) + 256));
+  H_RC(h->counter.reserve(64));
+  double* sums_dev = (double*)h->gicp_partials.p + (size_t)gicp_cost_blocks(ns) * 13;
+  if (o.k_correspondences <= nt)   // :61-65: otherwise PCL_ERROR and the covariances stay unset
+    H_RC(gicp_covariances(tgt, nt, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p, o.gicp_epsilon,
+                          (double*)h->cov_t.p, h->stream));
+  else H_CUDA(cudaMemsetAsync(h->cov_t.p, 0, (size_t)nt * 9 * sizeof(double), h->stream));
+  if (o.k_correspondences <= ns)
+    H_RC(gicp_covariances(src, ns, (const KdNode*)h->nodes2.p, (const BucketPoint*)h->bpts2.p, o.gicp_epsilon,
+                          (double*)h->cov_s.p, h->stream));
+  else H_CUDA(cudaMemsetAsync(h->cov_s.p, 0, (size_t)ns * 9 * sizeof(double), h->stream));
+  float transformation[16], previous[16];
+  for (int i = 0; i < 16; ++i) transformation[i] = previous[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  int nr_iterations = 0, evals = 0;
+  bool converged = false, device_error = false;
+  while (!converged) {
+    GicpIterParams IP;
+    for (int i = 0; i < 16; ++i) { IP.guess[i] = guess[i]; IP.transformation[i] = transformation[i]; }
+    for (int i = 0; i < 3; ++i)          // transform_R = transformation_ * guess in double (:423-429)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 4; ++k) s += (double)transformation[i + 4 * k] * (double)guess[k + 4 * j];
+        IP.R[i * 3 + j] = s;
+      }
+    IP.dist_threshold = o.corr_dist_threshold * o.corr_dist_threshold;
+    H_RC(gicp_correspond(src, ns, tgt, IP, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p,
+                         (const double*)h->cov_s.p, (const double*)h->cov_t.p, (int32_t*)h->match.p,
+                         (double*)h->maha.p, (uint32_t*)h->counter.p, h->stream));
+    uint32_t m_u = 0;
+    H_CUDA(cudaMemcpyAsync(&m_u, h->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    H_CUDA(cudaStreamSynchronize(h->stream));
+    const int m = (int)m_u;
+    for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
+    if (m < 4) break;                    // NotEnoughPointsException, caught at :489-492
+    double x[6] = {(double)transformation[12], (double)transformation[13], (double)transformation[14],
+                   atan2((double)transformation[2 + 4 * 1], (double)transformation[2 + 4 * 2]),
+                   asin(-(double)transformation[2 + 4 * 0]),
+                   atan2((double)transformation[1 + 4 * 0], (double)transformation[0 + 4 * 0])};
+    gicp::Minimizer mz;
+    mz.fdf = [&](const double* xx, double* f, double* g) -> int {
+      ++evals;
+      GicpCostParams CP;
+      for (int i = 0; i < 16; ++i) { CP.T[i] = guess[i]; CP.base[i] = guess[i]; }
+      gicp::apply_state(CP.T, xx);
+      if (gicp_cost(src, ns, tgt, CP, (const int32_t*)h->match.p, (const double*)h->maha.p,
+                    (double*)h->gicp_partials.p, sums_dev, h->stream) != 0) return -1;
+      if (cudaMemcpyAsync(h->host_sums, sums_dev, 13 * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+          cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+      const double* S = h->host_sums;
+      if (f) *f = S[0] / (double)m;
+      if (g) {
+        double Rm[9];
+        for (int r = 0; r < 3; ++r) g[r] = S[1 + r] * (2.0 / m);
+        for (int q = 0; q < 9; ++q) Rm[q] = S[4 + q] * (2.0 / m);
+        gicp::r_derivative(xx, Rm, g);
+      }
+      return 0;
+    };
+    mz.init(x);
+    int result = gicp::kRunning, inner = 0;
+    do {
+      ++inner;
+      result = mz.one_step(x);
+      if (result) break;
+      result = mz.test_gradient(1e-2);
+    } while (result == gicp::kRunning && inner < o.max_inner_iterations);
+    if (mz.failed) { device_error = true; break; }
+    if (result == gicp::kNoProgress || result == gicp::kSuccess || inner == o.max_inner_iterations) {
+      for (int i = 0; i < 16; ++i) transformation[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+      gicp::apply_state(transformation, x);
+    } else {
+      break;
+    }
+    double delta = 0.0;
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 4; ++l) {
+        const double ratio = (k < 3 && l < 3) ? 1.0 / o.rotation_epsilon : 1.0 / o.transformation_epsilon;
+        const double c_delta = ratio * fabs((double)previous[k + 4 * l] - (double)transformation[k + 4 * l]);
+        if (c_delta > delta) delta = c_delta;
+      }
+    ++nr_iterations;
+    if (nr_iterations >= o.max_iterations || delta < 1) {
+      converged = true;
+      for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
+    }
+  }
+  if (device_error) return cuda_fail(h);
+  float Rp[9], Rg[9], Rf[9];            // :505-508
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Rp[r * 3 + c] = previous[r + 4 * c]; Rg[r * 3 + c] = guess[r + 4 * c]; }
+  ndt::mul3(Rp, Rg, Rf);
+  for (int i = 0; i < 16; ++i) final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) final_T[r + 4 * c] = Rf[r * 3 + c];
+    final_T[12 + r] = previous[12 + r] + guess[12 + r];
+  }
+  *iterations = nr_iterations;
+  *bfgs_evals = evals;
+  return 0;
+}
+
+// NdtWithGicp::Align (ndt_gicp.cc:55-112)
+int ndt_gicp_align(sm_handle* h, const double* guess, double* result) {
+  if (!h->has_source || !h->has_target)
+    return fail(h, SM_ERR_MISSING_INPUT, "Align: source/target not set");   // null deref in the reference
+  const float* src = (const float*)h->src_f32.p;
+  const float* tgt = (const float*)h->tgt_f32.p;
+  int ns = (int)h->n_source, nt = (int)h->n_target;
+  if (h->ng.using_voxel_filter) {
+    H_RC(approx_filter(h, src, ns, h->ng.voxel_resolution, h->src_filt, &ns));
+    H_RC(approx_filter(h, tgt, nt, h->ng.voxel_resolution, h->tgt_filt, &nt));
+    src = (const float*)h->src_filt.p;
+    tgt = (const float*)h->tgt_filt.p;
+  }
+  memset(&h->info, 0, sizeof(h->info));
+  h->info.aux[2] = ns; h->info.aux[3] = nt;
+  if (ns <= 0 || nt <= 0) return fail(h, SM_ERR_MISSING_INPUT, "Align: empty cloud after the voxel filter");
+  float ndt_guess[16];
+  for (int i = 0; i < 16; ++i) ndt_guess[i] = (float)guess[i];
+  double ndt_score = 0.9;
+  if (h->ng.use_ndt) {                    // ndt_gicp.cc:82-88, configuration :44-47
+    ndt::Options no;
+    no.transformation_epsilon = 0.01; no.step_size = 0.1; no.resolution = 1.0f; no.max_iterations = 35;
+    NdtRunOut r;
+    H_RC(ndt_run(h, src, ns, tgt, nt, no, true, guess, &r));
+    ndt_score = r.fitness;
+    for (int i = 0; i < 16; ++i) ndt_guess[i] = r.final_T[i];
+    h->info.evaluations = r.evaluations;
+    h->info.ms_prologue = r.ms_grid + r.ms_iter + r.ms_fit;
+  } else {
+    H_RC(build_tree_f32(h, tgt, nt, h->tgt_soa, h->nodes, h->leaf_order, h->bpts));
+  }
+  h->info.aux[0] = ndt_score;
+  double icp_score = 10.0;
+  if (ndt_score <= 1.0) {                 // :92-103
+    float final_T[16];
+    int it = 0, evals = 0;
+    H_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    H_RC(gicp_run(h, src, ns, tgt, nt, ndt_guess, gicp::Options(), final_T, &it, &evals));
+    H_RC(h->ndt_ws.reserve(NdtWorkspace::bytes_needed(nt, ns)));
+    NdtWorkspace ws;
+    ws.carve(h->ndt_ws.p, nt, ns);
+    H_RC(fitness_score(h, src, ns, tgt, final_T, ws, &icp_score));
+    H_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    H_CUDA(cudaEventSynchronize(h->ev[1]));
+    cudaEventElapsedTime(&h->info.ms_iterations, h->ev[0], h->ev[1]);
+    h->final_score = exp(-icp_score);
+    for (int i = 0; i < 16; ++i) result[i] = (double)final_T[i];
+    h->info.iterations = it;
+    h->info.profiled_iterations = evals;   // BFGS cost evaluations
+    h->info.aux[1] = icp_score;
+    return 1;
+  }
+  for (int i = 0; i < 16; ++i) result[i] = guess[i];   // :104-108
+  h->final_score = exp(-icp_score);
+  return 0;
 }
 
 }  // namespace
@@ -547,7 +772,7 @@ const char* sm_version(void) { return "sm_b200 0.1 (sm_100a)"; }
 int sm_create(int type, int device, sm_handle** out) {
   if (!out) return SM_ERR_BAD_ARGUMENT;
   *out = nullptr;
-  if (type != SM_TYPE_FAST_ICP && type != SM_TYPE_NDT) return SM_ERR_UNSUPPORTED_TYPE;
+  if (type != SM_TYPE_FAST_ICP && type != SM_TYPE_NDT && type != SM_TYPE_NDT_WITH_GICP) return SM_ERR_UNSUPPORTED_TYPE;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
   if (device < 0 || device >= ndev) return SM_ERR_BAD_ARGUMENT;
@@ -586,6 +811,7 @@ int sm_destroy(sm_handle* h) {
   if (h->host_guess) cudaFreeHost(h->host_guess);
   for (int i = 0; i < 4; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
   h->src_f32.release(); h->tgt_f32.release(); h->ndt_ws.release(); h->tgt_soa.release();
+  { DevBuf* gb[] = {&h->src_filt, &h->tgt_filt, &h->approx_ws, &h->src_soa, &h->nodes2, &h->leaf_order2, &h->bpts2, &h->cov_s, &h->cov_t, &h->maha, &h->match, &h->gicp_partials, &h->counter}; for (DevBuf* b : gb) b->release(); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SM_OK;
@@ -603,6 +829,15 @@ int sm_set_stream(sm_handle* h, void* cuda_stream) {
 
 int sm_set_option(sm_handle* h, const char* name, const char* text) {
   if (!h || !name || !text) return SM_ERR_BAD_ARGUMENT;
+  if (h->type == SM_TYPE_NDT_WITH_GICP) {   // ndt_gicp.cc:31-36
+    const char* q = text;
+    while (*q == ' ' || *q == '\t' || *q == '\n') ++q;
+    const bool bv = (*q == '1' || *q == 't' || *q == 'T' || *q == 'y' || *q == 'Y');
+    if (strcmp(name, "use_ndt") == 0) { h->ng.use_ndt = bv; return SM_OK; }
+    if (strcmp(name, "using_voxel_filter") == 0) { h->ng.using_voxel_filter = bv; return SM_OK; }
+    if (strcmp(name, "voxel_resolution") == 0) { h->ng.voxel_resolution = strtof(text, nullptr); return SM_OK; }
+    return fail(h, SM_ERR_UNKNOWN_OPTION, std::string("Init an unknown option of this matcher! ") + name);
+  }
   if (h->type == SM_TYPE_NDT) {
     for (const NdtDoubleOpt& d : kNdtDoubleOptions)
       if (strcmp(d.name, name) == 0) {
@@ -690,6 +925,7 @@ int sm_align(sm_handle* h, const double* guess, double* result) {
   if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
   if (h->type == SM_TYPE_FAST_ICP) return icp_align(h, guess, result);
   if (h->type == SM_TYPE_NDT) return ndt_align(h, guess, result);
+  if (h->type == SM_TYPE_NDT_WITH_GICP) return ndt_gicp_align(h, guess, result);
   return fail(h, SM_ERR_UNSUPPORTED_TYPE, "matcher type not supported");
 }
 

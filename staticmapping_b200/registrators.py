@@ -200,7 +200,9 @@ class Interface:
     def GetAlignInfo(self):
         info = _lib.AlignInfo()
         self._lib.sm_get_align_info(self._h, C.byref(info))
-        return {k: getattr(info, k) for k, _ in _lib.AlignInfo._fields_ if k != "reserved"}
+        out = {k: getattr(info, k) for k, _ in _lib.AlignInfo._fields_ if k not in ("reserved", "aux")}
+        out["aux"] = [float(v) for v in info.aux]
+        return out
 
 
 class IcpFast(Interface):
@@ -279,6 +281,22 @@ class Ndt(Interface):
         return super().Align(guess)
 
 
+class NdtWithGicp(Ndt):
+    """registrator::NdtWithGicp (ndt_gicp.h / ndt_gicp.cc:28-112): ApproximateVoxelGrid(0.2 m) on
+    both clouds -> stock PCL NDT (resolution 1.0, step 0.1, eps 0.01, 35 it) -> stock PCL GICP
+    (rotation eps 1e-3, 35 it), gated on NDT fitness <= 1.  GetFitnessScore() = exp(-GICP fitness).
+    Registered options (ndt_gicp.cc:31-36): use_ndt, using_voxel_filter, voxel_resolution."""
+    _type = Type.kNdtWithGicp
+
+    def InitWithXml(self, node):
+        Interface.InitWithXml(self, node)
+
+    def Align(self, guess):
+        if self._source is None or self._target is None:
+            raise CheckFailure("NdtWithGicp::Align: input cloud not set (null dereference in the reference)")
+        return Interface.Align(self, guess)
+
+
 def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 0) -> Interface:
     """registrator::CreateMatcher (interface.cc:139-173)."""
     t = Type(options.type)
@@ -289,7 +307,9 @@ def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 
                            "please choose another type")   # LOG(FATAL), interface.cc:154-157
     elif t == Type.kNdt:
         matcher = Ndt(device)
-    elif t in (Type.kIcpPM, Type.kNdtWithGicp):
+    elif t == Type.kNdtWithGicp:
+        matcher = NdtWithGicp(device)
+    elif t == Type.kIcpPM:
         raise NotImplementedError(f"matcher type {t.name} is not built yet in sm_b200")
     else:
         print("Wrong type")   # PRINT_ERROR + nullptr, interface.cc:158-160

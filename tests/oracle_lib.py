@@ -30,6 +30,17 @@ class NdtOptions(C.Structure):
                 ("transformation_epsilon", C.c_double), ("max_iterations", C.c_int32)]
 
 
+class NdtGicpOptions(C.Structure):
+    _fields_ = [("voxel_resolution", C.c_float), ("using_voxel_filter", C.c_int32), ("use_ndt", C.c_int32)]
+
+
+class NdtGicpInfo(C.Structure):
+    _fields_ = [("n_source_filtered", C.c_int64), ("n_target_filtered", C.c_int64),
+                ("ndt_iterations", C.c_int32), ("gicp_iterations", C.c_int32),
+                ("bfgs_evaluations", C.c_int32), ("pad", C.c_int32), ("ndt_score", C.c_double),
+                ("gicp_fitness", C.c_double)]
+
+
 _lib = None
 
 
@@ -62,7 +73,39 @@ def lib():
         _lib.sm_oracle_ndt_voxels.argtypes = [fp, i64, C.c_float, i64, ip, ip, dp, dp, fp, ip]
         _lib.sm_oracle_ndt_derivatives.argtypes = [fp, i64, fp, i64, C.POINTER(NdtOptions), dp, dp, dp, dp, dp]
         _lib.sm_oracle_ndt_align.argtypes = [fp, i64, fp, i64, dp, C.POINTER(NdtOptions), dp, dp, ip, dp, dp]
+        _lib.sm_oracle_approx_voxel_grid.restype = C.c_int64
+        _lib.sm_oracle_approx_voxel_grid.argtypes = [fp, i64, C.c_float, fp, i64]
+        _lib.sm_oracle_gicp_covariances.argtypes = [fp, i64, C.c_int, C.c_double, dp]
+        _lib.sm_oracle_ndt_gicp_align.argtypes = [fp, i64, fp, i64, dp, C.POINTER(NdtGicpOptions), dp, dp,
+                                                  C.POINTER(NdtGicpInfo)]
     return _lib
+
+
+def approx_voxel_grid(points, leaf=0.2):
+    p = _fcloud(points)
+    out = np.zeros_like(p)
+    m = lib().sm_oracle_approx_voxel_grid(_f(p), p.shape[0], leaf, _f(out), p.shape[0])
+    return out[:m].copy()
+
+
+def gicp_covariances(points, k=20, eps=1e-3):
+    p = _fcloud(points)
+    cov = np.zeros((p.shape[0], 9))
+    lib().sm_oracle_gicp_covariances(_f(p), p.shape[0], k, eps, _d(cov))
+    return cov.reshape(-1, 3, 3)
+
+
+def ndt_gicp_align(source, target, guess=None, voxel_resolution=0.2, using_voxel_filter=True, use_ndt=True):
+    s, t = _fcloud(source), _fcloud(target)
+    g = np.eye(4) if guess is None else np.asarray(guess, dtype=np.float64)
+    g_cm = np.ascontiguousarray(g.T).ravel()
+    opt = NdtGicpOptions(voxel_resolution, int(using_voxel_filter), int(use_ndt))
+    res = np.zeros(16); sc = C.c_double(); info = NdtGicpInfo()
+    rc = lib().sm_oracle_ndt_gicp_align(_f(s), s.shape[0], _f(t), t.shape[0], _d(g_cm), C.byref(opt), _d(res),
+                                        C.byref(sc), C.byref(info))
+    out = {"rc": rc, "result": res.reshape(4, 4).T.copy(), "score": sc.value}
+    out.update({k: getattr(info, k) for k, _ in NdtGicpInfo._fields_ if k != "pad"})
+    return out
 
 
 def _f(a):
