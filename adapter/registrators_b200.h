@@ -85,6 +85,64 @@ class IcpFastB200 : public Interface {
   } options_;
 };
 
+// registrator::Ndt (registrators/ndt.h, ndt.cc:28-64) and registrator::NdtWithGicp
+// (ndt_gicp.h, ndt_gicp.cc:28-112) keep the caller's float cloud (base-class SetInput*,
+// interface.cc:38-60) and hand it over at Align: std::vector<InnerPointType>, 20-byte stride.
+template <int kType>
+class FloatCloudMatcherB200 : public Interface {
+ public:
+  USE_REGISTRATOR_CLOUDS;
+  explicit FloatCloudMatcherB200(int device = 0) : Interface() {
+    this->type_ = static_cast<Type>(kType);
+    const int rc = sm_create(kType, device, &handle_);
+    CHECK_EQ(rc, 0) << "sm_create failed (" << rc << ")";
+  }
+  ~FloatCloudMatcherB200() override { sm_destroy(handle_); }
+
+  bool Align(const Eigen::Matrix4d& guess, Eigen::Matrix4d& result) override {  // NOLINT
+    if (!this->source_cloud_ || !this->target_cloud_) {
+      if (kType == SM_TYPE_NDT) return false;                 // ndt.cc:40-42
+      CHECK(this->source_cloud_ && this->target_cloud_);      // NdtWithGicp dereferences them
+    }
+    const auto& s = this->source_cloud_->GetInnerCloud()->points;
+    const auto& t = this->target_cloud_->GetInnerCloud()->points;
+    CheckRc(sm_set_input_source_f32(handle_, &s[0].x, static_cast<int64_t>(s.size()),
+                                    sizeof(data::InnerPointType)));
+    CheckRc(sm_set_input_target_f32(handle_, &t[0].x, static_cast<int64_t>(t.size()),
+                                    sizeof(data::InnerPointType)));
+    const int rc = sm_align(handle_, guess.data(), result.data());
+    CheckRc(rc);
+    this->final_score_ = sm_get_fitness_score(handle_);
+    return rc == 1;
+  }
+
+ protected:
+  void CheckRc(int rc) const { CHECK_GE(rc, 0) << "sm_b200: " << sm_last_error(handle_); }
+  sm_handle* handle_ = nullptr;
+};
+
+class NdtB200 : public FloatCloudMatcherB200<SM_TYPE_NDT> {   // registers no option, like Ndt
+ public:
+  explicit NdtB200(int device = 0) : FloatCloudMatcherB200<SM_TYPE_NDT>(device) {}
+};
+
+class NdtWithGicpB200 : public FloatCloudMatcherB200<SM_TYPE_NDT_WITH_GICP> {
+ public:
+  explicit NdtWithGicpB200(int device = 0) : FloatCloudMatcherB200<SM_TYPE_NDT_WITH_GICP>(device) {
+    REG_REGISTRATOR_INNER_OPTION("use_ndt", OptionItemDataType::kBool, options_.use_ndt);            // ndt_gicp.cc:31-36
+    REG_REGISTRATOR_INNER_OPTION("using_voxel_filter", OptionItemDataType::kBool, options_.using_voxel_filter);
+    REG_REGISTRATOR_INNER_OPTION("voxel_resolution", OptionItemDataType::kFloat32, options_.voxel_resolution);
+  }
+  void InitWithOptions() override {
+    CheckRc(sm_set_option(handle_, "use_ndt", options_.use_ndt ? "1" : "0"));
+    CheckRc(sm_set_option(handle_, "using_voxel_filter", options_.using_voxel_filter ? "1" : "0"));
+    CheckRc(sm_set_option(handle_, "voxel_resolution", std::to_string(options_.voxel_resolution).c_str()));
+  }
+
+ private:
+  struct { float voxel_resolution = 0.2; bool using_voxel_filter = true; bool use_ndt = true; } options_;
+};
+
 // EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368); call sites
 // map_builder.cc:286,389 and submap.cc:161.
 inline void CalculateNormalsB200(data::EigenPointCloud* cloud, int device = 0) {

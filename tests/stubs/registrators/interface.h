@@ -6,6 +6,7 @@
 #include <memory>
 #include <string>
 #include <unordered_map>
+#include <vector>
 namespace Eigen {
 struct MatrixXd {
   MatrixXd() = default;
@@ -32,9 +33,12 @@ struct EigenPointCloud {
   Eigen::MatrixXd points, normals;
   bool HasNormals() const { return true; }
 };
+struct InnerPointType { float x, y, z, intensity, factor; };
+struct InnerCloudType { std::vector<InnerPointType> points; };
 struct InnerPointCloudData {
   using Ptr = std::shared_ptr<InnerPointCloudData>;
   std::shared_ptr<EigenPointCloud> GetEigenCloud() const { return nullptr; }
+  std::shared_ptr<InnerCloudType> GetInnerCloud() const { return nullptr; }
 };
 }  // namespace data
 namespace registrator {
@@ -53,6 +57,8 @@ class Interface {
  protected:
   double final_score_ = 0;
   Type type_ = kNoType;
+  InnerCloudPtr source_cloud_ = nullptr;
+  InnerCloudPtr target_cloud_ = nullptr;
   std::unordered_map<std::string, InnerOptionItem> inner_options_;
 };
 }  // namespace registrator

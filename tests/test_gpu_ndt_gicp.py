@@ -57,3 +57,19 @@ def test_unknown_option_rejected():
     m = smb.NdtWithGicp()
     with pytest.raises(smb.CheckFailure):
         m.InitWithXml({"max_iteration": 3})
+
+
+def test_ndt_gate_returns_false_and_guess():
+    # NDT fitness > 1 -> Align returns false, result = guess, score = exp(-10) (ndt_gicp.cc:104-108)
+    src, sub, _ = _pair(0)
+    far = (sub + np.array([500.0, 0.0, 0.0], np.float32)).astype(np.float32)
+    g = np.eye(4); g[0, 3] = 0.25
+    m = smb.NdtWithGicp()
+    m.SetInputSource(smb.InnerCloud(src))
+    m.SetInputTarget(smb.InnerCloud(far))
+    ok, res = m.Align(g)
+    o = O.ndt_gicp_align(src, far, guess=g)
+    assert ok is False and o["rc"] == 0
+    assert np.array_equal(res, g)
+    assert abs(m.GetFitnessScore() - np.exp(-10.0)) < 1e-15
+    assert abs(m.GetAlignInfo()["aux"][0] - o["ndt_score"]) <= 1e-6 * o["ndt_score"]
