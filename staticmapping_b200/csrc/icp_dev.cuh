@@ -107,12 +107,33 @@ __device__ __forceinline__ int child_idx(int idx, int right) {
 // they pass the test against the head known at push time (the head only shrinks, so nothing
 // the recursion would visit is dropped) and re-tested when popped, which is when the
 // recursion tests them.
+// The first kSmemStackDepth pending subtrees of a thread live in shared memory
+// ([level][thread], conflict free); deeper ones (rare) spill to the local array.  With
+// `ss.rd == nullptr` everything uses the local array.
+constexpr int kSmemStackDepth = 4;
+struct SmemStack {
+  double* rd; double* ox; double* oy; double* oz; int* idx;
+  int nthreads;
+};
+__device__ __forceinline__ SmemStack no_smem_stack() { return SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}; }
+// bytes of dynamic shared memory a block of `threads` needs for the stack
+__host__ __device__ __forceinline__ size_t smem_stack_bytes(int threads) {
+  return (size_t)kSmemStackDepth * threads * (4 * sizeof(double) + sizeof(int));
+}
+__device__ __forceinline__ SmemStack carve_smem_stack(void* base, int threads) {
+  double* d = reinterpret_cast<double*>(base);
+  const int n = kSmemStackDepth * threads;
+  return SmemStack{d, d + n, d + 2 * n, d + 3 * n, reinterpret_cast<int*>(d + 4 * n), threads};
+}
+
 __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
                                               const BucketPoint* __restrict__ bpts, double qx,
                                               double qy, double qz, double max_error2, int idx,
                                               double rd, double ox, double oy, double oz,
-                                              double& head, int& best, int max_rounds = 1 << 20) {
+                                              double& head, int& best, int max_rounds = 1 << 20,
+                                              SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   StackEntry stack[kMaxStack];
+  const int sdepth = ss.rd ? kSmemStackDepth : 0;
   int sp = 0;
   while (max_rounds-- > 0) {
     KdNode nd = load_node(nodes, idx);
@@ -125,14 +146,20 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
       const int right = new_off > 0.0 ? 1 : 0;
       // rd += - old_off*old_off + new_off*new_off
       const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
+      if (dmul(rd_new, max_error2) < head && sp < kMaxStack + sdepth) {
         StackEntry e;
         e.rd = rd_new;
         e.ox = cd == 0 ? new_off : ox;
         e.oy = cd == 1 ? new_off : oy;
         e.oz = cd == 2 ? new_off : oz;
         e.idx = child_idx(idx, 1 - right);
-        stack[sp++] = e;
+        if (sp < sdepth) {
+          const int k = sp * ss.nthreads + threadIdx.x;
+          ss.rd[k] = e.rd; ss.ox[k] = e.ox; ss.oy[k] = e.oy; ss.oz[k] = e.oz; ss.idx[k] = e.idx;
+        } else {
+          stack[sp - sdepth] = e;
+        }
+        ++sp;
       }
       idx = child_idx(idx, right);
       nd = load_node(nodes, idx);
@@ -140,7 +167,14 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
     if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
     bool found = false;
     while (sp > 0) {
-      const StackEntry e = stack[--sp];
+      --sp;
+      StackEntry e;
+      if (sp < sdepth) {
+        const int k = sp * ss.nthreads + threadIdx.x;
+        e.rd = ss.rd[k]; e.ox = ss.ox[k]; e.oy = ss.oy[k]; e.oz = ss.oz[k]; e.idx = ss.idx[k];
+      } else {
+        e = stack[sp - sdepth];
+      }
       if (dmul(e.rd, max_error2) < head) {
         idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
         found = true;
@@ -160,7 +194,8 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
 __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
                                      const BucketPoint* __restrict__ bpts, double qx, double qy,
                                      double qz, double max_error2, int& best_slot, double& best_d2,
-                                     int max_rounds = 1 << 30) {
+                                     int max_rounds = 1 << 30,
+                                     SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double head = inf;
   int best = -1;
@@ -178,7 +213,7 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
   if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
   // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
   if (dmul(min_off2, max_error2) < head)
-    visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds);
+    visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds, ss);
   best_slot = best;
   best_d2 = head;
 }
