@@ -131,6 +131,14 @@ __global__ void apply_g0_kernel(const double* __restrict__ in, double* __restric
   vals[i] = (uint32_t)i;
 }
 
+__global__ void visits_key_kernel(const uint8_t* __restrict__ visits, int n, uint64_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = visits[i];
+  vals[i] = (uint32_t)i;
+}
+
 // queries in Morton order: neighbouring threads walk the same tree lines and hit the same
 // buckets.  Only sums are formed over the source, so its order is free.
 __global__ void gather_source_kernel(const double* __restrict__ in, double* __restrict__ out,
@@ -158,8 +166,10 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
     transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
     int slot; double d2;
     if (p.debug_knn_mode == 0 || p.debug_knn_mode >= 10) {
+      int rounds = 0;
       knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2,
-           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30), ss);
+           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30), ss, &rounds);
+      if (b.visits) b.visits[i] = (uint8_t)min(rounds, 255);
     } else {   // profiling aid: truncated variants (results are NOT the k-NN)
       slot = 0; d2 = px * px + py * py + pz * pz + 1.0;
       if (p.debug_knn_mode >= 2) {
@@ -300,16 +310,37 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   return 0;
 }
 
-int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
+// Iterations start_iteration .. start_iteration+count-1 of one Align.  The k-NN of iteration 0
+// records how many buckets every query visited; right after it the queries are re-ordered by
+// that count (stable: Morton order survives inside a class), so that the lanes of a warp need
+// about the same number of sequential traversal rounds in all later iterations (the pose moves
+// little between iterations).  Only sums are formed over the source, so its order is free.
+int icp_enqueue_iterations(const IcpBuffers& b_in, const IcpParams& p, int start_iteration, int count,
                            cudaStream_t stream, cudaEvent_t* events) {
   const int nb = icp_accum_blocks(p.n_source);
+  const bool resort = p.resort_by_visits != 0;
+  IcpBuffers b = b_in;
+  IcpBuffers b_sorted = b_in;       // what iterations >= 1 read once the re-ordering happened
+  b_sorted.src0 = b_in.src_g0;
+  b_sorted.visits = nullptr;
+  if (!resort) b.visits = nullptr;
   for (int it = 0; it < count; ++it) {
+    const int global_it = start_iteration + it;
+    const IcpBuffers& bb = (resort && global_it >= 1) ? b_sorted : b;
     if (events) cudaEventRecord(events[4 * it + 0], stream);
-    icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(b, p);
+    icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
     if (events) cudaEventRecord(events[4 * it + 1], stream);
-    icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
+    icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(bb, p);
     if (events) cudaEventRecord(events[4 * it + 2], stream);
-    icp_finish_launch(b, p, nb, stream);
+    icp_finish_launch(bb, p, nb, stream);
+    if (resort && global_it == 0) {
+      visits_key_kernel<<<ceil_div(p.n_source, 256), 256, 0, stream>>>(b.visits, p.n_source, b.src_keys[0], b.src_vals[0]);
+      int rc = radix_sort_pairs_u64(b.src_keys[0], b.src_vals[0], b.src_keys[1], b.src_vals[1], p.n_source, 1,
+                                    b.sstride, b.src_scratch, stream, 1);   // 1 pass: result in [1]
+      if (rc) return rc;
+      gather_source_kernel<<<ceil_div(p.n_source, 256), 256, 0, stream>>>(b.src0, b.src_g0, b.sstride, p.n_source,
+                                                                         b.src_vals[1]);
+    }
     if (events) cudaEventRecord(events[4 * it + 3], stream);
   }
   SMB_CUDA_OK(cudaGetLastError());

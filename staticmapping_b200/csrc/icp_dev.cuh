@@ -126,7 +126,7 @@ __device__ __forceinline__ SmemStack carve_smem_stack(void* base, int threads) {
   return SmemStack{d, d + n, d + 2 * n, d + 3 * n, reinterpret_cast<int*>(d + 4 * n), threads};
 }
 
-__device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
+__device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
                                               const BucketPoint* __restrict__ bpts, double qx,
                                               double qy, double qz, double max_error2, int idx,
                                               double rd, double ox, double oy, double oz,
@@ -134,8 +134,9 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
                                               SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   StackEntry stack[kMaxStack];
   const int sdepth = ss.rd ? kSmemStackDepth : 0;
-  int sp = 0;
+  int sp = 0, rounds = 0;
   while (max_rounds-- > 0) {
+    ++rounds;
     KdNode nd = load_node(nodes, idx);
     int guard = 0;
     while (nd.dim != 3 && ++guard < 64) {   // a valid tree is at most 25 levels deep
@@ -183,6 +184,7 @@ __device__ __forceinline__ void visit_subtree(const KdNode* __restrict__ nodes,
     }
     if (!found) break;
   }
+  return rounds;
 }
 
 // libnabo knn, k = 1, allowSelfMatch, maxRadius = inf (icp_fast.cc:177-178), one query per
@@ -195,7 +197,8 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
                                      const BucketPoint* __restrict__ bpts, double qx, double qy,
                                      double qz, double max_error2, int& best_slot, double& best_d2,
                                      int max_rounds = 1 << 30,
-                                     SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
+                                     SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0},
+                                     int* rounds_out = nullptr) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double head = inf;
   int best = -1;
@@ -212,8 +215,10 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
   }
   if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
   // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
+  int rounds = 0;
   if (dmul(min_off2, max_error2) < head)
-    visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds, ss);
+    rounds = visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds, ss);
+  if (rounds_out) *rounds_out = rounds;
   best_slot = best;
   best_d2 = head;
 }

@@ -63,6 +63,7 @@ struct IcpParams {
   double max_error2;       // (1+eps)^2
   int disable_convergence;
   int tree_levels;         // kd_num_levels(n_target, 8): depth of the root-to-leaf path
+  int resort_by_visits;    // re-order the queries by their iteration-0 bucket count
   int debug_knn_mode;      // 0 = normal; 1..3 = truncated k-NN kernel variants (profiling aid only)
 };
 
@@ -86,6 +87,7 @@ struct IcpBuffers {
   uint32_t* src_scratch;  // radix scratch
   int64_t sstride;
   // per-iteration
+  uint8_t* visits;        // [n_source] buckets visited by the query in iteration 0 (or null)
   int32_t* slot;          // [n_source] bucket slot of the match
   double* d2;             // [n_source]
   uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
@@ -103,7 +105,7 @@ int icp_accum_blocks(int n_source);
 int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_dev,
                  KdWorkspace& ws, cudaStream_t stream);
 // events (optional): 4 per iteration — before A, after A, after B, after C
-int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int count,
+int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_iteration, int count,
                            cudaStream_t stream, cudaEvent_t* events);
 void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, cudaStream_t stream);
 // stand-alone k-NN over an already built tree (parity tests): ids = original indices

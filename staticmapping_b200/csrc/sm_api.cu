@@ -62,6 +62,7 @@ struct IcpOptions {
   bool profile_kernels = false;
   bool use_graphs = true;
   int32_t debug_knn_mode = 0;
+  bool resort_by_visits = false;   // measured slower (2.19 vs 2.00 ms): spatial coherence matters more
 };
 
 }  // namespace
@@ -125,6 +126,7 @@ const OptionDef kIcpOptions[] = {
     {"profile_kernels", kOptBool, offsetof(IcpOptions, profile_kernels)},
     {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
     {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
+    {"resort_by_visits", kOptBool, offsetof(IcpOptions, resort_by_visits)},
 };
 
 const OptionDef kNdtOptions[] = {
@@ -257,12 +259,13 @@ int icp_enqueue_chunk(sm_handle* h) {
   }
   if (r.graphs) {
     std::string ikey = r.key;
-    key_append(ikey, chunk);
+    const int first_chunk = r.enqueued == 0 ? 1 : 0;
+    key_append(ikey, chunk); key_append(ikey, first_chunk);
     H_RC(run_graphed(h, h->g_iterations, ikey, [&]() {
-      return icp_enqueue_iterations(r.b, p, chunk, h->stream, nullptr);
+      return icp_enqueue_iterations(r.b, p, r.enqueued, chunk, h->stream, nullptr);
     }));
   } else {
-    H_RC(icp_enqueue_iterations(r.b, p, chunk, h->stream, evs));
+    H_RC(icp_enqueue_iterations(r.b, p, r.enqueued, chunk, h->stream, evs));
   }
   r.enqueued += chunk;
   r.launches += 3 * chunk;
@@ -287,7 +290,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
   H_RC(h->bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
   H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
-  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t)));
+  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + (size_t)ns + 64));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
   H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
   H_RC(h->cand_idx.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(uint32_t)));
@@ -311,7 +314,8 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.src_keys[0] = (uint64_t*)h->src_sort.p; b.src_keys[1] = b.src_keys[0] + h->sstride;
   b.src_vals[0] = (uint32_t*)(b.src_keys[1] + h->sstride); b.src_vals[1] = b.src_vals[0] + h->sstride;
   b.src_scratch = b.src_vals[1] + h->sstride;
-  b.slot = (int32_t*)h->slot.p; b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
+  b.slot = (int32_t*)h->slot.p;
+  b.visits = (uint8_t*)((int32_t*)h->slot.p + ns); b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
   b.cand_idx = (uint32_t*)h->cand_idx.p;
@@ -327,6 +331,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   p.disable_convergence = h->icp.disable_convergence_check ? 1 : 0;
   p.debug_knn_mode = h->icp.debug_knn_mode;
   p.tree_levels = levels;
+  p.resort_by_visits = h->icp.resort_by_visits ? 1 : 0;
   if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large (tree deeper than 24 levels)");
 
   memcpy(h->host_guess, guess, 16 * sizeof(double));   // pinned: the caller's array may go away
