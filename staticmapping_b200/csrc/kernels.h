@@ -157,6 +157,7 @@ struct NdtWorkspace {
   double* partials;
   double* sums;             // [64] reduced outputs
   float* minmax;
+  float* sorted_pts;        // target points gathered into voxel order (packed xyz)
   NdtGrid* grid;
   int64_t stride;
   static size_t bytes_needed(int nt, int ns);

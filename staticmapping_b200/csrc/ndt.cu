@@ -147,25 +147,88 @@ __device__ __forceinline__ void inverse3_cofactor(const double* m, double* inv) 
   inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
 }
 
+__global__ void ndt_gather_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ order, int n,
+                                  float* __restrict__ sorted) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = order[k];
+  sorted[3 * (int64_t)k] = pts[3 * (int64_t)i];
+  sorted[3 * (int64_t)k + 1] = pts[3 * (int64_t)i + 1];
+  sorted[3 * (int64_t)k + 2] = pts[3 * (int64_t)i + 2];
+}
+
+// pts: the target points ALREADY in voxel order (ndt_gather_kernel), so a voxel is a contiguous run
 __global__ void ndt_leaf_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ order,
                                 const uint32_t* __restrict__ voxel_start, const NdtGrid* __restrict__ grid,
                                 NdtLeaf* __restrict__ leaves, int min_points, double eig_mult) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= grid->n_voxels) return;
+  // One WARP per voxel.  The 12 running sums of a leaf (sum x: 3, upper triangle of sum x x^T: 6,
+  // float centroid: 3) are 12 independent serial chains that must add the voxel's points in
+  // original order to round like the reference's serial loop.  Per batch of 32 points:
+  //   phase 1 (all lanes, one point each): the 9 double addends (x*1 and the products are formed
+  //            exactly like the serial code: (double)x_r * (double)x_c) go to shared memory,
+  //            transposed to [chain][point];
+  //   phase 2 (lane j owns chain j): 32 shared loads that do not depend on the chain, then the
+  //            32 dependent adds — the serial cost per point is one DADD latency.
+  // A dense voxel (tens of thousands of points next to the sensor) therefore costs ~10 cycles per
+  // point instead of one thread's ~40 dependent FP64 operations.
+  constexpr int kWarps = 8, kPad = 33;
+  __shared__ double s_d[kWarps][9 * kPad];
+  __shared__ float s_f[kWarps][3 * kPad];
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (v >= grid->n_voxels) return;   // whole warps leave together
   const uint32_t s0 = voxel_start[v], s1 = voxel_start[v + 1];
   const int n = (int)(s1 - s0);
-  double sum[3] = {0, 0, 0};
-  double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // Leaf::cov_ starts as identity (header :96-106)
-  float cen[3] = {0, 0, 0};
-  for (uint32_t k = s0; k < s1; ++k) {
-    const uint32_t i = order[k];
-    const float x = pts[3 * (int64_t)i], y = pts[3 * (int64_t)i + 1], z = pts[3 * (int64_t)i + 2];
-    const double p[3] = {(double)x, (double)y, (double)z};
-    for (int d = 0; d < 3; ++d) sum[d] += p[d];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) cov[r * 3 + c] += p[r] * p[c];
-    cen[0] += x; cen[1] += y; cen[2] += z;
+  double* sd = s_d[wib];
+  float* sf = s_f[wib];
+  // chain of the lane: 0..2 sum x_d, 3..8 sum x_r x_c for (r,c) = (0,0)(0,1)(0,2)(1,1)(1,2)(2,2);
+  // lanes 9..11 carry the float centroid of x_{lane-9}; the clamps keep the other lanes on valid
+  // (ignored) chains so the loop is branch-free
+  const int dch = min(lane, 8), fch = (lane >= 9 && lane < 12) ? lane - 9 : 0;
+  const double* my_d = sd + dch * kPad;
+  const float* my_f = sf + fch * kPad;
+  double accd = (lane == 3 || lane == 6 || lane == 8) ? 1.0 : 0.0;   // Leaf::cov_ starts as identity
+  float accf = 0.0f;
+  auto fetch = [&](uint32_t base, float& x, float& y, float& z) {
+    const uint32_t i = min(base + (uint32_t)lane, s1 - 1);
+    x = pts[3 * (int64_t)i]; y = pts[3 * (int64_t)i + 1]; z = pts[3 * (int64_t)i + 2];
+  };
+  float cx, cy, cz, nx = 0.f, ny = 0.f, nz = 0.f;
+  fetch(s0, cx, cy, cz);
+  for (uint32_t base = s0; base < s1; base += 32) {
+    if (base + 32 < s1) fetch(base + 32, nx, ny, nz);
+    const int cnt = (int)min(32u, s1 - base);
+    {
+      const double dx = (double)cx, dy = (double)cy, dz = (double)cz;
+      sd[0 * kPad + lane] = dx; sd[1 * kPad + lane] = dy; sd[2 * kPad + lane] = dz;
+      sd[3 * kPad + lane] = dx * dx; sd[4 * kPad + lane] = dx * dy; sd[5 * kPad + lane] = dx * dz;
+      sd[6 * kPad + lane] = dy * dy; sd[7 * kPad + lane] = dy * dz; sd[8 * kPad + lane] = dz * dz;
+      sf[0 * kPad + lane] = cx; sf[1 * kPad + lane] = cy; sf[2 * kPad + lane] = cz;
+    }
+    __syncwarp();
+    if (cnt == 32) {
+      double td[32]; float tf[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) { td[u] = my_d[u]; tf[u] = my_f[u]; }
+#pragma unroll
+      for (int u = 0; u < 32; ++u) { accd += td[u]; accf += tf[u]; }
+    } else {
+      for (int u = 0; u < cnt; ++u) { accd += my_d[u]; accf += my_f[u]; }
+    }
+    __syncwarp();
+    cx = nx; cy = ny; cz = nz;
   }
+  double sum[3], cov[9];
+  float cen[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { sum[d] = __shfl_sync(0xffffffffu, accd, d); cen[d] = __shfl_sync(0xffffffffu, accf, 9 + d); }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double c = __shfl_sync(0xffffffffu, accd, 3 + j);
+    const int r = j < 3 ? 0 : (j < 5 ? 1 : 2), cc = j < 3 ? j : (j < 5 ? j - 2 : 2);
+    cov[r * 3 + cc] = c; cov[cc * 3 + r] = c;   // x_r * x_c == x_c * x_r bit for bit
+  }
+  if (lane != 0) return;
   NdtLeaf out;
   out.nr_points = n; out.searchable = 0;
   for (int k = 0; k < 9; ++k) out.icov[k] = 0.0;
@@ -508,6 +571,7 @@ size_t NdtWorkspace::bytes_needed(int nt, int ns) {
   b += 2 * (size_t)ndt_table_size(nt) * sizeof(int);                        // hash table
   b += (size_t)(ndt_blocks(ns) + 8) * kNdtSums * sizeof(double) + 64 * sizeof(double);
   b += 1024 * 6 * sizeof(float) + sizeof(NdtGrid) + 4096;
+  b += 3 * st * sizeof(float) + 256;                                          // sorted_pts
   return b + 8192;
 }
 
@@ -534,6 +598,7 @@ void NdtWorkspace::carve(void* base, int nt, int ns) {
   partials = (double*)take((size_t)(ndt_blocks(ns) + 8) * kNdtSums * sizeof(double));
   sums = (double*)take(64 * sizeof(double));
   minmax = (float*)take(1024 * 6 * sizeof(float));
+  sorted_pts = (float*)take(3 * st * sizeof(float));
   grid = (NdtGrid*)take(sizeof(NdtGrid));
 }
 
@@ -551,9 +616,10 @@ int ndt_build_grid(const float* tgt, int nt, float resolution, NdtWorkspace& ws,
   radix_scan_kernel_launch(ws.scratch, nblk, 1, stream);
   ndt_heads_scatter_kernel<<<nblk, kSegT, 0, stream>>>(ws.keys[0], nt, ws.scratch, nblk, ws.voxel_start,
                                                       ws.voxel_key, ws.grid);
-  // one thread per voxel; the voxel count is only known on the device, so launch for nt
-  ndt_leaf_kernel<<<ceil_div(nt, 64), 64, 0, stream>>>(tgt, ws.order[0], ws.voxel_start, ws.grid, ws.leaves,
-                                                      6, 0.01);
+  // one warp per voxel; the voxel count is only known on the device, so launch for nt warps
+  ndt_gather_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(tgt, ws.order[0], nt, ws.sorted_pts);
+  ndt_leaf_kernel<<<ceil_div((int64_t)nt * 32, 256), 256, 0, stream>>>(ws.sorted_pts, ws.order[0], ws.voxel_start,
+                                                                      ws.grid, ws.leaves, 6, 0.01);
   SMB_CUDA_OK(cudaMemsetAsync(ws.table_key, 0xff, (size_t)ws.table_size * sizeof(int), stream));
   ndt_hash_insert_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(ws.voxel_key, ws.leaves, ws.grid, ws.table_key,
                                                                ws.table_val, ws.table_size - 1);
