@@ -216,17 +216,21 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
   for (int r = 0; r < kAccItems; ++r) {
     const int i = tile0 + r * kAccThreads + threadIdx.x;
     bool is_cand = false;
+    double F[6], dot = 0.0, d2 = 0.0;
     if (i < p.n_source && sel.bin >= 0) {
-      const double d2 = b.d2[i];
+      d2 = b.d2[i];
       if (finite_d2(d2)) {
         const int bin = dist_bin(d2);
-        if (bin < sel.bin) {
+        if (bin <= sel.bin) {   // one branch for kept points and quantile-bin members: no extra divergence
           double px, py, pz; BucketPoint q; BucketNormal n;
           load_match(b, T, i, px, py, pz, q, n);
-          accumulate_match(acc, px, py, pz, q, n, d2);
-        } else if (bin == sel.bin) {
-          is_cand = true;
-          atomicAdd(&b.hist2[sub_bin(d2)], 1u);
+          match_terms(px, py, pz, q, n, F, dot);
+          if (bin < sel.bin) {
+            add_terms(acc, F, dot, d2);
+          } else {
+            is_cand = true;
+            atomicAdd(&b.hist2[sub_bin(d2)], 1u);
+          }
         }
       }
     }
@@ -238,9 +242,11 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
 #pragma unroll
     for (int ww = 0; ww < kAccThreads / 32; ++ww) { const uint32_t c = cand_warp[ww]; if (ww < w) off += c; tot += c; }
     if (is_cand) {
-      const int slot = tile0 + off + __popc(m & ((1u << lane) - 1u));
-      b.cand_idx[slot] = (uint32_t)i;
-      b.cand_key[slot] = (unsigned long long)__double_as_longlong(b.d2[i]);
+      const int64_t slot = tile0 + off + __popc(m & ((1u << lane) - 1u));
+      b.cand_key[slot] = (unsigned long long)__double_as_longlong(d2);
+      double2* o = reinterpret_cast<double2*>(b.cand_terms + 8 * slot);
+      o[0] = make_double2(F[0], F[1]); o[1] = make_double2(F[2], F[3]);
+      o[2] = make_double2(F[4], F[5]); o[3] = make_double2(dot, sqrt(d2));
     }
     cand_base += tot;
     __syncthreads();

@@ -266,16 +266,17 @@ __device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist,
   return *out_sm;
 }
 
-// contribution of one match to the normal equations (icp_fast.cc:268-302)
-__device__ __forceinline__ void accumulate_match(double* acc, double px, double py, double pz,
-                                                 const BucketPoint& q, const BucketNormal& n,
-                                                 double d2) {
-  double F[6];
+// contribution of one match to the normal equations (icp_fast.cc:268-302), in two halves so
+// that phase B can park the terms of a quantile-bin member for phase C
+__device__ __forceinline__ void match_terms(double px, double py, double pz, const BucketPoint& q,
+                                            const BucketNormal& n, double* F, double& dot) {
   F[0] = py * n.z - pz * n.y;
   F[1] = pz * n.x - px * n.z;
   F[2] = px * n.y - py * n.x;
   F[3] = n.x; F[4] = n.y; F[5] = n.z;
-  const double dot = (px - q.x) * n.x + (py - q.y) * n.y + (pz - q.z) * n.z;
+  dot = (px - q.x) * n.x + (py - q.y) * n.y + (pz - q.z) * n.z;
+}
+__device__ __forceinline__ void add_terms(double* acc, const double* F, double dot, double d2) {
   int k = 0;
 #pragma unroll
   for (int r = 0; r < 6; ++r)
@@ -285,6 +286,13 @@ __device__ __forceinline__ void accumulate_match(double* acc, double px, double 
   for (int r = 0; r < 6; ++r) acc[21 + r] += F[r] * dot;
   acc[27] += sqrt(d2);
   acc[28] += 1.0;
+}
+__device__ __forceinline__ void accumulate_match(double* acc, double px, double py, double pz,
+                                                 const BucketPoint& q, const BucketNormal& n,
+                                                 double d2) {
+  double F[6], dot;
+  match_terms(px, py, pz, q, n, F, dot);
+  add_terms(acc, F, dot, d2);
 }
 
 __device__ __forceinline__ void load_match(const IcpBuffers& b, const double* T, int i,

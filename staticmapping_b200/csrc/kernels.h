@@ -54,7 +54,10 @@ struct IcpState {
   int done;               // 1 once converged or max_iteration reached
   int status;             // 0 ok, <0 error (-2 no finite distance, -3 nothing kept)
   int solve_path;         // 0 LLT, 1 min-norm, 2 SVD (last iteration)
+  int pad;
+  long long stamps[12];   // clock64 at the section boundaries of the last finish kernel (diagnostics)
 };
+static_assert(sizeof(IcpState) % 8 == 0, "IcpState is copied as 8-byte words");
 
 struct IcpParams {
   int n_source, n_target;
@@ -93,8 +96,9 @@ struct IcpBuffers {
   uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
   uint32_t* hist2;        // [kHistBins] second-level histogram inside the quantile bin (phase B)
   double* sums;           // [32] reduced normal-equation sums of the iteration (phase C1 -> C2)
-  uint32_t* cand_idx;     // [blocks*tile] per-block compacted candidates, then [n_source] flat
-  unsigned long long* cand_key;  // same layout: bit pattern of the candidate's dist^2
+  double* cand_terms;     // [blocks*tile][8] per-block compacted candidates (members of the quantile bin):
+                          // the 6 Jacobian terms, the residual and sqrt(d2) of the match (phase B -> C)
+  unsigned long long* cand_key;  // [blocks*tile] bit pattern of the candidate's dist^2
   uint32_t* cand_cnt;     // [accum blocks]
   double* partials;       // [accum blocks][32]
   double* mean_partials;  // [blocks][4]

@@ -293,8 +293,8 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + (size_t)ns + 64));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
   H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
-  H_RC(h->cand_idx.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(uint32_t)));
-  H_RC(h->cand_key.reserve(((size_t)nb * 512 + (size_t)ns) * sizeof(unsigned long long)));
+  H_RC(h->cand_idx.reserve((size_t)nb * 512 * 8 * sizeof(double)));   // cand_terms
+  H_RC(h->cand_key.reserve((size_t)nb * 512 * sizeof(unsigned long long)));
   H_RC(h->cand_cnt.reserve((size_t)nb * sizeof(uint32_t)));
   H_RC(h->partials.reserve((size_t)nb * 32 * sizeof(double)));
   H_RC(h->mean_partials.reserve((size_t)ceil_div(nt, 1024) * 4 * sizeof(double)));
@@ -318,7 +318,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.visits = (uint8_t*)((int32_t*)h->slot.p + ns); b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
-  b.cand_idx = (uint32_t*)h->cand_idx.p;
+  b.cand_terms = (double*)h->cand_idx.p;
   b.cand_key = (unsigned long long*)h->cand_key.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
   b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
   b.state = (IcpState*)h->state.p;
@@ -956,6 +956,14 @@ int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
 }
 
 const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
+
+// Diagnostics, not part of include/sm_b200.h: clock64 stamps of the sections of the last
+// icp_finish_kernel of the last IcpFast Align (profiles/finish_sections.py).
+int sm_debug_icp_stamps(const sm_handle* h, long long* out12) {
+  if (!h || !out12 || !h->host_state) return SM_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < 12; ++i) out12[i] = h->host_state->stamps[i];
+  return SM_OK;
+}
 
 int sm_calculate_normals(int device, const double* points, int64_t n, double* out_points,
                          double* out_normals, int64_t* m_out) {
