@@ -160,6 +160,23 @@ int sm_knn1(int device, const double* target_3xn, int64_t n_target, const double
 int sm_calculate_normals(int device, const double* points_3xn, int64_t n, double* out_points,
                          double* out_normals, int64_t* m_out);
 
+/* MotionCompensation (builder/map_builder.cc:232-257; called either side of Align at :320-352
+ * when motion_compensation_options.enable is set): every point is moved by
+ * common::InterpolateTransform(Identity, delta, point.factor) (common/math.h:198-211 — slerp of
+ * the rotation, linear translation).  `points` / `out` are arrays of the reference's
+ * data::InnerPointType {float x, y, z, intensity, factor} (builder/data/cloud_types.h:46-52),
+ * consecutive points `stride_bytes` (>= 20) apart; intensity and factor are copied.  `delta` is
+ * 16 doubles, column-major.  Returns SM_ERR_BAD_ARGUMENT where the reference CHECK-fails
+ * (a factor outside [0, 1], common/math.h:201); `out` is still written in that case.
+ * The _device form takes device pointers (in and out may not overlap) and runs on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream); it returns after the stream has
+ * finished. */
+int sm_motion_compensation(int device, const float* points, int64_t n, int64_t stride_bytes,
+                           const double* delta_4x4, float* out);
+int sm_motion_compensation_device(int device, const float* dev_points, int64_t n,
+                                  int64_t stride_bytes, const double* delta_4x4, float* dev_out,
+                                  void* cuda_stream);
+
 int sm_device_count(void);
 const char* sm_version(void);
 

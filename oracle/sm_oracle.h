@@ -117,6 +117,15 @@ int sm_oracle_ndt_gicp_align(const float* source, int64_t ns, const float* targe
                              const double* guess, const sm_oracle_ndt_gicp_options* opt, double* result,
                              double* final_score, sm_oracle_ndt_gicp_info* info);
 
+/* ---- motion compensation either side of Align (oracle/motion_oracle.cc) -------------------- */
+/* common::InterpolateTransform (common/math.h:198-211); -1 where the reference CHECK-fails. */
+int sm_oracle_interpolate_transform(const double* t1, const double* t2, float factor, double* out);
+/* MotionCompensation (builder/map_builder.cc:232-257); points/out: packed InnerPointType
+ * (x, y, z, intensity, factor), 5 floats per point. */
+int sm_oracle_motion_compensation(const float* points, int64_t n, const double* delta, float* out);
+/* common::AverageTransforms (common/math.cc:177-195). */
+int sm_oracle_average_transforms(const double* Ts, int32_t n, double* out);
+
 /* Pieces exposed for unit tests of the restatement itself. */
 int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
 int sm_oracle_quantile_index(int64_t n, float ratio);

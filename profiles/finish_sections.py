@@ -36,6 +36,8 @@ def main():
     f(m._h, out)
     st = list(out)
     d = {NAMES[i]: st[i + 1] - st[i] for i in range(8)}
+    if st[9]:
+        d["solve_again_warm"] = st[9] - st[8]
     print(json.dumps({"cycles": d, "total_cycles": st[8] - st[0],
                       "ms": {k: info[k] for k in ("ms_prologue", "ms_iterations", "ms_knn", "ms_accum", "ms_finish")},
                       "kept": info["kept"]}))

@@ -31,7 +31,6 @@ constexpr int kStateWords = (int)(sizeof(IcpState) / 8);
 struct SolveSmem {
   double S[32];       // reduced sums
   double A[36];       // normal matrix (row-major, symmetric)
-  double W[36];       // Cholesky factor (lower)
   double Z[6][8];     // columns 0..5: L^-1 (certificate), column 6: L^-1 rhs
   double rhs[6], x[6];
   double dT[16], Tn[16], tmp[16];
@@ -48,52 +47,58 @@ __device__ __noinline__ int solve_exact_path(const double* A, const double* rhs,
 // |r_kk| >= sigma_k / (6 * 2^5), so a bound below 1e9 certifies rank 6 with five orders
 // of magnitude to spare and the pivoted QR is skipped; otherwise the exact restatement
 // (QR rank, min-norm branch, SVD fallback) runs.  Returns the path: 0 LLT, 1 min-norm, 2 SVD.
+__device__ __forceinline__ int tri(int i, int j) { return (i * (i + 1)) / 2 + j; }
+
+// The 21 entries of the lower triangle live one per lane (lane = tri(i, j)); pivots and
+// multipliers travel by shuffle, so a factorisation step is sqrt -> divide -> multiply-subtract
+// with no shared-memory round trip in the dependent chain.
 __device__ __forceinline__ int solve_warp(SolveSmem& sm, int lane) {
-#pragma unroll 1
-  for (int idx = lane; idx < 36; idx += 32) {
-    const int r = idx / 6, c = idx % 6;
-    const int lo = min(r, c), hi = max(r, c);
-    const double v = sm.S[lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)];
-    sm.A[idx] = v; sm.W[idx] = v;
-  }
-  if (lane < 6) sm.rhs[lane] = -sm.S[21 + lane];
-  __syncwarp();
+  const int l20 = min(lane, 20);      // lanes 21..31 shadow lane 20 (results ignored)
+  int li = 0;
+#pragma unroll
+  for (int r = 1; r < 6; ++r) li += (l20 >= tri(r, 0)) ? 1 : 0;
+  const int lj = l20 - tri(li, 0);
+  // S holds the upper triangle row-major: A(i,j) with i >= j is entry (j, i)
+  double a = sm.S[lj * 6 - (lj * (lj - 1)) / 2 + (li - lj)];
+  double trace = (li == lj && lane < 21) ? a : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) trace += __shfl_xor_sync(0xffffffffu, trace, o);
+  // The dependent chain of the whole solve is its square roots and divisions (a double-precision
+  // sqrt or divide is a ~20-instruction dependent sequence), so each pivot costs ONE such
+  // sequence: r = 1/sqrt(d) gives l_kk = d*r and every later division by l_kk is a multiplication
+  // by r.  (Eigen's LLT divides; the two differ by rounding only, ~cond(A)*1e-16 relative with
+  // cond(A) < 1e9 certified below, against a parity bar of 1e-4.)
   bool ok = true;
+  double rinv = 0.0;                  // lane tri(k, k): 1 / l_kk
 #pragma unroll 1
   for (int k = 0; k < 6; ++k) {
-    const double d = sm.W[k * 6 + k];
-    ok = ok && (d > 0.0);
-    const double lkk = sqrt(d);
-    __syncwarp();
-    if (lane > k && lane < 6) sm.W[lane * 6 + k] = sm.W[lane * 6 + k] / lkk;
-    if (lane == k) sm.W[k * 6 + k] = lkk;
-    __syncwarp();
-#pragma unroll 1
-    for (int idx = lane; idx < 36; idx += 32) {
-      const int i = idx / 6, j = idx % 6;
-      if (j > k && i >= j) sm.W[idx] -= sm.W[i * 6 + k] * sm.W[j * 6 + k];
+    const double dkk = __shfl_sync(0xffffffffu, a, tri(k, k));
+    ok = ok && (dkk > 0.0);
+    const double r = rsqrt(dkk);
+    if (lj == k) {
+      if (li == k) { a = dkk * r; rinv = r; } else { a = a * r; }
     }
-    __syncwarp();
+    const double lik = __shfl_sync(0xffffffffu, a, tri(li, k));
+    const double ljk = __shfl_sync(0xffffffffu, a, tri(lj, k));   // meaningful for k < lj only
+    if (lj > k) a -= lik * ljk;
   }
   // forward substitution on 7 right-hand sides at once, one lane per column: the six unit
-  // vectors (columns of L^-1, the certificate) and rhs (first half of LLT::solve, icp_fast.cc:252)
+  // vectors (columns of L^-1, the certificate) and rhs = -b (first half of LLT::solve,
+  // icp_fast.cc:252); lanes 7..31 carry a zero column so that every lane joins the shuffles
+  const int c = min(lane, 7);
   double fro2 = 0.0;
-  if (lane < 7 && ok) {
-    const int c = lane;
 #pragma unroll 1
-    for (int i = 0; i < 6; ++i) {
-      double v = (c < 6) ? ((i == c) ? 1.0 : 0.0) : sm.rhs[i];
+  for (int i = 0; i < 6; ++i) {
+    double v = (c < 6) ? ((i == c) ? 1.0 : 0.0) : ((c == 6) ? -sm.S[21 + i] : 0.0);
 #pragma unroll 1
-      for (int j = 0; j < i; ++j) v -= sm.W[i * 6 + j] * sm.Z[j][c];
-      v /= sm.W[i * 6 + i];
-      sm.Z[i][c] = v;
-      if (c < 6) fro2 += v * v;
-    }
+    for (int j = 0; j < i; ++j) v -= __shfl_sync(0xffffffffu, a, tri(i, j)) * sm.Z[j][c];
+    v *= __shfl_sync(0xffffffffu, rinv, tri(i, i));
+    sm.Z[i][c] = v;
+    if (c < 6) fro2 += v * v;
   }
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) fro2 += __shfl_xor_sync(0xffffffffu, fro2, o);
   fro2 = __shfl_sync(0xffffffffu, fro2, 0);
-  const double trace = sm.A[0] + sm.A[7] + sm.A[14] + sm.A[21] + sm.A[28] + sm.A[35];
   const double cond_bound = trace * fro2;
   const bool certified = ok && (cond_bound < 1e9);   // false for NaN/inf as well
   int path = 0;
@@ -103,12 +108,22 @@ __device__ __forceinline__ int solve_warp(SolveSmem& sm, int lane) {
     double s = (lane < 6) ? sm.Z[lane][6] : 0.0;
 #pragma unroll 1
     for (int i = 5; i >= 0; --i) {
-      const double xi = __shfl_sync(0xffffffffu, s / sm.W[i * 6 + i], i);
+      const double ri = __shfl_sync(0xffffffffu, rinv, tri(i, i));
+      const double xi = __shfl_sync(0xffffffffu, s * ri, i);
+      const double lil = __shfl_sync(0xffffffffu, a, tri(i, min(lane, i)));   // L(i, lane)
       if (lane == i) sm.x[i] = xi;
-      if (lane < i) s -= sm.W[i * 6 + lane] * xi;
+      if (lane < i) s -= lil * xi;
     }
-  } else if (lane == 0) {
-    path = solve_exact_path(sm.A, sm.rhs, sm.x);
+  } else {
+#pragma unroll 1
+    for (int idx = lane; idx < 36; idx += 32) {
+      const int r = idx / 6, cc = idx % 6;
+      const int lo = min(r, cc), hi = max(r, cc);
+      sm.A[idx] = sm.S[lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)];
+    }
+    if (lane < 6) sm.rhs[lane] = -sm.S[21 + lane];
+    __syncwarp();
+    if (lane == 0) path = solve_exact_path(sm.A, sm.rhs, sm.x);
   }
   __syncwarp();
   return __shfl_sync(0xffffffffu, path, 0);
@@ -523,6 +538,12 @@ icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
   if (lane == 0) sst.stamps[7] = clock64();
   update_pose(&sst, p, solve, path, lane);
   if (lane == 0) sst.stamps[8] = clock64();
+#ifdef SMB_FINISH_EXPERIMENT
+  {   // how long does the same solve take with its code already fetched?
+    const int path2 = solve_warp(solve, lane);
+    if (lane == 0) { sst.stamps[9] = clock64(); sst.stamps[10] = path2; }
+  }
+#endif
   __syncwarp();
 #pragma unroll 1
   for (int i = lane; i < kStateWords; i += 32) gstate[i] = sstate[i];

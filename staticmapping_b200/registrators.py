@@ -353,3 +353,72 @@ def CalculateNormals(points, device=0) -> EigenCloud:
     if rc != 0:
         raise RuntimeError(f"sm_calculate_normals failed with {rc}")
     return EigenCloud(out_p[:m.value].copy(), out_n[:m.value].copy())
+
+
+def MotionCompensation(raw_cloud, delta_transform, device=0):
+    """MotionCompensation (builder/map_builder.cc:232-257) on the GPU.  `raw_cloud` is an (N,5)
+    float32 array of InnerPointType rows (x, y, z, intensity, factor); every point is moved by
+    common::InterpolateTransform(Identity, delta, factor) (common/math.h:198-211).  Raises
+    CheckFailure where the reference CHECK-fails (a factor outside [0, 1])."""
+    lib = _lib.lib()
+    pts = np.ascontiguousarray(np.asarray(raw_cloud, dtype=np.float32))
+    if pts.ndim != 2 or pts.shape[1] != 5:
+        raise ValueError("raw_cloud must be (N,5): x, y, z, intensity, factor")
+    d = np.asfortranarray(np.asarray(delta_transform, dtype=np.float64))
+    if d.shape != (4, 4):
+        raise ValueError("delta_transform must be 4x4")
+    out = np.empty_like(pts)
+    rc = lib.sm_motion_compensation(device, pts.ctypes.data, pts.shape[0], 20, d.ctypes.data_as(_lib._DP),
+                                    out.ctypes.data)
+    if rc == -20:
+        raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
+    if rc == -1:
+        raise CheckFailure("Check failed: factor >= 0. && factor <= 1. (common/math.h:201)")
+    if rc != 0:
+        raise RuntimeError(f"sm_motion_compensation failed with {rc}")
+    return out
+
+
+def RotationMatrixToEulerAngles(R):
+    """common/math.h:107-127 (host-side 3x3 math; the reference runs it once per frame)."""
+    R = np.asarray(R, dtype=np.float64)
+    sy = np.sqrt(R[0, 0] * R[0, 0] + R[1, 0] * R[1, 0])
+    if not sy < 1e-6:
+        return np.array([np.arctan2(R[2, 1], R[2, 2]), np.arctan2(-R[2, 0], sy), np.arctan2(R[1, 0], R[0, 0])])
+    return np.array([np.arctan2(-R[1, 2], R[1, 1]), np.arctan2(-R[2, 0], sy), 0.0])
+
+
+def AverageTransforms(transforms):
+    """common::AverageTransforms (common/math.cc:177-195): mean translation, mean Euler angles
+    (yaw * pitch * roll composition).  Used by the front end between Align and the second
+    MotionCompensation when motion_compensation_options.use_average is set
+    (map_builder.cc:333-341)."""
+    ts = [np.asarray(t, dtype=np.float64) for t in transforms]
+    if not ts:
+        raise CheckFailure("Check failed: !transforms.empty() (common/math.cc:180)")
+    tr = sum(t[:3, 3] for t in ts) / float(len(ts))
+    ang = sum(RotationMatrixToEulerAngles(t[:3, :3]) for t in ts) / float(len(ts))
+
+    def quat(angle, axis):
+        q = np.zeros(4)
+        q[0] = np.cos(0.5 * angle)
+        q[1 + axis] = np.sin(0.5 * angle)
+        return q
+
+    def mul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                         a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3],
+                         a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1]])
+
+    w, x, y, z = mul(mul(quat(ang[2], 2), quat(ang[1], 1)), quat(ang[0], 0))
+    tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    out = np.eye(4)
+    out[:3, :3] = [[1.0 - (tyy + tzz), txy - twz, txz + twy],
+                   [txy + twz, 1.0 - (txx + tzz), tyz - twx],
+                   [txz - twy, tyz + twx, 1.0 - (txx + tyy)]]
+    out[:3, 3] = tr
+    return out

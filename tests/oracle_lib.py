@@ -243,3 +243,34 @@ def quantile_index(n, ratio=0.7):
 
 def num_threads():
     return lib().sm_oracle_num_threads()
+
+
+# ---- motion compensation either side of Align (oracle/motion_oracle.cc) -------------------------
+def interpolate_transform(t1, t2, factor):
+    a = np.ascontiguousarray(np.asarray(t1, dtype=np.float64).T).ravel()
+    b = np.ascontiguousarray(np.asarray(t2, dtype=np.float64).T).ravel()
+    out = np.zeros(16)
+    f = lib().sm_oracle_interpolate_transform
+    f.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_float, C.POINTER(C.c_double)]
+    rc = f(_d(a), _d(b), float(factor), _d(out))
+    return rc, out.reshape(4, 4).T.copy()
+
+
+def motion_compensation(points5, delta):
+    p = np.ascontiguousarray(np.asarray(points5, dtype=np.float32))
+    assert p.ndim == 2 and p.shape[1] == 5
+    d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64).T).ravel()
+    out = np.zeros_like(p)
+    f = lib().sm_oracle_motion_compensation
+    f.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_void_p]
+    rc = f(p.ctypes.data, p.shape[0], _d(d), out.ctypes.data)
+    return rc, out
+
+
+def average_transforms(transforms):
+    ts = np.ascontiguousarray(np.stack([np.asarray(t, dtype=np.float64).T.ravel() for t in transforms]))
+    out = np.zeros(16)
+    f = lib().sm_oracle_average_transforms
+    f.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]
+    rc = f(_d(ts.ravel()), len(transforms), _d(out))
+    return rc, out.reshape(4, 4).T.copy()
