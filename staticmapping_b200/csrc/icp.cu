@@ -203,55 +203,84 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
   __shared__ BinSel sel_sm;
   __shared__ double T[16];
   __shared__ double red[kAccThreads / 32][kNumSums];
-  __shared__ uint32_t cand_warp[kAccThreads / 32];
+  __shared__ uint32_t cand_warp[kAccItems][kAccThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tile0 = blockIdx.x * kAccTile;
+  // (1) everything that does not depend on the quantile bin is requested up front, for all the
+  //     points of the thread at once (these reads overlap the histogram read of select_bin)
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double d2[kAccItems], sx[kAccItems], sy[kAccItems], sz[kAccItems];
+  int slot[kAccItems];
+#pragma unroll
+  for (int r = 0; r < kAccItems; ++r) {
+    const int i = tile0 + r * kAccThreads + threadIdx.x;
+    const bool in = i < p.n_source;
+    d2[r] = in ? b.d2[i] : inf;
+    slot[r] = in ? b.slot[i] : -1;
+    sx[r] = in ? b.src0[i] : 0.0;
+    sy[r] = in ? b.src0[b.sstride + i] : 0.0;
+    sz[r] = in ? b.src0[2 * b.sstride + i] : 0.0;
+  }
   if (b.state->done) return;
   if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
   const BinSel sel = select_bin(b.hist, p.dist_outlier_ratio, warp_tot, &sel_sm);
+  // (2) the matched target point and normal of every point at or below the quantile bin; the
+  //     other lanes read entry 0 and are masked out, so the gathers of all items go out together
+  bool use[kAccItems], is_cand[kAccItems];
+  int bin[kAccItems];
+  double2 qxy[kAccItems], nxy[kAccItems];
+  double qz[kAccItems], nz[kAccItems];
+#pragma unroll
+  for (int r = 0; r < kAccItems; ++r) {
+    bin[r] = finite_d2(d2[r]) ? dist_bin(d2[r]) : kHistBins;
+    use[r] = sel.bin >= 0 && slot[r] >= 0 && bin[r] <= sel.bin;
+    const int s = use[r] ? slot[r] : 0;
+    qxy[r] = __ldg(reinterpret_cast<const double2*>(b.bpts + s));
+    qz[r] = __ldg(reinterpret_cast<const double*>(b.bpts + s) + 2);
+    nxy[r] = __ldg(reinterpret_cast<const double2*>(b.bnrm + s));
+    nz[r] = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
+  }
   double acc[kNumSums];
 #pragma unroll
   for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t cand_base = 0;
-  const int tile0 = blockIdx.x * kAccTile;
-  for (int r = 0; r < kAccItems; ++r) {
-    const int i = tile0 + r * kAccThreads + threadIdx.x;
-    bool is_cand = false;
-    double F[6], dot = 0.0, d2 = 0.0;
-    if (i < p.n_source && sel.bin >= 0) {
-      d2 = b.d2[i];
-      if (finite_d2(d2)) {
-        const int bin = dist_bin(d2);
-        if (bin <= sel.bin) {   // one branch for kept points and quantile-bin members: no extra divergence
-          double px, py, pz; BucketPoint q; BucketNormal n;
-          load_match(b, T, i, px, py, pz, q, n);
-          match_terms(px, py, pz, q, n, F, dot);
-          if (bin < sel.bin) {
-            add_terms(acc, F, dot, d2);
-          } else {
-            is_cand = true;
-            atomicAdd(&b.hist2[sub_bin(d2)], 1u);
-          }
-        }
-      }
-    }
-    // ordered compaction of candidates: (round, warp, lane) == ascending point index
-    const uint32_t m = __ballot_sync(0xffffffffu, is_cand);
-    if (lane == 0) cand_warp[w] = __popc(m);
-    __syncthreads();
-    uint32_t off = cand_base, tot = 0;
+  double F[kAccItems][6], dot[kAccItems], sq[kAccItems];
 #pragma unroll
-    for (int ww = 0; ww < kAccThreads / 32; ++ww) { const uint32_t c = cand_warp[ww]; if (ww < w) off += c; tot += c; }
-    if (is_cand) {
-      const int64_t slot = tile0 + off + __popc(m & ((1u << lane) - 1u));
-      b.cand_key[slot] = (unsigned long long)__double_as_longlong(d2);
-      double2* o = reinterpret_cast<double2*>(b.cand_terms + 8 * slot);
-      o[0] = make_double2(F[0], F[1]); o[1] = make_double2(F[2], F[3]);
-      o[2] = make_double2(F[4], F[5]); o[3] = make_double2(dot, sqrt(d2));
-    }
-    cand_base += tot;
-    __syncthreads();
+  for (int r = 0; r < kAccItems; ++r) {
+    double px, py, pz;
+    transform_point(T, sx[r], sy[r], sz[r], px, py, pz);
+    BucketPoint q; BucketNormal n;
+    q.x = qxy[r].x; q.y = qxy[r].y; q.z = qz[r];
+    n.x = nxy[r].x; n.y = nxy[r].y; n.z = nz[r];
+    match_terms(px, py, pz, q, n, F[r], dot[r]);
+    sq[r] = sqrt(use[r] ? d2[r] : 0.0);
+    add_terms_if(acc, F[r], dot[r], sq[r], use[r] && bin[r] < sel.bin);
+    is_cand[r] = use[r] && bin[r] == sel.bin;
+    if (is_cand[r]) atomicAdd(&b.hist2[sub_bin(d2[r])], 1u);
   }
-  if (threadIdx.x == 0) b.cand_cnt[blockIdx.x] = cand_base;
+  // (3) ordered compaction of the quantile-bin members: (item, warp, lane) == ascending point index
+  uint32_t m[kAccItems];
+#pragma unroll
+  for (int r = 0; r < kAccItems; ++r) {
+    m[r] = __ballot_sync(0xffffffffu, is_cand[r]);
+    if (lane == 0) cand_warp[r][w] = __popc(m[r]);
+  }
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int r = 0; r < kAccItems; ++r) {
+    uint32_t off = base, tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < kAccThreads / 32; ++ww) { const uint32_t c = cand_warp[r][ww]; if (ww < w) off += c; tot += c; }
+    if (is_cand[r]) {
+      const int64_t dst = tile0 + off + __popc(m[r] & ((1u << lane) - 1u));
+      b.cand_key[dst] = (unsigned long long)__double_as_longlong(d2[r]);
+      double2* o = reinterpret_cast<double2*>(b.cand_terms + 8 * dst);
+      o[0] = make_double2(F[r][0], F[r][1]); o[1] = make_double2(F[r][2], F[r][3]);
+      o[2] = make_double2(F[r][4], F[r][5]); o[3] = make_double2(dot[r], sq[r]);
+    }
+    base += tot;
+  }
+  if (threadIdx.x == 0) b.cand_cnt[blockIdx.x] = base;
   block_reduce_sums<kAccThreads>(acc, red, b.partials + (int64_t)blockIdx.x * 32);
 }
 

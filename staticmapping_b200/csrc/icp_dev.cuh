@@ -308,17 +308,51 @@ __device__ __forceinline__ void load_match(const IcpBuffers& b, const double* T,
   n.z = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
 }
 
+// acc += pred ? terms : 0 (adding +0.0 leaves a sum unchanged, so no branch is needed and the
+// loads feeding several matches can be in flight together); sq = sqrt(d2)
+__device__ __forceinline__ void add_terms_if(double* acc, const double* Fin, double dot_in, double sq,
+                                             bool pred) {
+  double F[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) F[r] = pred ? Fin[r] : 0.0;
+  const double dot = pred ? dot_in : 0.0;
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c) acc[k++] += F[r] * F[c];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) acc[21 + r] += F[r] * dot;
+  acc[27] += pred ? sq : 0.0;
+  acc[28] += pred ? 1.0 : 0.0;
+}
+
+// Sum 32 per-lane values across the warp: on return lane L holds the warp total of v[L].
+// 31 exchanges instead of the 160 of 32 separate butterflies; the pairing is the butterfly's
+// (offsets 16, 8, 4, 2, 1), so each total is bit-identical to the xor-shuffle reduction.
+__device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
 // deterministic block reduction of kNumSums doubles (fixed shuffle tree, fixed warp order)
 template <int NT>
 __device__ __forceinline__ void block_reduce_sums(double* acc, double (*sm)[kNumSums], double* out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double v32[32];
 #pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sm[w][k] = v;
-  }
+  for (int k = 0; k < 32; ++k) v32[k] = k < kNumSums ? acc[k] : 0.0;
+  const double tot = warp_transpose_reduce32(v32, lane);
+  if (lane < kNumSums) sm[w][lane] = tot;
   __syncthreads();
   if (threadIdx.x < kNumSums) {
     double v = 0.0;

@@ -244,30 +244,14 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_t
   return __shfl_sync(0xffffffffu, xi - x, w) + incl - v;
 }
 
-// Sum 32 per-lane values across the warp: on return lane L holds the warp total of v[L].
-// 31 exchanges instead of the 160 of 32 separate butterflies; the pairing is the butterfly's
-// (offsets 16, 8, 4, 2, 1), so each total is bit-identical to the xor-shuffle reduction.
-__device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32], int lane) {
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const double send = up ? v[i] : v[i + h];
-      const double keep = up ? v[i + h] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return v[0];
-}
-
 // exclusive scan of the candidate counts of blocks [base, base + kSelThreads) into
 // blk_off[0..kSelThreads] (the last entry = number of candidates in the chunk)
 __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ cand_cnt, int base, int nblocks,
-                                           uint32_t* blk_off, uint32_t* warp_tot) {
+                                           uint32_t* blk_off, uint32_t* warp_tot, uint32_t cnt0 = 0u,
+                                           bool have_cnt0 = false) {
   const int t = threadIdx.x;
   const int blk = base + t;
-  const uint32_t c = blk < nblocks ? cand_cnt[blk] : 0;
+  const uint32_t c = (have_cnt0 && base == 0) ? cnt0 : (blk < nblocks ? cand_cnt[blk] : 0);
   uint32_t tot;
   const uint32_t excl = block_scan_excl(c, warp_tot, tot);   // syncs before touching warp_tot
   blk_off[t] = excl;
@@ -310,20 +294,9 @@ __device__ __forceinline__ CandTerms load_candidate(const IcpBuffers& b, uint32_
   const double2* o = reinterpret_cast<const double2*>(b.cand_terms + 8 * (int64_t)slot);
   return CandTerms{o[0], o[1], o[2], o[3]};
 }
-// acc += member ? terms : 0 (adding +0.0 leaves a sum unchanged, so no branch is needed)
 __device__ __forceinline__ void add_candidate(double* acc, const CandTerms& c, bool member) {
-  const double F[6] = {member ? c.a0.x : 0.0, member ? c.a0.y : 0.0, member ? c.a1.x : 0.0,
-                       member ? c.a1.y : 0.0, member ? c.a2.x : 0.0, member ? c.a2.y : 0.0};
-  const double dot = member ? c.a3.x : 0.0;
-  int k = 0;
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int cc = r; cc < 6; ++cc) acc[k++] += F[r] * F[cc];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) acc[21 + r] += F[r] * dot;
-  acc[27] += member ? c.a3.y : 0.0;
-  acc[28] += member ? 1.0 : 0.0;
+  const double F[6] = {c.a0.x, c.a0.y, c.a1.x, c.a1.y, c.a2.x, c.a2.y};
+  add_terms_if(acc, F, c.a3.x, c.a3.y, member);
 }
 
 __global__ void __launch_bounds__(kSelThreads)
@@ -350,6 +323,9 @@ icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
   __syncthreads();
   if (sst.done) return;
   if (t == 0) sst.stamps[0] = clock64();
+  // independent global reads issued together with select_bin's histogram read
+  const uint32_t cnt0 = t < nblocks_b ? b.cand_cnt[t] : 0u;
+  const uint4 cq = *reinterpret_cast<const uint4*>(b.hist2 + 4 * t);
   const BinSel sel = select_bin(b.hist, p.dist_outlier_ratio, warp_tot, &sel_sm);
   if (sel.nvalid == 0) {
     if (t == 0) { b.state->status = -2; b.state->done = 1; }  // CHECK(!values.empty()), icp_fast.cc:81
@@ -361,7 +337,6 @@ icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
   if (!fallback) {
     // ---- second-level histogram: 4 bins per thread, block exclusive scan ------------------
     static_assert(kSelThreads * 4 == kHistBins, "4 second-level bins per thread");
-    const uint4 cq = *reinterpret_cast<const uint4*>(b.hist2 + 4 * t);
     const uint32_t c[4] = {cq.x, cq.y, cq.z, cq.w};
     const uint32_t s = c[0] + c[1] + c[2] + c[3];
     uint32_t tot2;
@@ -389,7 +364,7 @@ icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
     constexpr int R = 3;                  // candidates per thread whose loads are in flight together
 #pragma unroll 1
     for (int base = 0; base < nblocks_b; base += kSelThreads) {
-      if (!have_scan) scan_chunk(b.cand_cnt, base, nblocks_b, blk_off, warp_tot);
+      if (!have_scan) scan_chunk(b.cand_cnt, base, nblocks_b, blk_off, warp_tot, cnt0, true);
       const uint32_t tot = blk_off[kSelThreads];
 #pragma unroll 1
       for (uint32_t k0 = 0; k0 < tot; k0 += kSelThreads * R) {
