@@ -143,6 +143,30 @@ class NdtWithGicpB200 : public FloatCloudMatcherB200<SM_TYPE_NDT_WITH_GICP> {
   struct { float voxel_resolution = 0.2; bool using_voxel_filter = true; bool use_ndt = true; } options_;
 };
 
+// Stand-in for registrator::IcpUsingPointMatcher (icp_pointmatcher.h, .cc:125-247): the default
+// libpointmatcher chain (random reading filter 0.9, surface-normal reference filter knn 7, k-d
+// tree eps 3.16, trimmed 0.7, point-to-plane, 150 iterations / differential checker) run by the
+// IcpFast kernels; Align() is false below score 0.6 (.cc:145).  Registers no option.  It is what
+// loop_detector.cc:304-308 would construct instead of `new IcpUsingPointMatcher`.
+class IcpUsingPointMatcherB200 : public FloatCloudMatcherB200<SM_TYPE_ICP_PM> {
+ public:
+  explicit IcpUsingPointMatcherB200(int device = 0) : FloatCloudMatcherB200<SM_TYPE_ICP_PM>(device) {}
+};
+
+// MotionCompensation (builder/map_builder.cc:232-257) on the GPU: same signature as the static
+// function it replaces, so the two call sites (:325-327, :344-347) stay as they are.
+inline void MotionCompensationB200(const data::InnerCloudType& raw_cloud, const Eigen::Matrix4d& delta_transform,
+                                   data::InnerCloudType* const output_cloud, int device = 0) {
+  CHECK(output_cloud);
+  output_cloud->stamp = raw_cloud.stamp;
+  output_cloud->points.resize(raw_cloud.points.size());
+  if (raw_cloud.points.empty()) return;
+  const int rc = sm_motion_compensation(device, &raw_cloud.points[0].x, static_cast<int64_t>(raw_cloud.points.size()),
+                                        sizeof(data::InnerPointType), delta_transform.data(),
+                                        &output_cloud->points[0].x);
+  CHECK_EQ(rc, 0) << "MotionCompensation: factor outside [0, 1] (common/math.h:201) or CUDA failure";
+}
+
 // EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368); call sites
 // map_builder.cc:286,389 and submap.cc:161.
 inline void CalculateNormalsB200(data::EigenPointCloud* cloud, int device = 0) {

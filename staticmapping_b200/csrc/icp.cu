@@ -157,7 +157,6 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
   // measured: keeping the first 4 pending subtrees per thread in shared memory is SLOWER
   // (2.34 vs 2.00 ms per 30 launches): the 37 KB per block come out of the L1 that caches the
   // tree lines.  The stack therefore stays in (L1-cached) local memory.
-  const SmemStack ss = no_smem_stack();
   if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
   __syncthreads();
   const int i = blockIdx.x * kKnnThreads + threadIdx.x;
@@ -168,7 +167,7 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
     if (p.debug_knn_mode == 0 || p.debug_knn_mode >= 10) {
       int rounds = 0;
       knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2,
-           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30), ss, &rounds);
+           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30), &rounds);
       if (b.visits) b.visits[i] = (uint8_t)min(rounds, 255);
     } else {   // profiling aid: truncated variants (results are NOT the k-NN)
       slot = 0; d2 = px * px + py * py + pz * pz + 1.0;
@@ -177,7 +176,7 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
         KdNode nd = load_node(b.nodes, 0);
         while (nd.dim != 3) {
           const double q = nd.dim == 0 ? px : (nd.dim == 1 ? py : pz);
-          idx = child_idx(idx, (dsub(q, nd.cut) > 0.0) ? 1 : 0);
+          idx = child_idx(idx, (q > nd.cut) ? 1 : 0);
           nd = load_node(b.nodes, idx);
         }
         slot = (int)(__double_as_longlong(nd.cut) & 0xffffffffll);

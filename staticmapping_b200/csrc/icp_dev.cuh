@@ -67,7 +67,13 @@ __device__ __forceinline__ double ldg_f64(const void* p) {
 
 // Scan one bucket.  All 8 entries are fetched up front (the bucket array is padded by 8
 // entries, so reading past `count` is safe); entries >= count are ignored.
-// Strict '<': first visited wins.
+// libnabo walks the bucket in order and replaces the head on a strict '<', i.e. it ends with the
+// FIRST entry that attains the bucket minimum, provided that minimum is below the head.  The 8
+// squared distances are formed with the reference's exact operation order; the selection then
+// runs on their bit patterns (non-negative doubles order like unsigned integers; a NaN sorts
+// above +inf and is never taken, like a false '<') as a 3-level tournament in which the lower
+// index wins ties.  FP64 compares sit on the 23-cycle double pipe (profiles/microbench), so a
+// serial compare/select chain over 8 entries was the longest dependency of a bucket visit.
 __device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, const KdNode& leaf,
                                           double qx, double qy, double qz, double& head,
                                           int& best) {
@@ -81,11 +87,28 @@ __device__ __forceinline__ void scan_leaf(const BucketPoint* __restrict__ bpts, 
     xy[k] = ldg_f64x2(base + 32 * k);
     z[k] = ldg_f64(base + 32 * k + 16);
   }
+  unsigned long long key[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const double dx = dsub(qx, xy[k].x), dy = dsub(qy, xy[k].y), dz = dsub(qz, z[k]);
     const double dist = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
-    if (k < count && dist < head) { head = dist; best = first + k; }
+    key[k] = k < count ? (unsigned long long)__double_as_longlong(dist) : ~0ull;
+  }
+  int arg[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) arg[k] = k;
+#pragma unroll
+  for (int step = 1; step < 8; step <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2 * step) {
+      const bool take = key[k + step] < key[k];      // strict: the lower index keeps a tie
+      key[k] = take ? key[k + step] : key[k];
+      arg[k] = take ? arg[k + step] : arg[k];
+    }
+  }
+  if (key[0] < (unsigned long long)__double_as_longlong(head)) {
+    head = __longlong_as_double((long long)key[0]);
+    best = first + arg[0];
   }
 }
 
@@ -107,33 +130,17 @@ __device__ __forceinline__ int child_idx(int idx, int right) {
 // they pass the test against the head known at push time (the head only shrinks, so nothing
 // the recursion would visit is dropped) and re-tested when popped, which is when the
 // recursion tests them.
-// The first kSmemStackDepth pending subtrees of a thread live in shared memory
-// ([level][thread], conflict free); deeper ones (rare) spill to the local array.  With
-// `ss.rd == nullptr` everything uses the local array.
-constexpr int kSmemStackDepth = 4;
-struct SmemStack {
-  double* rd; double* ox; double* oy; double* oz; int* idx;
-  int nthreads;
-};
-__device__ __forceinline__ SmemStack no_smem_stack() { return SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}; }
-// bytes of dynamic shared memory a block of `threads` needs for the stack
-__host__ __device__ __forceinline__ size_t smem_stack_bytes(int threads) {
-  return (size_t)kSmemStackDepth * threads * (4 * sizeof(double) + sizeof(int));
-}
-__device__ __forceinline__ SmemStack carve_smem_stack(void* base, int threads) {
-  double* d = reinterpret_cast<double*>(base);
-  const int n = kSmemStackDepth * threads;
-  return SmemStack{d, d + n, d + 2 * n, d + 3 * n, reinterpret_cast<int*>(d + 4 * n), threads};
-}
-
+// The side of the cut is decided by `q > cut` (== `q - cut > 0` for IEEE doubles) and the near
+// child's node is requested at once; the far-side bookkeeping (new_off, rd, the push test: six
+// dependent FP64 operations) then runs in the shadow of that load instead of in front of it.
+// The pending subtrees live in (L1-cached) local memory: a shared-memory stack was measured
+// slower, it takes its bytes from the L1 that caches the tree lines.
 __device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
                                               const BucketPoint* __restrict__ bpts, double qx,
                                               double qy, double qz, double max_error2, int idx,
                                               double rd, double ox, double oy, double oz,
-                                              double& head, int& best, int max_rounds = 1 << 20,
-                                              SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
+                                              double& head, int& best, int max_rounds = 1 << 20) {
   StackEntry stack[kMaxStack];
-  const int sdepth = ss.rd ? kSmemStackDepth : 0;
   int sp = 0, rounds = 0;
   while (max_rounds-- > 0) {
     ++rounds;
@@ -143,39 +150,28 @@ __device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
       const int cd = nd.dim;
       const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
       const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+      const int right = q > nd.cut ? 1 : 0;
+      const int next = child_idx(idx, right);
+      const KdNode nd_next = load_node(nodes, next);
       const double new_off = dsub(q, nd.cut);
-      const int right = new_off > 0.0 ? 1 : 0;
       // rd += - old_off*old_off + new_off*new_off
       const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-      if (dmul(rd_new, max_error2) < head && sp < kMaxStack + sdepth) {
+      if (dmul(rd_new, max_error2) < head && sp < kMaxStack) {
         StackEntry e;
         e.rd = rd_new;
         e.ox = cd == 0 ? new_off : ox;
         e.oy = cd == 1 ? new_off : oy;
         e.oz = cd == 2 ? new_off : oz;
         e.idx = child_idx(idx, 1 - right);
-        if (sp < sdepth) {
-          const int k = sp * ss.nthreads + threadIdx.x;
-          ss.rd[k] = e.rd; ss.ox[k] = e.ox; ss.oy[k] = e.oy; ss.oz[k] = e.oz; ss.idx[k] = e.idx;
-        } else {
-          stack[sp - sdepth] = e;
-        }
-        ++sp;
+        stack[sp++] = e;
       }
-      idx = child_idx(idx, right);
-      nd = load_node(nodes, idx);
+      idx = next;
+      nd = nd_next;
     }
     if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
     bool found = false;
     while (sp > 0) {
-      --sp;
-      StackEntry e;
-      if (sp < sdepth) {
-        const int k = sp * ss.nthreads + threadIdx.x;
-        e.rd = ss.rd[k]; e.ox = ss.ox[k]; e.oy = ss.oy[k]; e.oz = ss.oz[k]; e.idx = ss.idx[k];
-      } else {
-        e = stack[sp - sdepth];
-      }
+      const StackEntry e = stack[--sp];
       if (dmul(e.rd, max_error2) < head) {
         idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
         found = true;
@@ -196,9 +192,7 @@ __device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
 __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
                                      const BucketPoint* __restrict__ bpts, double qx, double qy,
                                      double qz, double max_error2, int& best_slot, double& best_d2,
-                                     int max_rounds = 1 << 30,
-                                     SmemStack ss = SmemStack{nullptr, nullptr, nullptr, nullptr, nullptr, 0},
-                                     int* rounds_out = nullptr) {
+                                     int max_rounds = 1 << 30, int* rounds_out = nullptr) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double head = inf;
   int best = -1;
@@ -208,16 +202,17 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
   int guard = 0;
   while (nd.dim != 3 && ++guard < 64) {
     const double q = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
+    idx = child_idx(idx, (q > nd.cut) ? 1 : 0);
+    const KdNode nd_next = load_node(nodes, idx);
     const double off = dsub(q, nd.cut);
     min_off2 = fmin(min_off2, dmul(off, off));
-    idx = child_idx(idx, (off > 0.0) ? 1 : 0);
-    nd = load_node(nodes, idx);
+    nd = nd_next;
   }
   if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
   // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
   int rounds = 0;
   if (dmul(min_off2, max_error2) < head)
-    rounds = visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds, ss);
+    rounds = visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds);
   if (rounds_out) *rounds_out = rounds;
   best_slot = best;
   best_d2 = head;

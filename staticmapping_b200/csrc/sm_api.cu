@@ -50,6 +50,45 @@ __global__ void deinterleave3_kernel(const double* __restrict__ aos, double* __r
   soa[2 * stride + i] = aos[3 * (int64_t)i + 2];
 }
 
+// ---- reading filter of the IcpUsingPointMatcher stand-in (see pm_align) ----------------------
+__device__ __forceinline__ bool pm_keep(uint32_t i, uint32_t seed, uint32_t thresh, bool all) {
+  uint32_t x = i * 0x9E3779B9u + seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return all || x < thresh;
+}
+
+__global__ void __launch_bounds__(256)
+pm_sample_count_kernel(int n, uint32_t seed, uint32_t thresh, int all, uint32_t* __restrict__ block_cnt) {
+  __shared__ uint32_t wc[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool k = i < n && pm_keep((uint32_t)i, seed, thresh, all != 0);
+  const uint32_t m = __ballot_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += wc[w]; block_cnt[blockIdx.x] = t; }
+}
+
+// kept points, original order, as 3xN column-major doubles (EigenPointCloud::FromPointCloud)
+__global__ void __launch_bounds__(256)
+pm_sample_scatter_kernel(const float* __restrict__ pts, int n, uint32_t seed, uint32_t thresh, int all,
+                         const uint32_t* __restrict__ block_off, double* __restrict__ out) {
+  __shared__ uint32_t wc[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool k = i < n && pm_keep((uint32_t)i, seed, thresh, all != 0);
+  const uint32_t m = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) wc[w] = __popc(m);
+  __syncthreads();
+  uint32_t off = block_off[blockIdx.x];
+  for (int ww = 0; ww < w; ++ww) off += wc[ww];
+  if (k) {
+    const int64_t d = off + __popc(m & ((1u << lane) - 1u));
+    out[3 * d] = (double)pts[3 * (int64_t)i];
+    out[3 * d + 1] = (double)pts[3 * (int64_t)i + 1];
+    out[3 * d + 2] = (double)pts[3 * (int64_t)i + 2];
+  }
+}
+
 enum OptKind { kOptInt, kOptFloat, kOptBool };
 struct OptionDef { const char* name; OptKind kind; size_t offset; };
 
@@ -63,6 +102,10 @@ struct IcpOptions {
   bool use_graphs = true;
   int32_t debug_knn_mode = 0;
   bool resort_by_visits = false;   // measured slower (2.19 vs 2.00 ms): spatial coherence matters more
+  // type 1 (IcpUsingPointMatcher stand-in) only, icp_pointmatcher.cc:166-247
+  float reading_sample_prob = 0.9f;      // RandomSamplingDataPointsFilter prob (:173)
+  float accept_min_score = 0.6f;         // Align returns false below it (:145)
+  int32_t sample_seed = 1;
 };
 
 }  // namespace
@@ -113,6 +156,10 @@ struct sm_handle {
   // NdtWithGicp
   struct { float voxel_resolution = 0.2f; bool using_voxel_filter = true; bool use_ndt = true; } ng;   // ndt_gicp.h:71-75
   DevBuf src_filt, tgt_filt, approx_ws, src_soa, nodes2, leaf_order2, bpts2, cov_s, cov_t, maha, match, gicp_partials, counter;
+  // IcpUsingPointMatcher stand-in (type 1): raw float clouds -> filtered double clouds
+  int64_t pm_n_src = 0, pm_n_tgt = 0;
+  bool pm_src_dirty = false, pm_tgt_dirty = false;
+  DevBuf pm_coord, pm_nodes, pm_order, pm_kdws, pm_tmp_pts, pm_tmp_nrm, pm_keep, pm_bsum, pm_outp, pm_outn, pm_cnt, pm_src;
 };
 
 namespace {
@@ -127,6 +174,9 @@ const OptionDef kIcpOptions[] = {
     {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
     {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
     {"resort_by_visits", kOptBool, offsetof(IcpOptions, resort_by_visits)},
+    {"reading_sample_prob", kOptFloat, offsetof(IcpOptions, reading_sample_prob)},
+    {"accept_min_score", kOptFloat, offsetof(IcpOptions, accept_min_score)},
+    {"sample_seed", kOptInt, offsetof(IcpOptions, sample_seed)},
 };
 
 const OptionDef kNdtOptions[] = {
@@ -243,6 +293,7 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
 
 int ndt_align(sm_handle* h, const double* guess, double* result);
 int ndt_gicp_align(sm_handle* h, const double* guess, double* result);
+int pm_align(sm_handle* h, const double* guess, double* result);
 
 // one chunk of iterations + the asynchronous read-back of the state record
 int icp_enqueue_chunk(sm_handle* h) {
@@ -405,6 +456,79 @@ int icp_end(sm_handle* h, double* result) {
 int icp_align(sm_handle* h, const double* guess, double* result) {
   H_RC(icp_begin(h, guess));
   return icp_end(h, result);
+}
+
+// ---- IcpUsingPointMatcher stand-in (type 1) ------------------------------------------------
+// registrators/icp_pointmatcher.cc:125-247 drives libpointmatcher 1.3.1 (external, float) with
+//   reading filter    RandomSampling prob 0.9                      -> pm_sample_* below (a counter
+//                     hash instead of std::rand, so the kept set is reproducible)
+//   reference filter  SamplingSurfaceNormal knn 7, one point per box -> CalculateNormals, the
+//                     reference author's own restatement of that filter (cloud_types.cc:73-144)
+//   matcher / outlier filter / minimiser / checkers                 -> the IcpFast chain, which
+//                     icp_fast.cc ported from exactly these modules (k-d tree eps 3.16, trim 0.7,
+//                     point-to-plane, 4-sample differential checker 0.001 rad / 0.01 m), here in
+//                     double, capped at 150 iterations
+//   Align()           false when exp(-mean kept distance) < 0.6 (:145)
+// It is a deterministic equivalent, not a bit-level restatement: libpointmatcher's float
+// arithmetic and its rand() stream cannot be pinned from this tree.
+int pm_align(sm_handle* h, const double* guess, double* result) {
+  if (!h->has_source || !h->has_target || h->pm_n_src <= 0 || h->pm_n_tgt <= 0)
+    return fail(h, SM_ERR_MISSING_INPUT, "Align: source/target not set");
+  cudaStream_t s = h->stream;
+  if (h->pm_tgt_dirty) {
+    const int64_t n = h->pm_n_tgt, cs = pad64(n);
+    const int levels = kd_num_levels((int)n, 7);
+    const size_t aos = (size_t)3 * (size_t)n * sizeof(double);
+    H_RC(h->pm_coord.reserve((size_t)3 * cs * sizeof(double)));
+    H_RC(h->pm_nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
+    H_RC(h->pm_order.reserve((size_t)n * sizeof(uint32_t)));
+    H_RC(h->pm_kdws.reserve(KdWorkspace::bytes_needed((int)n, 7)));
+    H_RC(h->pm_tmp_pts.reserve(aos)); H_RC(h->pm_tmp_nrm.reserve(aos));
+    H_RC(h->pm_keep.reserve((size_t)n * sizeof(uint32_t)));
+    H_RC(h->pm_bsum.reserve((size_t)(normals_scratch_blocks((int)n) + 1) * sizeof(uint32_t)));
+    H_RC(h->pm_outp.reserve(aos)); H_RC(h->pm_outn.reserve(aos));
+    H_RC(h->pm_cnt.reserve(((size_t)ceil_div(h->pm_n_src > n ? h->pm_n_src : n, 256) + 8) * sizeof(uint32_t)));
+    H_RC(ndt_float_to_soa((const float*)h->tgt_f32.p, (int)n, (double*)h->pm_coord.p, cs, s));
+    KdWorkspace ws;
+    ws.carve(h->pm_kdws.p, (int)n, 7);
+    uint32_t* mdev = (uint32_t*)h->pm_cnt.p;
+    H_RC(normals_run((const double*)h->pm_coord.p, cs, (int)n, ws, (KdNode*)h->pm_nodes.p, (uint32_t*)h->pm_order.p,
+                     (double*)h->pm_tmp_pts.p, (double*)h->pm_tmp_nrm.p, (uint32_t*)h->pm_keep.p,
+                     (uint32_t*)h->pm_bsum.p, (double*)h->pm_outp.p, (double*)h->pm_outn.p, mdev, s));
+    uint32_t m = 0;
+    H_CUDA(cudaMemcpyAsync(&m, mdev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    H_CUDA(cudaStreamSynchronize(s));
+    if (m == 0) return fail(h, SM_ERR_MISSING_INPUT, "Align: no target point survived the surface-normal filter");
+    H_RC(set_target(h, (const double*)h->pm_outp.p, (const double*)h->pm_outn.p, (int64_t)m, true));
+    h->pm_tgt_dirty = false;
+  }
+  if (h->pm_src_dirty) {
+    const int64_t n = h->pm_n_src;
+    const int nb = ceil_div(n, 256);
+    H_RC(h->pm_cnt.reserve(((size_t)nb + 8) * sizeof(uint32_t)));
+    H_RC(h->pm_src.reserve((size_t)3 * (size_t)n * sizeof(double)));
+    const double prob = (double)h->icp.reading_sample_prob;
+    const int all = prob >= 1.0 ? 1 : 0;
+    const uint32_t thresh = prob <= 0.0 ? 0u : (all ? 0xffffffffu : (uint32_t)(prob * 4294967296.0));
+    uint32_t* cnt = (uint32_t*)h->pm_cnt.p;
+    H_CUDA(cudaMemsetAsync(cnt + nb, 0, sizeof(uint32_t), s));
+    pm_sample_count_kernel<<<nb, 256, 0, s>>>((int)n, (uint32_t)h->icp.sample_seed, thresh, all, cnt);
+    radix_scan_kernel_launch(cnt, nb + 1, 1, s);            // exclusive: cnt[nb] = number kept
+    pm_sample_scatter_kernel<<<nb, 256, 0, s>>>((const float*)h->src_f32.p, (int)n, (uint32_t)h->icp.sample_seed, thresh,
+                                              all, cnt, (double*)h->pm_src.p);
+    H_CUDA(cudaGetLastError());
+    uint32_t kept = 0;
+    H_CUDA(cudaMemcpyAsync(&kept, cnt + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    H_CUDA(cudaStreamSynchronize(s));
+    if (kept == 0) return fail(h, SM_ERR_MISSING_INPUT, "Align: the reading filter kept no point");
+    H_RC(set_source(h, (const double*)h->pm_src.p, (int64_t)kept, true));
+    h->pm_src_dirty = false;
+  }
+  const int rc = icp_align(h, guess, result);
+  h->info.aux[2] = (double)h->n_source;   // reading points after the filter
+  h->info.aux[3] = (double)h->n_target;   // reference points after the filter
+  if (rc < 0) return rc;
+  return h->final_score < (double)h->icp.accept_min_score ? 0 : 1;
 }
 
 // ---- Ndt ---------------------------------------------------------------------------------
@@ -777,13 +901,15 @@ const char* sm_version(void) { return "sm_b200 0.1 (sm_100a)"; }
 int sm_create(int type, int device, sm_handle** out) {
   if (!out) return SM_ERR_BAD_ARGUMENT;
   *out = nullptr;
-  if (type != SM_TYPE_FAST_ICP && type != SM_TYPE_NDT && type != SM_TYPE_NDT_WITH_GICP) return SM_ERR_UNSUPPORTED_TYPE;
+  if (type != SM_TYPE_FAST_ICP && type != SM_TYPE_NDT && type != SM_TYPE_NDT_WITH_GICP && type != SM_TYPE_ICP_PM)
+    return SM_ERR_UNSUPPORTED_TYPE;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
   if (device < 0 || device >= ndev) return SM_ERR_BAD_ARGUMENT;
   sm_handle* h = new sm_handle();
   h->type = type;
   h->device = device;
+  if (type == SM_TYPE_ICP_PM) h->icp.max_iteration = 150;   // CounterTransformationChecker, icp_pointmatcher.cc:214
   memset(&h->info, 0, sizeof(h->info));
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -817,6 +943,7 @@ int sm_destroy(sm_handle* h) {
   for (int i = 0; i < 4; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
   h->src_f32.release(); h->tgt_f32.release(); h->ndt_ws.release(); h->tgt_soa.release();
   { DevBuf* gb[] = {&h->src_filt, &h->tgt_filt, &h->approx_ws, &h->src_soa, &h->nodes2, &h->leaf_order2, &h->bpts2, &h->cov_s, &h->cov_t, &h->maha, &h->match, &h->gicp_partials, &h->counter}; for (DevBuf* b : gb) b->release(); }
+  { DevBuf* pb[] = {&h->pm_coord, &h->pm_nodes, &h->pm_order, &h->pm_kdws, &h->pm_tmp_pts, &h->pm_tmp_nrm, &h->pm_keep, &h->pm_bsum, &h->pm_outp, &h->pm_outn, &h->pm_cnt, &h->pm_src}; for (DevBuf* b : pb) b->release(); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SM_OK;
@@ -906,22 +1033,22 @@ int sm_set_input_target_device(sm_handle* h, const double* p, const double* nrm,
 
 int sm_set_input_source_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, false, h->src_f32);
-  if (rc == 0) { h->n_source = n; h->has_source = true; }
+  if (rc == 0) { h->n_source = n; h->has_source = true; h->pm_n_src = n; h->pm_src_dirty = true; }
   return rc;
 }
 int sm_set_input_target_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, false, h->tgt_f32);
-  if (rc == 0) { h->n_target = n; h->has_target = true; }
+  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; }
   return rc;
 }
 int sm_set_input_source_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, true, h->src_f32);
-  if (rc == 0) { h->n_source = n; h->has_source = true; }
+  if (rc == 0) { h->n_source = n; h->has_source = true; h->pm_n_src = n; h->pm_src_dirty = true; }
   return rc;
 }
 int sm_set_input_target_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, true, h->tgt_f32);
-  if (rc == 0) { h->n_target = n; h->has_target = true; }
+  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; }
   return rc;
 }
 
@@ -931,6 +1058,7 @@ int sm_align(sm_handle* h, const double* guess, double* result) {
   if (h->type == SM_TYPE_FAST_ICP) return icp_align(h, guess, result);
   if (h->type == SM_TYPE_NDT) return ndt_align(h, guess, result);
   if (h->type == SM_TYPE_NDT_WITH_GICP) return ndt_gicp_align(h, guess, result);
+  if (h->type == SM_TYPE_ICP_PM) return pm_align(h, guess, result);
   return fail(h, SM_ERR_UNSUPPORTED_TYPE, "matcher type not supported");
 }
 

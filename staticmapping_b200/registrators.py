@@ -297,6 +297,29 @@ class NdtWithGicp(Ndt):
         return Interface.Align(self, guess)
 
 
+class IcpUsingPointMatcher(Ndt):
+    """Stand-in for registrator::IcpUsingPointMatcher (icp_pointmatcher.h / .cc:125-247), the
+    libpointmatcher-driven ICP that loop_detector.cc:304-308 constructs directly.  Same module
+    chain as the reference's default config (:166-247): reading filter RandomSampling 0.9,
+    reference filter SamplingSurfaceNormal knn 7 (== CalculateNormals), k-d tree matcher eps 3.16,
+    TrimmedDist 0.7, point-to-plane minimiser, 150-iteration counter + 4-sample differential
+    checker; GetFitnessScore() = exp(-mean kept distance), Align() is False below 0.6 (:145).
+    libpointmatcher itself (1.3.1, float, std::rand) is external to the reference tree, so this is
+    a deterministic double-precision equivalent built from the IcpFast kernels, not a bit-level
+    restatement.  It registers no XML option (the reference takes a YAML file name instead)."""
+    _type = Type.kIcpPM
+
+    def __init__(self, device: int = 0, ymal_file: str = ""):
+        if ymal_file:
+            raise CheckFailure("IcpUsingPointMatcher: YAML configs are not supported, only loadDefaultConfig()")
+        super().__init__(device)
+
+    def Align(self, guess):
+        if self._source is None or self._target is None:
+            raise CheckFailure("IcpUsingPointMatcher::Align: input cloud not set")
+        return Interface.Align(self, guess)
+
+
 def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 0) -> Interface:
     """registrator::CreateMatcher (interface.cc:139-173)."""
     t = Type(options.type)
@@ -310,7 +333,7 @@ def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 
     elif t == Type.kNdtWithGicp:
         matcher = NdtWithGicp(device)
     elif t == Type.kIcpPM:
-        raise NotImplementedError(f"matcher type {t.name} is not built yet in sm_b200")
+        matcher = IcpUsingPointMatcher(device)
     else:
         print("Wrong type")   # PRINT_ERROR + nullptr, interface.cc:158-160
         return None

@@ -274,3 +274,37 @@ def average_transforms(transforms):
     f.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]
     rc = f(_d(ts.ravel()), len(transforms), _d(out))
     return rc, out.reshape(4, 4).T.copy()
+
+
+# ---- IcpUsingPointMatcher stand-in (type 1): composition of the pieces above ---------------------
+def pm_keep_mask(n, prob=0.9, seed=1):
+    """The engine's reading filter: counter hash of the point index (murmur3 finaliser) below
+    prob * 2^32 (staticmapping_b200/csrc/sm_api.cu pm_keep)."""
+    p = float(np.float32(prob))
+    if p >= 1.0:
+        return np.ones(n, dtype=bool)
+    thresh = np.uint32(0) if p <= 0.0 else np.uint32(int(p * 4294967296.0))
+    with np.errstate(over="ignore"):
+        x = np.arange(n, dtype=np.uint32) * np.uint32(0x9E3779B9) + np.uint32(seed)
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x85EBCA6B)
+        x ^= x >> np.uint32(13)
+        x *= np.uint32(0xC2B2AE35)
+        x ^= x >> np.uint32(16)
+    return x < thresh
+
+
+def icp_pm_equivalent(source_f32, target_f32, guess=None, prob=0.9, seed=1, max_iteration=150,
+                      accept_min_score=0.6):
+    """Reference-side chain of icp_pointmatcher.cc:166-247 restated with the oracle's pieces:
+    CalculateNormals on the target (SamplingSurfaceNormal knn 7), hash subsample of the reading,
+    IcpFast::Align capped at 150 iterations, Align() false below score 0.6."""
+    src = np.asarray(source_f32, dtype=np.float32)
+    tgt = np.asarray(target_f32, dtype=np.float32)
+    tp, tn = calculate_normals(tgt.astype(np.float64))
+    keep = pm_keep_mask(src.shape[0], prob, seed)
+    o = icp_fast_align(src[keep].astype(np.float64), tp, tn, guess, max_iteration=max_iteration)
+    o["ok"] = o["score"] >= float(np.float32(accept_min_score))
+    o["n_source"] = int(keep.sum())
+    o["n_target"] = int(tp.shape[0])
+    return o

@@ -34,7 +34,7 @@ struct EigenPointCloud {
   bool HasNormals() const { return true; }
 };
 struct InnerPointType { float x, y, z, intensity, factor; };
-struct InnerCloudType { std::vector<InnerPointType> points; };
+struct InnerCloudType { long long stamp = 0; std::vector<InnerPointType> points; };   // stamp: SimpleTime in the reference
 struct InnerPointCloudData {
   using Ptr = std::shared_ptr<InnerPointCloudData>;
   std::shared_ptr<EigenPointCloud> GetEigenCloud() const { return nullptr; }
