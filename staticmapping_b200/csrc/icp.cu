@@ -195,6 +195,33 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
   }
 }
 
+// Diagnostics (sm_debug_knn_profile): the phase-A search with per-thread clocks.
+__global__ void __launch_bounds__(kKnnThreads)
+icp_knn_profile_kernel(IcpBuffers b, IcpParams p, int identity, uint32_t* __restrict__ cycles,
+                       uint8_t* __restrict__ rounds_out, uint8_t* __restrict__ smid_out,
+                       unsigned long long* __restrict__ t0_out, unsigned long long* __restrict__ t1_out) {
+  __shared__ double T[16];
+  if (threadIdx.x < 16) T[threadIdx.x] = identity ? ((threadIdx.x % 5 == 0) ? 1.0 : 0.0) : b.state->T_iter[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
+  if (i >= p.n_source) return;
+  unsigned long long g0, g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+  const long long c0 = clock64();
+  double px, py, pz;
+  transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+  int slot, rounds = 0; double d2;
+  knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2, 1 << 30, &rounds);
+  const long long c1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+  uint32_t sm;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+  cycles[i] = (uint32_t)(c1 - c0) + (slot < 0 ? 0u : 0u) + (d2 < 0.0 ? 1u : 0u);
+  rounds_out[i] = (uint8_t)min(rounds, 255);
+  smid_out[i] = (uint8_t)sm;
+  t0_out[i] = g0; t1_out[i] = g1;
+}
+
 // -------------------------------------------------------------------------------- phase B
 __global__ void __launch_bounds__(kAccThreads)
 icp_accum_kernel(IcpBuffers b, IcpParams p) {
@@ -377,6 +404,14 @@ int icp_enqueue_iterations(const IcpBuffers& b_in, const IcpParams& p, int start
     }
     if (events) cudaEventRecord(events[4 * it + 3], stream);
   }
+  SMB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int icp_knn_profile(const IcpBuffers& b, const IcpParams& p, int identity, uint32_t* cycles, uint8_t* rounds,
+                    uint8_t* smid, unsigned long long* t0, unsigned long long* t1, cudaStream_t stream) {
+  icp_knn_profile_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(b, p, identity, cycles, rounds,
+                                                                                       smid, t0, t1);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

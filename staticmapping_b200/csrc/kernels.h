@@ -117,6 +117,9 @@ int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query,
               int nq, double max_error2, int tree_levels, int32_t* ids, double* d2,
               cudaStream_t stream);
 int knn_configure();
+// diagnostics: phase-A search with per-thread clocks (device output arrays of n_source entries)
+int icp_knn_profile(const IcpBuffers& b, const IcpParams& p, int identity, uint32_t* cycles, uint8_t* rounds,
+                    uint8_t* smid, unsigned long long* t0, unsigned long long* t1, cudaStream_t stream);
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);

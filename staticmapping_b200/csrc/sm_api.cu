@@ -1085,6 +1085,31 @@ int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
 
 const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
 
+// Diagnostics, not part of include/sm_b200.h: re-run the phase-A search of the last IcpFast Align
+// with per-thread clocks (profiles/knn_profile.py).  Host arrays of n_source entries each.
+int sm_debug_knn_profile(sm_handle* h, int identity, uint32_t* cycles, uint8_t* rounds, uint8_t* smid,
+                         unsigned long long* t0_ns, unsigned long long* t1_ns) {
+  if (!h || !cycles || !rounds || !smid || !t0_ns || !t1_ns || h->run.p.n_source <= 0) return SM_ERR_BAD_ARGUMENT;
+  H_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->run.p.n_source;
+  DevBuf d;
+  H_RC(d.reserve(n * (4 + 1 + 1 + 8 + 8) + 256));
+  unsigned long long* t0 = (unsigned long long*)d.p;
+  unsigned long long* t1 = t0 + n;
+  uint32_t* cyc = (uint32_t*)(t1 + n);
+  uint8_t* rd = (uint8_t*)(cyc + n);
+  uint8_t* sm = rd + n;
+  int rc = icp_knn_profile(h->run.b, h->run.p, identity, cyc, rd, sm, t0, t1, h->stream);
+  if (rc == 0 && (cudaMemcpyAsync(cycles, cyc, n * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaMemcpyAsync(rounds, rd, n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaMemcpyAsync(smid, sm, n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaMemcpyAsync(t0_ns, t0, n * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaMemcpyAsync(t1_ns, t1, n * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = SM_ERR_CUDA;
+  d.release();
+  return rc;
+}
+
 // Diagnostics, not part of include/sm_b200.h: clock64 stamps of the sections of the last
 // icp_finish_kernel of the last IcpFast Align (profiles/finish_sections.py).
 int sm_debug_icp_stamps(const sm_handle* h, long long* out12) {
