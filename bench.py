@@ -190,7 +190,10 @@ class Worker:
         self.nt = self.tp.shape[0]
         self.stream = torch.cuda.Stream(device=dev)
         self.m = smb.IcpFast(local_rank)
-        self.m.InitWithXml({"max_iteration": ITERATIONS, "disable_convergence_check": 1})
+        opts = {"max_iteration": ITERATIONS, "disable_convergence_check": 1}
+        if os.environ.get("SM_B200_KNN_REFILL") is not None:      # A/B switch for profiles/ (default: on)
+            opts["knn_refill"] = os.environ["SM_B200_KNN_REFILL"]
+        self.m.InitWithXml(opts)
         self.m.SetStream(self.stream.cuda_stream)
         self.d_src = torch.from_numpy(self.src).to(dev)
         self.d_tp = torch.from_numpy(self.tp).to(dev)

@@ -84,8 +84,9 @@ __global__ void fill_buckets_kernel(const double* __restrict__ coord, int64_t cs
 
 // one block: G0 = T_mean^-1 * guess, state reset, histogram clear (icp_fast.cc:460-480)
 __global__ void icp_init_kernel(IcpState* __restrict__ st, const double* __restrict__ guess,
-                                uint32_t* __restrict__ hist) {
-  for (int i = threadIdx.x; i < 2 * kHistBins; i += blockDim.x) hist[i] = 0;  // hist + hist2
+                                uint32_t* __restrict__ hist, uint32_t* __restrict__ claim, int nchunks) {
+  for (int i = threadIdx.x; i < 2 * kHistBins + 2; i += blockDim.x) hist[i] = 0;  // hist + hist2 + steal cursor + started blocks
+  for (int i = threadIdx.x; i < nchunks; i += blockDim.x) claim[i] = 0;            // stamps start at 1
   if (threadIdx.x != 0) return;
   double Tm[16], Tmi[16];
   for (int i = 0; i < 16; ++i) { Tm[i] = (i % 5 == 0) ? 1.0 : 0.0; Tmi[i] = Tm[i]; }
@@ -151,7 +152,7 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 
 // -------------------------------------------------------------------------------- phase A
 __global__ void __launch_bounds__(kKnnThreads)
-icp_knn_kernel(IcpBuffers b, IcpParams p) {
+icp_knn_static_kernel(IcpBuffers b, IcpParams p) {
   __shared__ double T[16];
   if (b.state->done) return;
   // measured: keeping the first 4 pending subtrees per thread in shared memory is SLOWER
@@ -192,6 +193,148 @@ icp_knn_kernel(IcpBuffers b, IcpParams p) {
     // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident);
     // no block-level staging, so a warp retires as soon as its own queries are done
     if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
+  }
+}
+
+// Phase A with work sharing.  The search of one query is the same sequence of passes as in knn1 /
+// visit_subtree (pass 0: read-only descent + first bucket; then one pass per far visit), but a
+// lane whose query is finished does not idle until the slowest lane of its warp is done: the warp
+// claims further 32-query chunks (Morton-consecutive, so still coherent) and hands their queries
+// to lanes as they become free.  Chunk c belongs to warp c ("home"); a warp claims its home chunk
+// with one atomicExch on the chunk's own stamp (no shared address), and steals from the END of
+// the chunk list through a cursor.  With one alignment in flight every warp is resident at once,
+// claims its home chunk and finds nothing to steal: the kernel behaves like the static one.  With
+// many alignments in flight the warps of late blocks start late, early warps take over their
+// chunks, late blocks find them claimed and retire at once: lanes stay busy and a warp slot is
+// released as soon as the work runs out (profiles/knn_profile.py: 14 of 32 lanes are active on
+// average in the static kernel).
+// MEASURED: slower than the static kernel in both regimes — 2.26 vs 1.87 ms
+// of k-NN per alignment with one in flight (58 vs 40 registers, the claim round trips, the
+// per-pass ballots) and 777 vs 1050 alignments/s with 16 in flight (lanes of one warp end up in
+// distant tree regions, every pass waits for more distinct lines).  Option knn_refill, default off.
+// Results do not depend on who runs a query: each query's search is self-contained.
+constexpr int kRefillMin = 8;   // free lanes before a warp looks for more work
+
+__global__ void __launch_bounds__(kKnnThreads)
+icp_knn_kernel(IcpBuffers b, IcpParams p) {
+  __shared__ double T[16];
+  if (b.state->done) return;
+  if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
+  const uint32_t stamp = (uint32_t)b.state->iteration + 1u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int n = p.n_source;
+  const int nchunks = (n + 31) >> 5;
+  const int home = (blockIdx.x * kKnnThreads + threadIdx.x) >> 5;
+  uint32_t* cursor = b.hist + 2 * kHistBins;
+  uint32_t* started = cursor + 1;        // blocks of this launch that have begun
+  if (threadIdx.x == 0) atomicAdd(started, 1u);
+  const KdNode* __restrict__ nodes = b.nodes;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  const double me2 = p.max_error2;
+  // the warp's window of claimed, not yet started queries (warp-uniform)
+  int win_next = 0, win_end = 0;
+  bool tried_home = false, exhausted = false;
+  // per-lane search state
+  bool active = false;
+  int qi = 0, phase = 0, best = -1, idx = 0, sp = 0, rounds = 0;
+  double qx = 0, qy = 0, qz = 0, head = inf, rd = 0, ox = 0, oy = 0, oz = 0, min_rd = inf;
+  StackEntry stack[kMaxStack];
+  while (true) {
+    // ---- hand queries to free lanes --------------------------------------------------------
+    uint32_t freem = __ballot_sync(0xffffffffu, !active);
+    while (freem != 0u) {
+      if (win_next >= win_end) {
+        if (exhausted || (__popc(freem) < kRefillMin && freem != 0xffffffffu)) break;
+        int c = -1;
+        if (lane == 0) {
+          if (!tried_home && home < nchunks && atomicExch(&b.knn_claim[home], stamp) != stamp) {
+            c = home;
+          } else {
+            // steal from the end of the list, but never from a block that has already started: its
+            // own warps are claiming those chunks (with one alignment in flight every block has
+            // started and this ends after one look)
+            while (true) {
+              const uint32_t k = atomicAdd(cursor, 1u);
+              const int cand = nchunks - 1 - (int)k;
+              const int s = (int)*reinterpret_cast<volatile uint32_t*>(started);
+              if (cand < 0 || cand < s * (kKnnThreads / 32)) { c = -2; break; }
+              if (atomicExch(&b.knn_claim[cand], stamp) != stamp) { c = cand; break; }
+            }
+          }
+        }
+        tried_home = true;
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c < 0) { exhausted = true; break; }
+        win_next = c << 5;
+        win_end = min(win_next + 32, n);
+      }
+      const int avail = win_end - win_next;
+      const int rank = __popc(freem & lt);
+      if (!active && rank < avail) {
+        qi = win_next + rank;
+        transform_point(T, b.src0[qi], b.src0[b.sstride + qi], b.src0[2 * b.sstride + qi], qx, qy, qz);
+        active = true; phase = 0; best = -1; idx = 0; sp = 0; rounds = 0;
+        head = inf; rd = 0.0; ox = 0.0; oy = 0.0; oz = 0.0; min_rd = inf;
+      }
+      win_next += min(__popc(freem), avail);
+      freem = __ballot_sync(0xffffffffu, !active);
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+    // ---- one pass: descend to a bucket, scan it, pick the next pending subtree ---------------
+    if (active) {
+      KdNode nd = load_node(nodes, idx);
+      int guard = 0;
+      while (nd.dim != 3 && ++guard < 64) {
+        const int cd = nd.dim;
+        const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+        const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+        const int right = q > nd.cut ? 1 : 0;
+        const int next = child_idx(idx, right);
+        const KdNode nd_next = load_node(nodes, next);
+        const double new_off = dsub(q, nd.cut);
+        const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+        if (phase == 0) {
+          min_rd = fmin(min_rd, rd_new);     // == new_off^2 on the first descent (rd = 0, offsets 0)
+        } else if (dmul(rd_new, me2) < head && sp < kMaxStack) {
+          StackEntry e;
+          e.rd = rd_new;
+          e.ox = cd == 0 ? new_off : ox;
+          e.oy = cd == 1 ? new_off : oy;
+          e.oz = cd == 2 ? new_off : oz;
+          e.idx = child_idx(idx, 1 - right);
+          stack[sp++] = e;
+        }
+        idx = next;
+        nd = nd_next;
+      }
+      if (nd.dim == 3) scan_leaf(b.bpts, nd, qx, qy, qz, head, best);
+      bool fin;
+      if (phase == 0) {
+        // no far subtree can qualify if even the closest cut plane fails the test (see knn1)
+        fin = !(dmul(min_rd, me2) < head);
+        phase = 1; idx = 0; rd = 0.0; ox = 0.0; oy = 0.0; oz = 0.0; sp = 0;   // else: replay from the root
+      } else {
+        ++rounds;
+        fin = true;
+        while (sp > 0) {
+          const StackEntry e = stack[--sp];
+          if (dmul(e.rd, me2) < head) {
+            idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+            fin = false;
+            break;
+          }
+        }
+      }
+      if (fin) {
+        b.slot[qi] = best;
+        b.d2[qi] = head;
+        if (b.visits) b.visits[qi] = (uint8_t)min(rounds, 255);
+        if (finite_d2(head)) atomicAdd(&b.hist[dist_bin(head)], 1u);
+        active = false;
+      }
+    }
   }
 }
 
@@ -359,7 +502,7 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   if (rc) return rc;
   rc = kd_fill_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, b.bpts, b.bnrm, stream);
   if (rc) return rc;
-  icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist);
+  icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist, b.knn_claim, ceil_div(p.n_source, 32));
   apply_g0_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_raw, b.src_g0, b.sstride, ns, b.state,
                                                         b.src_keys[0], b.src_vals[0]);
   rc = radix_sort_pairs_u64(b.src_keys[0], b.src_vals[0], b.src_keys[1], b.src_vals[1], ns, 1,
@@ -389,7 +532,10 @@ int icp_enqueue_iterations(const IcpBuffers& b_in, const IcpParams& p, int start
     const int global_it = start_iteration + it;
     const IcpBuffers& bb = (resort && global_it >= 1) ? b_sorted : b;
     if (events) cudaEventRecord(events[4 * it + 0], stream);
-    icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
+    if (p.knn_refill && p.debug_knn_mode == 0)
+      icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
+    else
+      icp_knn_static_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
     if (events) cudaEventRecord(events[4 * it + 1], stream);
     icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(bb, p);
     if (events) cudaEventRecord(events[4 * it + 2], stream);

@@ -68,6 +68,7 @@ struct IcpParams {
   int tree_levels;         // kd_num_levels(n_target, 8): depth of the root-to-leaf path
   int resort_by_visits;    // re-order the queries by their iteration-0 bucket count
   int debug_knn_mode;      // 0 = normal; 1..3 = truncated k-NN kernel variants (profiling aid only)
+  int knn_refill;          // phase A: lanes that finish their query take the next unclaimed one (default 0: measured slower)
 };
 
 struct IcpBuffers {
@@ -93,6 +94,8 @@ struct IcpBuffers {
   uint8_t* visits;        // [n_source] buckets visited by the query in iteration 0 (or null)
   int32_t* slot;          // [n_source] bucket slot of the match
   double* d2;             // [n_source]
+  uint32_t* knn_claim;    // [ceil(n_source / 32)] claim stamp of every 32-query chunk (phase A work sharing);
+                          // the steal cursor is hist[2 * kHistBins], cleared with the histograms
   uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
   uint32_t* hist2;        // [kHistBins] second-level histogram inside the quantile bin (phase B)
   double* sums;           // [32] reduced normal-equation sums of the iteration (phase C1 -> C2)

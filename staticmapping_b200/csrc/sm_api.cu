@@ -103,6 +103,8 @@ struct IcpOptions {
   int32_t debug_knn_mode = 0;
   bool resort_by_visits = false;   // measured slower (2.19 vs 2.00 ms): spatial coherence matters more
   // type 1 (IcpUsingPointMatcher stand-in) only, icp_pointmatcher.cc:166-247
+  bool knn_refill = false;         // phase A work sharing (icp.cu icp_knn_kernel): measured SLOWER (777 vs 1050
+                                   // alignments/s, 2.26 vs 1.87 ms k-NN per alignment); kept as an option
   float reading_sample_prob = 0.9f;      // RandomSamplingDataPointsFilter prob (:173)
   float accept_min_score = 0.6f;         // Align returns false below it (:145)
   int32_t sample_seed = 1;
@@ -174,6 +176,7 @@ const OptionDef kIcpOptions[] = {
     {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
     {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
     {"resort_by_visits", kOptBool, offsetof(IcpOptions, resort_by_visits)},
+    {"knn_refill", kOptBool, offsetof(IcpOptions, knn_refill)},
     {"reading_sample_prob", kOptFloat, offsetof(IcpOptions, reading_sample_prob)},
     {"accept_min_score", kOptFloat, offsetof(IcpOptions, accept_min_score)},
     {"sample_seed", kOptInt, offsetof(IcpOptions, sample_seed)},
@@ -343,7 +346,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
   H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + (size_t)ns + 64));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
-  H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
+  H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double) + ((size_t)ceil_div(ns, 32) + 8) * sizeof(uint32_t)));
   H_RC(h->cand_idx.reserve((size_t)nb * 512 * 8 * sizeof(double)));   // cand_terms
   H_RC(h->cand_key.reserve((size_t)nb * 512 * sizeof(unsigned long long)));
   H_RC(h->cand_cnt.reserve((size_t)nb * sizeof(uint32_t)));
@@ -369,6 +372,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.visits = (uint8_t*)((int32_t*)h->slot.p + ns); b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
+  b.knn_claim = (uint32_t*)(b.sums + 32);
   b.cand_terms = (double*)h->cand_idx.p;
   b.cand_key = (unsigned long long*)h->cand_key.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
   b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
@@ -381,6 +385,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   p.max_error2 = (1.0 + eps) * (1.0 + eps);
   p.disable_convergence = h->icp.disable_convergence_check ? 1 : 0;
   p.debug_knn_mode = h->icp.debug_knn_mode;
+  p.knn_refill = h->icp.knn_refill ? 1 : 0;
   p.tree_levels = levels;
   p.resort_by_visits = h->icp.resort_by_visits ? 1 : 0;
   if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large (tree deeper than 24 levels)");
