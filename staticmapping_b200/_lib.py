@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsm_b200.so")
+# SM_B200_LIB: A/B builds for profiles/ (same ABI); the product library is libsm_b200.so
+LIB_PATH = os.environ.get("SM_B200_LIB") or os.path.join(_HERE, "libsm_b200.so")
 
 
 class AlignInfo(C.Structure):

@@ -139,7 +139,8 @@ __device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
                                               const BucketPoint* __restrict__ bpts, double qx,
                                               double qy, double qz, double max_error2, int idx,
                                               double rd, double ox, double oy, double oz,
-                                              double& head, int& best, int max_rounds = 1 << 20) {
+                                              double& head, int& best, int max_rounds = 1 << 20,
+                                              bool first_bucket_scanned = false) {
   StackEntry stack[kMaxStack];
   int sp = 0, rounds = 0;
   while (max_rounds-- > 0) {
@@ -168,7 +169,7 @@ __device__ __forceinline__ int visit_subtree(const KdNode* __restrict__ nodes,
       idx = next;
       nd = nd_next;
     }
-    if (nd.dim == 3) scan_leaf(bpts, nd, qx, qy, qz, head, best);
+    if (nd.dim == 3 && !(first_bucket_scanned && rounds == 1)) scan_leaf(bpts, nd, qx, qy, qz, head, best);
     bool found = false;
     while (sp > 0) {
       const StackEntry e = stack[--sp];
@@ -212,7 +213,7 @@ __device__ __forceinline__ void knn1(const KdNode* __restrict__ nodes,
   // re-scanning the first bucket during the replay is harmless (strict '<' keeps the winner)
   int rounds = 0;
   if (dmul(min_off2, max_error2) < head)
-    rounds = visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds);
+    rounds = visit_subtree(nodes, bpts, qx, qy, qz, max_error2, 0, 0.0, 0.0, 0.0, 0.0, head, best, max_rounds, true);
   if (rounds_out) *rounds_out = rounds;
   best_slot = best;
   best_d2 = head;
