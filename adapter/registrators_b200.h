@@ -167,6 +167,23 @@ inline void MotionCompensationB200(const data::InnerCloudType& raw_cloud, const 
   CHECK_EQ(rc, 0) << "MotionCompensation: factor outside [0, 1] (common/math.h:201) or CUDA failure";
 }
 
+// pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) on the GPU:
+// the body of that member becomes
+//   this->FilterPrepare(cloud); registrator::VoxelGridFilterB200(*this->inner_cloud_, voxel_size_, cloud.get());
+// Output points come in ascending voxel order instead of unordered_map iteration order.
+inline void VoxelGridFilterB200(const data::InnerCloudType& input, float voxel_size,
+                                data::InnerCloudType* const output, int device = 0) {
+  CHECK(output);
+  output->points.resize(input.points.size());
+  int64_t m = 0;
+  if (!input.points.empty()) {
+    const int rc = sm_voxel_grid_filter(device, &input.points[0].x, static_cast<int64_t>(input.points.size()),
+                                        sizeof(data::InnerPointType), voxel_size, &output->points[0].x, &m);
+    CHECK_EQ(rc, 0) << "sm_voxel_grid_filter failed (" << rc << ")";
+  }
+  output->points.resize(m);
+}
+
 // EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368); call sites
 // map_builder.cc:286,389 and submap.cc:161.
 inline void CalculateNormalsB200(data::EigenPointCloud* cloud, int device = 0) {

@@ -177,6 +177,19 @@ int sm_motion_compensation_device(int device, const float* dev_points, int64_t n
                                   int64_t stride_bytes, const double* delta_4x4, float* dev_out,
                                   void* cuda_stream);
 
+/* pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78), the
+ * down-sampling Submap::InsertFrame applies before CalculateNormals (builder/submap.cc:144-161):
+ * one output point per occupied voxel, voxel index = lround(coordinate / voxel_size) per axis
+ * (:47-49), x / y / z / intensity = mean of the voxel's points accumulated in double in input
+ * order (:58-70), factor = 0.  `points`: data::InnerPointType records (x, y, z, intensity, ...)
+ * `stride_bytes` (>= 16) apart; `out`: capacity n records of 5 packed floats; *m_out = number of
+ * voxels.  Every value is bit-identical to the reference's; the ORDER of the output points is
+ * ascending (ix, iy, iz), where the reference emits them in std::unordered_map iteration order.
+ * SM_ERR_BAD_ARGUMENT: voxel_size <= 1e-6 (ConfigsValid, :35), a NaN/inf coordinate, or a voxel
+ * index beyond +-2^20. */
+int sm_voxel_grid_filter(int device, const float* points, int64_t n, int64_t stride_bytes,
+                         float voxel_size, float* out, int64_t* m_out);
+
 int sm_device_count(void);
 const char* sm_version(void);
 

@@ -153,3 +153,56 @@ int sm_oracle_average_transforms(const double* Ts, int32_t n, double* out) {
 }
 
 }  // extern "C"
+
+// ---- pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) --------
+// points / out: packed InnerPointType (x, y, z, intensity, factor).  order_mode 0: output voxels in
+// ascending (ix, iy, iz) (the order the CUDA path emits); order_mode 1: the literal iteration order
+// of std::unordered_map<Eigen::Vector3i, ...> with the reference's hash (common/eigen_hash.h:31-43)
+// as this toolchain's libstdc++ produces it.  Returns the number of voxels, -1 on a bad voxel size.
+#include <array>
+#include <cmath>
+#include <map>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+struct Key3 { int v[3]; bool operator==(const Key3& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2]; } };
+struct Key3Hash {   // common/eigen_hash.h:34-42 with std::hash<int> (identity)
+  size_t operator()(const Key3& k) const {
+    size_t seed = 0;
+    for (int i = 0; i < 3; ++i) seed ^= std::hash<int>()(k.v[i]) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+    return seed;
+  }
+};
+void AveragePoint(const std::vector<const float*>& pts, float* o) {   // filter_voxel_grid.cc:54-72
+  double sum[4] = {0, 0, 0, 0};
+  for (const float* p : pts) { sum[0] += p[0]; sum[1] += p[1]; sum[2] += p[2]; sum[3] += p[3]; }
+  const int size = (int)pts.size();
+  o[0] = (float)(sum[0] / size); o[1] = (float)(sum[1] / size); o[2] = (float)(sum[2] / size);
+  o[3] = (float)(sum[3] / size);
+  o[4] = 0.f;   // InnerPointType::factor default
+}
+}  // namespace
+
+extern "C" int64_t sm_oracle_voxel_grid_filter(const float* points, int64_t n, float voxel_size, int order_mode,
+                                                float* out) {
+  if (!(voxel_size > 1.e-6f)) return -1;   // ConfigsValid(), filter_voxel_grid.cc:35
+  int64_t m = 0;
+  auto key_of = [&](const float* p) {
+    return Key3{{(int)std::lround(p[0] / voxel_size), (int)std::lround(p[1] / voxel_size),
+                 (int)std::lround(p[2] / voxel_size)}};
+  };
+  if (order_mode == 1) {
+    std::unordered_map<Key3, std::vector<const float*>, Key3Hash> grid;
+    for (int64_t i = 0; i < n; ++i) grid[key_of(points + 5 * i)].push_back(points + 5 * i);
+    for (const auto& g : grid) AveragePoint(g.second, out + 5 * (m++));
+  } else {
+    std::map<std::array<int, 3>, std::vector<const float*>> grid;
+    for (int64_t i = 0; i < n; ++i) {
+      const Key3 k = key_of(points + 5 * i);
+      grid[{k.v[0], k.v[1], k.v[2]}].push_back(points + 5 * i);
+    }
+    for (const auto& g : grid) AveragePoint(g.second, out + 5 * (m++));
+  }
+  return m;
+}

@@ -126,6 +126,12 @@ int sm_oracle_motion_compensation(const float* points, int64_t n, const double* 
 /* common::AverageTransforms (common/math.cc:177-195). */
 int sm_oracle_average_transforms(const double* Ts, int32_t n, double* out);
 
+/* pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78); packed
+ * InnerPointType in/out; order_mode 0 = ascending (ix, iy, iz), 1 = the reference's literal
+ * std::unordered_map iteration order.  Returns the number of voxels. */
+int64_t sm_oracle_voxel_grid_filter(const float* points, int64_t n, float voxel_size, int order_mode,
+                                    float* out);
+
 /* Pieces exposed for unit tests of the restatement itself. */
 int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
 int sm_oracle_quantile_index(int64_t n, float ratio);

@@ -45,6 +45,64 @@ def main():
             D = np.linalg.inv(o["result"]) @ res
             out[name]["parity_dt_m"] = float(np.linalg.norm(D[:3, 3]))
             out[name]["oracle_threads"] = O.num_threads()
+    # ---- section 8(f) rows: type-1 matcher (rank 2) and motion compensation (rank 3) ------------
+    m = smb.IcpUsingPointMatcher()
+    m.SetInputSource(smb.InnerCloud(s32))
+    m.SetInputTarget(smb.InnerCloud(t32))
+    t0 = time.perf_counter()
+    ok, res = m.Align(np.eye(4))                       # includes both data filters (CalculateNormals on 500 k)
+    first = time.perf_counter() - t0
+    walls = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ok, res = m.Align(np.eye(4))                   # filtered clouds cached
+        walls.append(time.perf_counter() - t0)
+    info = m.GetAlignInfo()
+    E = np.linalg.inv(P) @ res
+    out["icp_pm"] = {"ok": bool(ok), "first_align_ms": 1e3 * first, "repeat_align_ms": 1e3 * float(np.median(walls)),
+                     "iterations": info["iterations"], "score": m.GetFitnessScore(),
+                     "n_source_filtered": info["aux"][2], "n_target_filtered": info["aux"][3],
+                     "err_vs_truth_m": float(np.linalg.norm(E[:3, 3]))}
+    if with_oracle:
+        import oracle_lib as O
+        t0 = time.perf_counter()
+        o = O.icp_pm_equivalent(s32, t32)
+        out["icp_pm"]["oracle_s"] = time.perf_counter() - t0
+        out["icp_pm"]["parity_dt_m"] = float(np.linalg.norm((np.linalg.inv(o["result"]) @ res)[:3, 3]))
+    raw = np.zeros((s32.shape[0], 5), np.float32)
+    raw[:, :3] = s32
+    raw[:, 4] = np.arange(s32.shape[0], dtype=np.float32) / (s32.shape[0] - 1)
+    smb.MotionCompensation(raw, P)
+    walls = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        comp = smb.MotionCompensation(raw, P)
+        walls.append(time.perf_counter() - t0)
+    out["motion_compensation"] = {"points": int(raw.shape[0]), "host_buffers_ms": 1e3 * float(np.median(walls))}
+    if with_oracle:
+        import oracle_lib as O
+        t0 = time.perf_counter()
+        rc, want = O.motion_compensation(raw, P)
+        out["motion_compensation"]["oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["motion_compensation"]["max_abs_diff_m"] = float(np.max(np.abs(comp[:, :3] - want[:, :3])))
+    # ---- section 8(f) rank 4 (first half): submap voxel filter at the 500 k-point submap ----------
+    sub5 = np.zeros((t32.shape[0], 5), np.float32)
+    sub5[:, :3] = t32
+    smb.VoxelGridFilter(sub5, 0.1)
+    walls = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        vf = smb.VoxelGridFilter(sub5, 0.1)
+        walls.append(time.perf_counter() - t0)
+    out["voxel_grid_filter"] = {"points": int(sub5.shape[0]), "voxel_size": 0.1, "voxels": int(vf.shape[0]),
+                                "host_buffers_ms": 1e3 * float(np.median(walls))}
+    if with_oracle:
+        import oracle_lib as O
+        t0 = time.perf_counter()
+        mm, want = O.voxel_grid_filter(sub5, 0.1, order_mode=1)      # the reference's own unordered_map walk
+        out["voxel_grid_filter"]["oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+        mm0, want0 = O.voxel_grid_filter(sub5, 0.1)
+        out["voxel_grid_filter"]["bit_exact"] = bool(mm0 == vf.shape[0] and np.array_equal(vf.view(np.uint32), want0.view(np.uint32)))
     print(json.dumps(out))
 
 

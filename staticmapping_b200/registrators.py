@@ -445,3 +445,24 @@ def AverageTransforms(transforms):
                    [txz - twy, tyz + twx, 1.0 - (txx + tyy)]]
     out[:3, 3] = tr
     return out
+
+
+def VoxelGridFilter(cloud, voxel_size, device=0):
+    """pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) on
+    the GPU.  `cloud`: (N,5) float32 InnerPointType rows; returns the (M,5) voxel means in
+    ascending (ix, iy, iz) order (the reference's order is std::unordered_map iteration order)."""
+    lib = _lib.lib()
+    pts = np.ascontiguousarray(np.asarray(cloud, dtype=np.float32))
+    if pts.ndim != 2 or pts.shape[1] != 5:
+        raise ValueError("cloud must be (N,5): x, y, z, intensity, factor")
+    out = np.empty_like(pts)
+    m = C.c_int64(0)
+    rc = lib.sm_voxel_grid_filter(device, pts.ctypes.data, pts.shape[0], 20, float(voxel_size), out.ctypes.data,
+                                  C.byref(m))
+    if rc == -20:
+        raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
+    if rc == -1:
+        raise CheckFailure("VoxelGrid: invalid voxel_size (ConfigsValid) or a coordinate outside the voxel index range")
+    if rc != 0:
+        raise RuntimeError(f"sm_voxel_grid_filter failed with {rc}")
+    return out[:m.value].copy()

@@ -1,0 +1,55 @@
+"""GPU parity of VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) against the oracle:
+bit-identical voxel means, in the engine's ascending-voxel order."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scenes
+import staticmapping_b200 as smb
+
+pytestmark = pytest.mark.gpu
+
+
+def as5(xyz, seed=0):
+    rng = np.random.default_rng(seed)
+    p = np.zeros((xyz.shape[0], 5), np.float32)
+    p[:, :3] = xyz
+    p[:, 3] = rng.uniform(0, 255, xyz.shape[0])
+    p[:, 4] = rng.uniform(0, 1, xyz.shape[0])
+    return p
+
+
+@pytest.mark.parametrize("voxel", [0.1, 0.2, 1.0])
+def test_submap_bit_exact(voxel):
+    _, sub, _ = scenes.lidar_pair(pair=1)          # 60 k-point submap of the synthetic scene
+    pts = as5(sub.astype(np.float32), seed=1)
+    m, want = O.voxel_grid_filter(pts, voxel)
+    got = smb.VoxelGridFilter(pts, voxel)
+    assert got.shape == (m, 5)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))      # bit for bit
+
+
+def test_full_size_dense_voxels_and_ties():
+    rng = np.random.default_rng(9)
+    n = 500_000
+    xyz = rng.uniform(-4, 4, (n, 3)).astype(np.float32)                   # ~1000 points per 0.8 m voxel
+    xyz[:1000, 0] = np.float32(0.4)                                       # exactly on a voxel boundary (x / 0.8 = 0.5)
+    xyz[1000:2000, 0] = np.float32(-0.4)
+    pts = as5(xyz, seed=2)
+    m, want = O.voxel_grid_filter(pts, 0.8)
+    got = smb.VoxelGridFilter(pts, 0.8)
+    assert got.shape[0] == m and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_edge_cases():
+    one = np.array([[1.0, -2.0, 3.0, 7.0, 0.9]], np.float32)
+    assert np.array_equal(smb.VoxelGridFilter(one, 0.5), np.array([[1.0, -2.0, 3.0, 7.0, 0.0]], np.float32))
+    assert smb.VoxelGridFilter(np.zeros((0, 5), np.float32), 0.5).shape == (0, 5)
+    with pytest.raises(smb.CheckFailure):
+        smb.VoxelGridFilter(one, 0.0)                                     # ConfigsValid
+    bad = one.copy(); bad[0, 1] = np.nan
+    with pytest.raises(smb.CheckFailure):
+        smb.VoxelGridFilter(bad, 0.5)
+    same = np.tile(one, (5000, 1))                                        # everything in one voxel
+    out = smb.VoxelGridFilter(same, 0.5)
+    assert out.shape == (1, 5) and np.array_equal(out[0, :4], one[0, :4])
