@@ -123,7 +123,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def oracle_module():
+    """The CPU arm runs on all PHYSICAL cores: one OpenMP thread per SMT sibling was measured 3.6x
+    slower on the 64-core / 128-thread box (0.51 vs 1.85 alignments/s), so unless the caller set
+    OMP_NUM_THREADS the thread count is pinned before libgomp starts (both CPU legs, same rule)."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(physical_cores()))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     return oracle_lib
