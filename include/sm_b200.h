@@ -129,7 +129,10 @@ typedef struct sm_align_info {
   int32_t evaluations;        /* computeDerivatives calls (ndt_omp_impl.hpp:180) */
   double trans_probability;   /* score / N_source (ndt_omp_impl.hpp:170) */
   double mean_neighbors;      /* mean number of neighbour voxels per source point */
-  /* NdtWithGicp only: [0] NDT fitness (the <= 1.0 gate, ndt_gicp.cc:92), [1] GICP fitness,
+  /* IcpUsingPointMatcher stand-in (type 1): [0] IcpFast's own score of the last iteration,
+   * [1] matches kept by the trim in the final score pass, [2] reading / [3] reference points after
+   * the data filters.
+   * NdtWithGicp only: [0] NDT fitness (the <= 1.0 gate, ndt_gicp.cc:92), [1] GICP fitness,
    * [2] source points after ApproximateVoxelGrid, [3] target points after it;
    * iterations = GICP outer iterations, profiled_iterations = BFGS cost evaluations */
   double aux[4];

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "icp_dev.cuh"
 #include "kernels.h"
 #include "gicp_host.h"
 #include "ndt_host.h"
@@ -89,6 +90,62 @@ pm_sample_scatter_kernel(const float* __restrict__ pts, int n, uint32_t seed, ui
   }
 }
 
+// ---- score of the IcpUsingPointMatcher stand-in (icp_pointmatcher.cc:131-148): the UNFILTERED
+// reading cloud moved by the result is matched against the UNFILTERED reference (same k-d tree
+// matcher, eps 3.16), trimmed at the 0.7 quantile, and the mean kept distance goes into exp(-x)
+__global__ void __launch_bounds__(256)
+pm_score_knn_kernel(const float* __restrict__ src, int n, const double* __restrict__ T, const KdNode* __restrict__ nodes,
+                    const BucketPoint* __restrict__ bpts, double max_error2, uint64_t* __restrict__ keys,
+                    uint32_t* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = (double)src[3 * (int64_t)i], y = (double)src[3 * (int64_t)i + 1], z = (double)src[3 * (int64_t)i + 2];
+  double px, py, pz;
+  dev::transform_point(T, x, y, z, px, py, pz);
+  int slot; double d2;
+  dev::knn1(nodes, bpts, px, py, pz, max_error2, slot, d2);
+  keys[i] = (uint64_t)__double_as_longlong(d2);     // non-negative doubles sort like their bit patterns; +inf = no match
+  vals[i] = (uint32_t)i;
+}
+
+// keys sorted ascending; out[0] = mean of sqrt(d2) over the kept matches, out[1] = kept, out[2] = valid
+__global__ void __launch_bounds__(1024)
+pm_score_reduce_kernel(const uint64_t* __restrict__ keys, int n, float ratio, double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ int s_kept, s_valid;
+  const uint64_t inf_bits = 0x7ff0000000000000ull;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n;                                // first index with key >= +inf
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < inf_bits) lo = mid + 1; else hi = mid; }
+    const int valid = lo;
+    int kept = 0;
+    if (valid > 0) {
+      const double q = (double)ratio;                  // GetDistsQuantile, as icp_fast.cc:82-89
+      int qi = (q == 1.0) ? valid - 1 : (int)((double)valid * q);
+      if (qi > valid - 1) qi = valid - 1;
+      const uint64_t limit = keys[qi];
+      lo = qi; hi = valid;                             // first index with key > limit
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] <= limit) lo = mid + 1; else hi = mid; }
+      kept = lo;
+    }
+    s_kept = kept; s_valid = valid;
+  }
+  __syncthreads();
+  const int kept = s_kept;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < kept; i += 1024) v += sqrt(__longlong_as_double((long long)keys[i]));
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    out[0] = kept > 0 ? t / (double)kept : 0.0;
+    out[1] = (double)kept;
+    out[2] = (double)s_valid;
+  }
+}
+
 enum OptKind { kOptInt, kOptFloat, kOptBool };
 struct OptionDef { const char* name; OptKind kind; size_t offset; };
 
@@ -161,6 +218,8 @@ struct sm_handle {
   // IcpUsingPointMatcher stand-in (type 1): raw float clouds -> filtered double clouds
   int64_t pm_n_src = 0, pm_n_tgt = 0;
   bool pm_src_dirty = false, pm_tgt_dirty = false;
+  bool pm_score_tree_dirty = true;
+  DevBuf pm_score_buf;
   DevBuf pm_coord, pm_nodes, pm_order, pm_kdws, pm_tmp_pts, pm_tmp_nrm, pm_keep, pm_bsum, pm_outp, pm_outn, pm_cnt, pm_src;
 };
 
@@ -297,6 +356,7 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
 int ndt_align(sm_handle* h, const double* guess, double* result);
 int ndt_gicp_align(sm_handle* h, const double* guess, double* result);
 int pm_align(sm_handle* h, const double* guess, double* result);
+int build_tree_f32(sm_handle* h, const float* pts, int n, DevBuf& soa, DevBuf& nodes, DevBuf& order, DevBuf& bpts);
 
 // one chunk of iterations + the asynchronous read-back of the state record
 int icp_enqueue_chunk(sm_handle* h) {
@@ -473,7 +533,8 @@ int icp_align(sm_handle* h, const double* guess, double* result) {
 //                     icp_fast.cc ported from exactly these modules (k-d tree eps 3.16, trim 0.7,
 //                     point-to-plane, 4-sample differential checker 0.001 rad / 0.01 m), here in
 //                     double, capped at 150 iterations
-//   Align()           false when exp(-mean kept distance) < 0.6 (:145)
+//   score (:131-148)  unfiltered reading moved by the result vs unfiltered reference, same matcher,
+//                     trim 0.7, exp(-mean kept distance); Align() false below 0.6 (:145)
 // It is a deterministic equivalent, not a bit-level restatement: libpointmatcher's float
 // arithmetic and its rand() stream cannot be pinned from this tree.
 int pm_align(sm_handle* h, const double* guess, double* result) {
@@ -533,6 +594,38 @@ int pm_align(sm_handle* h, const double* guess, double* result) {
   h->info.aux[2] = (double)h->n_source;   // reading points after the filter
   h->info.aux[3] = (double)h->n_target;   // reference points after the filter
   if (rc < 0) return rc;
+  h->info.aux[0] = h->final_score;        // IcpFast's own score (last iteration, filtered clouds)
+  // ---- "compute the final score" (icp_pointmatcher.cc:131-148) -------------------------------
+  {
+    const int ns = (int)h->pm_n_src, nt = (int)h->pm_n_tgt;
+    if (h->pm_score_tree_dirty) {
+      H_RC(build_tree_f32(h, (const float*)h->tgt_f32.p, nt, h->tgt_soa, h->nodes2, h->leaf_order2, h->bpts2));
+      h->pm_score_tree_dirty = false;
+    }
+    const int64_t st = pad64(ns);
+    const size_t scratch = radix_sort_scratch_bytes(ns, 1);
+    H_RC(h->pm_score_buf.reserve((size_t)st * 24 + scratch + 16 * sizeof(double) + 8 * sizeof(double) + 1024));
+    uint64_t* k0 = (uint64_t*)h->pm_score_buf.p;
+    uint64_t* k1 = k0 + st;
+    uint32_t* v0 = (uint32_t*)(k1 + st);
+    uint32_t* v1 = v0 + st;
+    uint32_t* scr = v1 + st;
+    double* Tdev = (double*)((char*)scr + ((scratch + 255) & ~(size_t)255));
+    double* outdev = Tdev + 16;
+    for (int i = 0; i < 16; ++i) h->host_guess[i] = result[i];      // pinned staging
+    H_CUDA(cudaMemcpyAsync(Tdev, h->host_guess, 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    const double eps = (double)h->icp.knn_epsilon;
+    pm_score_knn_kernel<<<ceil_div(ns, 256), 256, 0, s>>>((const float*)h->src_f32.p, ns, Tdev, (const KdNode*)h->nodes2.p,
+                                                       (const BucketPoint*)h->bpts2.p, (1.0 + eps) * (1.0 + eps), k0, v0);
+    H_RC(radix_sort_pairs_u64(k0, v0, k1, v1, ns, 1, st, scr, s, 8));
+    pm_score_reduce_kernel<<<1, 1024, 0, s>>>(k0, ns, h->icp.dist_outlier_ratio, outdev);
+    H_CUDA(cudaGetLastError());
+    H_CUDA(cudaMemcpyAsync(h->host_sums, outdev, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    H_CUDA(cudaStreamSynchronize(s));
+    if (!(h->host_sums[1] > 0.0)) return fail(h, SM_ERR_NOTHING_TO_MINIMIZE, "Align: no matched point for the score");
+    h->final_score = exp(-h->host_sums[0]);
+    h->info.aux[1] = h->host_sums[1];     // matches kept by the trim in the score pass
+  }
   return h->final_score < (double)h->icp.accept_min_score ? 0 : 1;
 }
 
@@ -948,7 +1041,7 @@ int sm_destroy(sm_handle* h) {
   for (int i = 0; i < 4; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
   h->src_f32.release(); h->tgt_f32.release(); h->ndt_ws.release(); h->tgt_soa.release();
   { DevBuf* gb[] = {&h->src_filt, &h->tgt_filt, &h->approx_ws, &h->src_soa, &h->nodes2, &h->leaf_order2, &h->bpts2, &h->cov_s, &h->cov_t, &h->maha, &h->match, &h->gicp_partials, &h->counter}; for (DevBuf* b : gb) b->release(); }
-  { DevBuf* pb[] = {&h->pm_coord, &h->pm_nodes, &h->pm_order, &h->pm_kdws, &h->pm_tmp_pts, &h->pm_tmp_nrm, &h->pm_keep, &h->pm_bsum, &h->pm_outp, &h->pm_outn, &h->pm_cnt, &h->pm_src}; for (DevBuf* b : pb) b->release(); }
+  { DevBuf* pb[] = {&h->pm_coord, &h->pm_nodes, &h->pm_order, &h->pm_kdws, &h->pm_tmp_pts, &h->pm_tmp_nrm, &h->pm_keep, &h->pm_bsum, &h->pm_outp, &h->pm_outn, &h->pm_cnt, &h->pm_src, &h->pm_score_buf}; for (DevBuf* b : pb) b->release(); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SM_OK;
@@ -1043,7 +1136,7 @@ int sm_set_input_source_f32(sm_handle* h, const float* xyz, int64_t n, int64_t s
 }
 int sm_set_input_target_f32(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, false, h->tgt_f32);
-  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; }
+  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; h->pm_score_tree_dirty = true; }
   return rc;
 }
 int sm_set_input_source_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
@@ -1053,7 +1146,7 @@ int sm_set_input_source_f32_device(sm_handle* h, const float* xyz, int64_t n, in
 }
 int sm_set_input_target_f32_device(sm_handle* h, const float* xyz, int64_t n, int64_t stride) {
   int rc = load_cloud_f32(h, xyz, n, stride, true, h->tgt_f32);
-  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; }
+  if (rc == 0) { h->n_target = n; h->has_target = true; h->pm_n_tgt = n; h->pm_tgt_dirty = true; h->pm_score_tree_dirty = true; }
   return rc;
 }
 

@@ -303,7 +303,8 @@ class IcpUsingPointMatcher(Ndt):
     chain as the reference's default config (:166-247): reading filter RandomSampling 0.9,
     reference filter SamplingSurfaceNormal knn 7 (== CalculateNormals), k-d tree matcher eps 3.16,
     TrimmedDist 0.7, point-to-plane minimiser, 150-iteration counter + 4-sample differential
-    checker; GetFitnessScore() = exp(-mean kept distance), Align() is False below 0.6 (:145).
+    checker; GetFitnessScore() = exp(-mean kept distance) of the UNFILTERED clouds re-matched after
+    the result (:131-148), Align() is False below 0.6 (:145).
     libpointmatcher itself (1.3.1, float, std::rand) is external to the reference tree, so this is
     a deterministic double-precision equivalent built from the IcpFast kernels, not a bit-level
     restatement.  It registers no XML option (the reference takes a YAML file name instead)."""

@@ -304,20 +304,23 @@ def icp_pm_equivalent(source_f32, target_f32, guess=None, prob=0.9, seed=1, max_
     tp, tn = calculate_normals(tgt.astype(np.float64))
     keep = pm_keep_mask(src.shape[0], prob, seed)
     o = icp_fast_align(src[keep].astype(np.float64), tp, tn, guess, max_iteration=max_iteration)
-    o["ok"] = o["score"] >= float(np.float32(accept_min_score))
+    o["icp_fast_score"] = o["score"]
     o["n_source"] = int(keep.sum())
     o["n_target"] = int(tp.shape[0])
+    # "compute the final score" (icp_pointmatcher.cc:131-148): UNFILTERED reading moved by the result,
+    # matched against the UNFILTERED reference (same matcher, eps 3.16), trimmed at 0.7
+    R = o["result"]
+    s64 = src.astype(np.float64)
+    moved = np.empty_like(s64)
+    for r in range(3):   # the engine's (and cloud_types.cc:288-296) accumulation order
+        moved[:, r] = ((R[r, 0] * s64[:, 0] + R[r, 1] * s64[:, 1]) + R[r, 2] * s64[:, 2]) + R[r, 3]
+    _, d2 = knn1(tgt.astype(np.float64), moved, epsilon=3.16)
+    v = np.sort(d2[np.isfinite(d2)])
+    if v.size:
+        q = float(np.float32(0.7))
+        qi = v.size - 1 if q == 1.0 else min(int(v.size * q), v.size - 1)
+        kept = v[v <= v[qi]]
+        o["score"] = float(np.exp(-(np.sqrt(kept).sum() / kept.size)))
+        o["score_kept"] = int(kept.size)
+    o["ok"] = o["score"] >= float(np.float32(accept_min_score))
     return o
-
-
-def voxel_grid_filter(points5, voxel_size, order_mode=0):
-    """pre_processers::filter::VoxelGrid::Filter; order_mode 1 = the reference's literal
-    unordered_map iteration order."""
-    p = np.ascontiguousarray(np.asarray(points5, dtype=np.float32))
-    assert p.ndim == 2 and p.shape[1] == 5
-    out = np.zeros_like(p)
-    f = lib().sm_oracle_voxel_grid_filter
-    f.restype = C.c_int64
-    f.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]
-    m = f(p.ctypes.data, p.shape[0], float(voxel_size), int(order_mode), out.ctypes.data)
-    return m, out[:max(m, 0)].copy()

@@ -31,7 +31,9 @@ def test_matches_oracle_chain(pair):
     assert info["iterations"] == o["iterations"]
     dt, dr = scenes.se3_error(o["result"], res)
     assert dt <= 1e-4 and dr <= 1e-4, (dt, dr)            # the parity bar; observed ~1e-13
-    assert abs(m.GetFitnessScore() - o["score"]) < 1e-9
+    assert abs(m.GetFitnessScore() - o["score"]) < 1e-9              # score of the unfiltered clouds after the result
+    assert abs(info["aux"][0] - o["icp_fast_score"]) < 1e-9 and int(info["aux"][1]) == o["score_kept"]
+    assert m.GetFitnessScore() > o["icp_fast_score"]                  # the raw reference is 5x denser than the filtered one
     gt_t, gt_r = scenes.se3_error(P, res)
     assert gt_t < 0.05 and gt_r < 0.01                      # and it actually registers the scan
 
