@@ -66,7 +66,11 @@ int sm_destroy(sm_handle* h);
  * registrator::Ndt registers NO option (ndt.cc:28-34) — the reference-facing mirrors reject
  * every <param> for type 5; the engine itself accepts the pclomp setters hard-coded by the
  * reference: resolution (1.0), step_size (0.1), outlier_ratio (0.55),
- * transformation_epsilon (0.1), max_iterations (35). */
+ * transformation_epsilon (0.1), max_iterations (35).
+ * SM_TYPE_ICP_PM (stand-in for IcpUsingPointMatcher's default libpointmatcher chain,
+ * icp_pointmatcher.cc:166-247; float clouds through the _f32 setters) registers no option in the
+ * reference either; the engine accepts the IcpFast names (max_iteration defaults to 150, :214)
+ * plus reading_sample_prob (0.9, :173), accept_min_score (0.6, :145) and sample_seed (1). */
 int sm_set_option(sm_handle* h, const char* name, const char* text);
 /* Interface::PrintOptions (interface.cc:115-137): writes "name -> value\n" lines. */
 int sm_print_options(sm_handle* h, char* buf, int64_t buf_len);
