@@ -170,12 +170,30 @@ kd_part_count_kernel(const uint32_t* __restrict__ lists, int64_t lstride, int n,
   if (threadIdx.x == 0) block_sum[d * nblk + blockIdx.x] = total;
 }
 
+// FUSED_SCAN: block_off holds the RAW per-tile counts of kd_part_count_kernel and every block scans
+// them itself (at most 256 tiles = 524 288 points), which saves one launch per tree level.
+template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(kPartThreads)
 kd_part_scatter_kernel(const uint32_t* __restrict__ lists, uint32_t* __restrict__ lists_out,
                        int64_t lstride, int n, int bucket, int L,
                        const uint8_t* __restrict__ flag, const uint32_t* __restrict__ gloc,
                        const uint32_t* __restrict__ block_off, int nblk) {
+  __shared__ uint32_t s_off[kPartThreads];
+  __shared__ uint32_t s_warp[kPartThreads / 32];
   const int d = blockIdx.y;
+  if (FUSED_SCAN) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t c = t < nblk ? block_off[d * nblk + t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (int ww = 0; ww < w; ++ww) wb += s_warp[ww];
+    s_off[t] = wb + incl - c;
+    __syncthreads();
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t* list = lists + d * lstride;
@@ -184,8 +202,10 @@ kd_part_scatter_kernel(const uint32_t* __restrict__ lists, uint32_t* __restrict_
   const bool inner = locate_pos(i, L, n, bucket, &j, &first, &count);
   int pos = i;
   if (inner) {
-    const uint32_t gi = gloc[d * lstride + i] + block_off[d * nblk + i / kPartTile];
-    const uint32_t gs = gloc[d * lstride + first] + block_off[d * nblk + first / kPartTile];
+    const uint32_t oi = FUSED_SCAN ? s_off[i / kPartTile] : block_off[d * nblk + i / kPartTile];
+    const uint32_t of = FUSED_SCAN ? s_off[first / kPartTile] : block_off[d * nblk + first / kPartTile];
+    const uint32_t gi = gloc[d * lstride + i] + oi;
+    const uint32_t gs = gloc[d * lstride + first] + of;
     const int rank_left = (int)(gi - gs);
     const int left = count - (count >> 1);
     pos = (flag[pid] == 0) ? first + rank_left : first + left + ((i - first) - rank_left);
@@ -293,9 +313,14 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
                                                         ws.level_dim, ws.flag);
     kd_part_count_kernel<<<dim3(nblk, 3), kPartThreads, 0, stream>>>(
         ws.lists[cur], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
-    radix_scan_kernel_launch(ws.scratch, nblk, 3, stream);
-    kd_part_scatter_kernel<<<dim3(ceil_div(n, kPartThreads), 3), kPartThreads, 0, stream>>>(
-        ws.lists[cur], ws.lists[cur ^ 1], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
+    if (nblk <= kPartThreads) {
+      kd_part_scatter_kernel<true><<<dim3(ceil_div(n, kPartThreads), 3), kPartThreads, 0, stream>>>(
+          ws.lists[cur], ws.lists[cur ^ 1], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
+    } else {
+      radix_scan_kernel_launch(ws.scratch, nblk, 3, stream);
+      kd_part_scatter_kernel<false><<<dim3(ceil_div(n, kPartThreads), 3), kPartThreads, 0, stream>>>(
+          ws.lists[cur], ws.lists[cur ^ 1], ls, n, bucket, L, ws.flag, ws.gloc, ws.scratch, nblk);
+    }
     cur ^= 1;
   }
   const int total = (1 << (levels + 1)) - 1;

@@ -16,6 +16,7 @@ constexpr int kThreads = 256;
 constexpr int kItems = 8;
 constexpr int kTile = kThreads * kItems;  // 2048
 constexpr int kWarps = kThreads / 32;
+constexpr int kFusedScanMaxTiles = 128;   // <= 262 144 keys: the scatter kernel scans the histograms itself
 
 __global__ void __launch_bounds__(kThreads)
 radix_hist_kernel(const uint64_t* __restrict__ keys, int n, int64_t stride, int shift,
@@ -72,6 +73,11 @@ radix_scan_kernel(uint32_t* __restrict__ data, int count) {
   }
 }
 
+// FUSED_SCAN: block_offs holds the RAW per-tile histograms [batch][digit][tile]; every block derives
+// its own offsets (row prefix up to its tile + totals of the lower digits), which saves the
+// separate one-block scan launch.  Worth it only while a histogram row is short (each block reads
+// 256 x nblk counters), i.e. for the ~100 k-point sorts of the ICP prologue.
+template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(kThreads)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
@@ -102,9 +108,25 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
     __syncwarp();
   }
   __syncthreads();
+  __shared__ uint32_t digit_base[kWarps];
   {  // exclusive scan across warps for digit = threadIdx.x, plus the global offset
     const int d = threadIdx.x;
-    uint32_t run = block_offs[((int64_t)b * 256 + d) * nblk + blockIdx.x];
+    uint32_t run;
+    if (FUSED_SCAN) {
+      const uint32_t* row = block_offs + ((int64_t)b * 256 + d) * nblk;
+      uint32_t before = 0, total = 0;
+      for (int t = 0; t < nblk; ++t) { const uint32_t c = row[t]; if (t < (int)blockIdx.x) before += c; total += c; }
+      uint32_t incl = total;                       // exclusive scan of the digit totals over the block
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      if (lane == 31) digit_base[w] = incl;
+      __syncthreads();
+      uint32_t wb = 0;
+      for (int ww = 0; ww < w; ++ww) wb += digit_base[ww];
+      run = wb + incl - total + before;
+    } else {
+      run = block_offs[((int64_t)b * 256 + d) * nblk + blockIdx.x];
+    }
 #pragma unroll
     for (int ww = 0; ww < kWarps; ++ww) {
       const uint32_t c = warp_hist[ww][d];
@@ -150,9 +172,12 @@ int radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, u
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * 8;
     radix_hist_kernel<<<grid, kThreads, 0, stream>>>(kin, n, stride, shift, scratch, nblk);
-    radix_scan_kernel<<<batch, 1024, 0, stream>>>(scratch, 256 * nblk);
-    radix_scatter_kernel<<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift,
-                                                        scratch, nblk);
+    if (nblk <= kFusedScanMaxTiles) {
+      radix_scatter_kernel<true><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk);
+    } else {
+      radix_scan_kernel<<<batch, 1024, 0, stream>>>(scratch, 256 * nblk);
+      radix_scatter_kernel<false><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk);
+    }
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
