@@ -324,3 +324,16 @@ def icp_pm_equivalent(source_f32, target_f32, guess=None, prob=0.9, seed=1, max_
         o["score_kept"] = int(kept.size)
     o["ok"] = o["score"] >= float(np.float32(accept_min_score))
     return o
+
+
+def voxel_grid_filter(points5, voxel_size, order_mode=0):
+    """pre_processers::filter::VoxelGrid::Filter; order_mode 1 = the reference's literal
+    unordered_map iteration order."""
+    p = np.ascontiguousarray(np.asarray(points5, dtype=np.float32))
+    assert p.ndim == 2 and p.shape[1] == 5
+    out = np.zeros_like(p)
+    f = lib().sm_oracle_voxel_grid_filter
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]
+    m = f(p.ctypes.data, p.shape[0], float(voxel_size), int(order_mode), out.ctypes.data)
+    return m, out[:max(m, 0)].copy()
