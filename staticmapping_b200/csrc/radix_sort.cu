@@ -73,16 +73,73 @@ radix_scan_kernel(uint32_t* __restrict__ data, int count) {
   }
 }
 
+// Large sorts (more than kFusedScanMaxTiles tiles): the 256 x nblk counters of a batch are scanned
+// by many blocks instead of one.  Each block scans one chunk of kScanChunk counters in place
+// (exclusive, relative to the chunk) and publishes the chunk total; the block that finishes last
+// (ticket counter) turns the chunk totals of every batch into exclusive chunk offsets.  The
+// scatter kernel adds chunk_off[entry / kScanChunk] to the counter it reads.
+constexpr int kScanChunk = 4096;   // counters per scan block: 1024 threads x 4
+
+__global__ void __launch_bounds__(1024)
+radix_scan_chunks_kernel(uint32_t* __restrict__ data, int count, int nchunks, uint32_t* __restrict__ chunk_tot,
+                         uint32_t* __restrict__ ticket) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ bool is_last;
+  const int b = blockIdx.y, c = blockIdx.x;
+  uint32_t* d = data + (int64_t)b * count;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i0 = c * kScanChunk + threadIdx.x * 4;
+  uint32_t v[4], s = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { v[r] = (i0 + r < count) ? d[i0 + r] : 0u; s += v[r]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const uint32_t x = warp_sums[lane];
+    uint32_t xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+    warp_sums[lane] = xi - x;
+    if (lane == 31) chunk_tot[b * nchunks + c] = xi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[w] + incl - s;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { if (i0 + r < count) d[i0 + r] = run; run += v[r]; }
+  // ---- last block: chunk totals -> exclusive chunk offsets, per batch --------------------------
+  __threadfence();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0;                 // ready for the next pass
+  for (int bb = w; bb < (int)gridDim.y; bb += 32) {  // one warp per batch; nchunks is small (<= 2^18 keys -> 32)
+    uint32_t carry = 0;
+    for (int base = 0; base < nchunks; base += 32) {
+      const int k = base + lane;
+      const uint32_t x = k < nchunks ? *reinterpret_cast<volatile uint32_t*>(chunk_tot + bb * nchunks + k) : 0u;
+      uint32_t xi = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+      if (k < nchunks) chunk_tot[bb * nchunks + k] = carry + xi - x;
+      carry += __shfl_sync(0xffffffffu, xi, 31);
+    }
+  }
+}
+
 // FUSED_SCAN: block_offs holds the RAW per-tile histograms [batch][digit][tile]; every block derives
 // its own offsets (row prefix up to its tile + totals of the lower digits), which saves the
 // separate one-block scan launch.  Worth it only while a histogram row is short (each block reads
 // 256 x nblk counters), i.e. for the ~100 k-point sorts of the ICP prologue.
-template <bool FUSED_SCAN>
+template <int SCAN_MODE>   // 0: offsets fully scanned, 1: raw histograms (fused scan), 2: chunk-relative + chunk_off
 __global__ void __launch_bounds__(kThreads)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n,
                      int64_t stride, int shift, const uint32_t* __restrict__ block_offs,
-                     int nblk) {
+                     int nblk, const uint32_t* __restrict__ chunk_off, int nchunks) {
   __shared__ uint32_t warp_hist[kWarps][256];
   const int b = blockIdx.y;
   keys_in += (int64_t)b * stride; vals_in += (int64_t)b * stride;
@@ -112,7 +169,7 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
   {  // exclusive scan across warps for digit = threadIdx.x, plus the global offset
     const int d = threadIdx.x;
     uint32_t run;
-    if (FUSED_SCAN) {
+    if (SCAN_MODE == 1) {
       const uint32_t* row = block_offs + ((int64_t)b * 256 + d) * nblk;
       uint32_t before = 0, total = 0;
       for (int t = 0; t < nblk; ++t) { const uint32_t c = row[t]; if (t < (int)blockIdx.x) before += c; total += c; }
@@ -125,7 +182,9 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
       for (int ww = 0; ww < w; ++ww) wb += digit_base[ww];
       run = wb + incl - total + before;
     } else {
-      run = block_offs[((int64_t)b * 256 + d) * nblk + blockIdx.x];
+      const int64_t e = (int64_t)d * nblk + blockIdx.x;          // entry inside this batch
+      run = block_offs[(int64_t)b * 256 * nblk + e];
+      if (SCAN_MODE == 2) run += chunk_off[b * nchunks + (int)(e / kScanChunk)];
     }
 #pragma unroll
     for (int ww = 0; ww < kWarps; ++ww) {
@@ -155,7 +214,8 @@ void radix_scan_kernel_launch(uint32_t* data, int count, int batch, cudaStream_t
 
 size_t radix_sort_scratch_bytes(int n, int batch) {
   const int nblk = ceil_div(n, kTile);
-  return (size_t)batch * 256 * (size_t)nblk * sizeof(uint32_t);
+  const size_t count = (size_t)256 * (size_t)nblk;
+  return ((size_t)batch * count + (size_t)batch * ((count + kScanChunk - 1) / kScanChunk) + 8) * sizeof(uint32_t);
 }
 
 // Sorts keys_a/vals_a (layout [batch][stride]); keys_b/vals_b are ping-pong buffers.
@@ -173,10 +233,16 @@ int radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, u
     const int shift = pass * 8;
     radix_hist_kernel<<<grid, kThreads, 0, stream>>>(kin, n, stride, shift, scratch, nblk);
     if (nblk <= kFusedScanMaxTiles) {
-      radix_scatter_kernel<true><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk);
+      radix_scatter_kernel<1><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk,
+                                                             nullptr, 0);
     } else {
-      radix_scan_kernel<<<batch, 1024, 0, stream>>>(scratch, 256 * nblk);
-      radix_scatter_kernel<false><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk);
+      const int count = 256 * nblk, nchunks = ceil_div(count, kScanChunk);
+      uint32_t* chunk_tot = scratch + (int64_t)batch * count;     // [batch][nchunks], then the ticket
+      uint32_t* ticket = chunk_tot + (int64_t)batch * nchunks;
+      if (pass == 0) cudaMemsetAsync(ticket, 0, sizeof(uint32_t), stream);
+      radix_scan_chunks_kernel<<<dim3(nchunks, batch), 1024, 0, stream>>>(scratch, count, nchunks, chunk_tot, ticket);
+      radix_scatter_kernel<2><<<grid, kThreads, 0, stream>>>(kin, vin, kout, vout, n, stride, shift, scratch, nblk,
+                                                             chunk_tot, nchunks);
     }
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
