@@ -89,3 +89,19 @@ def test_average_transforms_oracle_and_mirror():
     assert np.allclose(R.AverageTransforms([A]), A, atol=1e-14)
     with pytest.raises(R.CheckFailure):
         R.AverageTransforms([])
+
+
+def test_type1_reading_filter_and_chain_on_the_corner_scene():
+    """The oracle-side composition used as the checker of the type-1 matcher (tests/oracle_lib
+    icp_pm_equivalent): the hash filter keeps ~90 % reproducibly, the chain registers the scene."""
+    import scenes
+    keep = O.pm_keep_mask(100_000, 0.9, 1)
+    assert abs(keep.mean() - 0.9) < 5e-3 and np.array_equal(keep, O.pm_keep_mask(100_000, 0.9, 1))
+    assert not np.array_equal(keep, O.pm_keep_mask(100_000, 0.9, 2))
+    assert O.pm_keep_mask(10, 1.0).all() and not O.pm_keep_mask(10, 0.0).any()
+    src, tgt, GT = scenes.corner_pair()
+    o = O.icp_pm_equivalent(src.astype(np.float32), tgt.astype(np.float32))
+    dt, dr = scenes.se3_error(GT, o["result"])
+    assert o["rc"] == 1 and o["ok"] and dt < 0.03 and dr < 5e-3
+    assert 0.6 < o["icp_fast_score"] <= o["score"] < 1.0        # raw reference is denser than the filtered one
+    assert o["n_target"] == 1024 and 4300 < o["n_source"] < 4700
