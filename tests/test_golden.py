@@ -59,3 +59,38 @@ def test_gpu_reproduces_golden():
     dt, dr = scenes.se3_error(G["ng_result"], res)
     assert dt <= 1e-4 and dr <= 1e-4 and abs(g.GetFitnessScore() - float(G["ng_score"])) < 1e-9
     assert g.GetAlignInfo()["aux"][2:] == [float(v) for v in G["ng_counts"][:2]]
+
+
+# ---- section 8(f) rows: tests/golden/rows_f.npz (tests/golden/make_golden_rows_f.py) -------------------
+F = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rows_f.npz"))
+
+
+def test_oracle_reproduces_golden_rows_f():
+    rc, comp = O.motion_compensation(F["scan"], F["delta"])
+    assert rc == 0 and np.array_equal(comp, F["compensated"])
+    m, vox = O.voxel_grid_filter(F["cloud"], float(F["voxel_size"]))
+    assert m == F["voxels"].shape[0] and np.array_equal(vox, F["voxels"])
+    src, tgt, _ = scenes.corner_pair()
+    pm = O.icp_pm_equivalent(src.astype(np.float32), tgt.astype(np.float32))
+    assert [pm["n_source"], pm["n_target"], pm["iterations"], pm["score_kept"]] == list(F["pm_counts"])
+    assert np.allclose(pm["result"], F["pm_result"], atol=1e-12) and abs(pm["score"] - float(F["pm_score"])) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_rows_f():
+    comp = smb.MotionCompensation(F["scan"], F["delta"])
+    want = F["compensated"]
+    d = np.abs(comp[:, :3].astype(np.float64) - want[:, :3].astype(np.float64))
+    assert np.all(d <= np.spacing(np.abs(want[:, :3])).astype(np.float64)) and np.array_equal(comp[:, 3:], want[:, 3:])
+    vox = smb.VoxelGridFilter(F["cloud"], float(F["voxel_size"]))
+    assert np.array_equal(vox.view(np.uint32), F["voxels"].view(np.uint32))
+    src, tgt, _ = scenes.corner_pair()
+    m = smb.IcpUsingPointMatcher()
+    m.SetInputSource(smb.InnerCloud(src.astype(np.float32)))
+    m.SetInputTarget(smb.InnerCloud(tgt.astype(np.float32)))
+    ok, res = m.Align(np.eye(4))
+    info = m.GetAlignInfo()
+    dt, dr = scenes.se3_error(F["pm_result"], res)
+    assert ok == bool(F["pm_ok"]) and dt <= 1e-4 and dr <= 1e-4
+    assert [int(info["aux"][2]), int(info["aux"][3]), info["iterations"], int(info["aux"][1])] == list(F["pm_counts"])
+    assert abs(m.GetFitnessScore() - float(F["pm_score"])) < 1e-9 and abs(info["aux"][0] - float(F["pm_icp_fast_score"])) < 1e-9
