@@ -456,7 +456,10 @@ def main():
                        "working set is L2-resident, so this is a latency-bound kernel",
                 "per_alignment_ms": {k: prof[k] / prof["n"] for k in ("prologue", "knn", "accum", "finish")},
                 "iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS / (iter_ms * 1e-3) / 1e9) / peak,
-                "aggregate_iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS * value / world / 1e9) / peak}
+                "aggregate_iteration_bytes_frac": (BYTES_PER_POINT_ITER * N_SOURCE * ITERATIONS * value / world / 1e9) / peak,
+                # informational (SURVEY 8d second figure, NOT the graded fraction): bytes the traversal
+                # itself touches per query — 14 nodes x 8 B + an 8-point bucket x 16 B + the 64 B above
+                "traversal_inclusive_frac": (304 * N_SOURCE / (knn_ms * 1e-3) / 1e9) / peak}
 
     cfg = workload_config(w0.nt)
     cfg["pairs_in_flight_per_gpu"] = P
