@@ -90,3 +90,28 @@ def test_cpp_adapter_matches_oracle(tmp_path):
     mvox, vox = O.voxel_grid_filter(tgt5, 0.5)
     assert int(out["voxel_sums"][0]) == mvox
     assert np.allclose(out["voxel_sums"][1:], vox[:, :4].astype(np.float64).sum(axis=0), rtol=1e-12, atol=1e-6)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/sm_b200.h is a C ABI: a C99 translation unit includes it, calls through it and links
+    against libsm_b200.so without any C++ runtime on its side."""
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "c_client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "sm_b200.h"\n'
+        "int main(void) {\n"
+        "  sm_handle* h = NULL;\n"
+        "  int n = sm_device_count();\n"
+        "  int rc = sm_create(SM_TYPE_FAST_ICP, 0, &h);\n"
+        '  printf("%s %d %d\\n", sm_version(), n, rc);\n'
+        "  if (rc == SM_OK) { sm_destroy(h); return 0; }\n"
+        "  return (n <= 0 && rc == SM_ERR_NO_DEVICE) ? 0 : 1;   /* no device: the documented loud error */\n"
+        "}\n")
+    exe = str(tmp_path / "c_client")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                        "-L", LIBDIR, "-l:libsm_b200.so", "-Wl,-rpath," + LIBDIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
