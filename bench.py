@@ -446,7 +446,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_KNN_PER_POINT * N_SOURCE / (knn_ms * 1e-3) / 1e9
     iter_ms = (prof["knn"] + prof["accum"] + prof["finish"]) / prof["n"]
-    roofline = {"bound": "hbm", "kernel": "icp_knn_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "icp_knn_static_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "avg_launch_ms": knn_ms,
