@@ -155,6 +155,8 @@ int sm_oracle_average_transforms(const double* Ts, int32_t n, double* out) {
 }  // extern "C"
 
 // ---- pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) --------
+// PINNED by the reference's own unit test (pre_processors/test/test_filter_voxel_grid.cc:34-100: 100 / 36 / 9
+// voxels for its 10 x 10 lattice at 0.1 / 0.2 / 0.4, voxel_size 0 invalid), tests/test_oracle_voxel_filter.py.
 // points / out: packed InnerPointType (x, y, z, intensity, factor).  order_mode 0: output voxels in
 // ascending (ix, iy, iz) (the order the CUDA path emits); order_mode 1: the literal iteration order
 // of std::unordered_map<Eigen::Vector3i, ...> with the reference's hash (common/eigen_hash.h:31-43)

@@ -9,7 +9,9 @@
  * registrators/ (README.md:203-206; builder/data/test/test_cloud_types.cc:158 is an
  * empty stub) and cannot be compiled in this image (Eigen, PCL, libnabo, glog, Boost
  * absent), so this restatement is checked only against analytic known-answer scenes,
- * brute force and scipy's cKDTree (tests/test_oracle_*.py).
+ * brute force and scipy's cKDTree (tests/test_oracle_*.py).  The one row that does have reference
+ * golden values is the voxel filter (pre_processors/test/test_filter_voxel_grid.cc), which the
+ * restatement reproduces (tests/test_oracle_voxel_filter.py).
  *
  * All matrices crossing this API use Eigen's default layout: column-major.
  * Clouds are 3xN column-major doubles (x0,y0,z0,x1,...), as Eigen::MatrixXd in

@@ -53,3 +53,16 @@ def test_edge_cases():
     same = np.tile(one, (5000, 1))                                        # everything in one voxel
     out = smb.VoxelGridFilter(same, 0.5)
     assert out.shape == (1, 5) and np.array_equal(out[0, :4], one[0, :4])
+
+
+def test_reference_unit_test_vectors():
+    """pre_processors/test/test_filter_voxel_grid.cc:52-100: 100 / 36 / 9 voxels at 0.1 / 0.2 / 0.4, invalid
+    size rejected — the golden values the reference itself holds for this row."""
+    from test_oracle_voxel_filter import reference_test_cloud
+    pts = reference_test_cloud()
+    for voxel, want in ((0.1, 100), (0.2, 36), (0.4, 9), (10.0, 1)):
+        got = smb.VoxelGridFilter(pts, voxel)
+        m, ref = O.voxel_grid_filter(pts, voxel)
+        assert got.shape[0] == want == m and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(smb.CheckFailure):
+        smb.VoxelGridFilter(pts, 0.0)
