@@ -38,3 +38,17 @@ def lidar_pair(n_az=300, n_beams=32, submap_points=60000, pair=0, seed=0):
     P = synth.perturbation(pair)
     src = synth.apply_se3(np.linalg.inv(P), world).astype(np.float32).astype(np.float64)
     return src, sub, P
+
+
+def reference_voxel_test_cloud():
+    """The cloud of the reference's own unit test (pre_processors/test/test_filter_voxel_grid.cc:54-63):
+    a 10 x 10 lattice, x = i*0.1f + 0.02f, y = j*0.1f + 0.02f, z = 0.1f, intensity 0 (float arithmetic)."""
+    pts = np.zeros((100, 5), np.float32)
+    k = 0
+    for x in range(10):
+        for y in range(10):
+            pts[k, 0] = np.float32(x) * np.float32(0.1) + np.float32(0.02)
+            pts[k, 1] = np.float32(y) * np.float32(0.1) + np.float32(0.02)
+            pts[k, 2] = np.float32(0.1)
+            k += 1
+    return pts

@@ -58,8 +58,7 @@ def test_edge_cases():
 def test_reference_unit_test_vectors():
     """pre_processors/test/test_filter_voxel_grid.cc:52-100: 100 / 36 / 9 voxels at 0.1 / 0.2 / 0.4, invalid
     size rejected — the golden values the reference itself holds for this row."""
-    from test_oracle_voxel_filter import reference_test_cloud
-    pts = reference_test_cloud()
+    pts = scenes.reference_voxel_test_cloud()
     for voxel, want in ((0.1, 100), (0.2, 36), (0.4, 9), (10.0, 1)):
         got = smb.VoxelGridFilter(pts, voxel)
         m, ref = O.voxel_grid_filter(pts, voxel)

@@ -3,6 +3,7 @@ pre_processors/filter_voxel_grid.cc:37-78).  No GPU."""
 import numpy as np
 
 import oracle_lib as O
+import scenes
 
 
 def cloud(n, seed=0, span=20.0):
@@ -51,25 +52,11 @@ def test_means_and_invalid_size():
     assert O.voxel_grid_filter(pts, 0.0)[0] == -1
 
 
-def reference_test_cloud():
-    """The cloud of the reference's own unit test (pre_processors/test/test_filter_voxel_grid.cc:54-63):
-    a 10 x 10 lattice, x = i*0.1f + 0.02f, y = j*0.1f + 0.02f, z = 0.1f, intensity 0 (float arithmetic)."""
-    pts = np.zeros((100, 5), np.float32)
-    k = 0
-    for x in range(10):
-        for y in range(10):
-            pts[k, 0] = np.float32(x) * np.float32(0.1) + np.float32(0.02)
-            pts[k, 1] = np.float32(y) * np.float32(0.1) + np.float32(0.02)
-            pts[k, 2] = np.float32(0.1)
-            k += 1
-    return pts
-
-
 def test_pinned_by_the_reference_unit_test():
     """BOOST_AUTO_TEST_CASE(Filter) / (FilterConfig) of test_filter_voxel_grid.cc: voxel 0.1 keeps all 100
     points (:76), 0.2 leaves 36 (:87), 0.4 leaves 9 (:98); voxel_size 0 is an invalid config (:37-41),
     10 a valid one (:44-48).  These are the only golden values the reference holds for this row."""
-    pts = reference_test_cloud()
+    pts = scenes.reference_voxel_test_cloud()
     for order_mode in (0, 1):
         assert O.voxel_grid_filter(pts, 0.1, order_mode)[0] == 100
         assert O.voxel_grid_filter(pts, 0.2, order_mode)[0] == 36
