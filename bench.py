@@ -206,8 +206,8 @@ class Worker:
         self.stream = torch.cuda.Stream(device=dev)
         self.m = smb.IcpFast(local_rank)
         opts = {"max_iteration": ITERATIONS, "disable_convergence_check": 1}
-        if os.environ.get("SM_B200_KNN_REFILL") is not None:      # A/B switch for profiles/ (default: on)
-            opts["knn_refill"] = os.environ["SM_B200_KNN_REFILL"]
+        if os.environ.get("SM_B200_KNN_QPC") is not None:         # A/B switch for profiles/: phase-A queries per CTA
+            opts["knn_queries_per_cta"] = os.environ["SM_B200_KNN_QPC"]
         self.m.InitWithXml(opts)
         self.m.SetStream(self.stream.cuda_stream)
         self.d_src = torch.from_numpy(self.src).to(dev)
@@ -446,7 +446,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_KNN_PER_POINT * N_SOURCE / (knn_ms * 1e-3) / 1e9
     iter_ms = (prof["knn"] + prof["accum"] + prof["finish"]) / prof["n"]
-    roofline = {"bound": "hbm", "kernel": "icp_knn_static_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "icp_knn_smem_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "avg_launch_ms": knn_ms,

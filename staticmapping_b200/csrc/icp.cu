@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "icp_dev.cuh"
+#include "knn_smem.cuh"
 #include "linalg_dev.cuh"
 
 namespace smb {
@@ -84,9 +85,8 @@ __global__ void fill_buckets_kernel(const double* __restrict__ coord, int64_t cs
 
 // one block: G0 = T_mean^-1 * guess, state reset, histogram clear (icp_fast.cc:460-480)
 __global__ void icp_init_kernel(IcpState* __restrict__ st, const double* __restrict__ guess,
-                                uint32_t* __restrict__ hist, uint32_t* __restrict__ claim, int nchunks) {
-  for (int i = threadIdx.x; i < 2 * kHistBins + 2; i += blockDim.x) hist[i] = 0;  // hist + hist2 + steal cursor + started blocks
-  for (int i = threadIdx.x; i < nchunks; i += blockDim.x) claim[i] = 0;            // stamps start at 1
+                                uint32_t* __restrict__ hist) {
+  for (int i = threadIdx.x; i < 2 * kHistBins; i += blockDim.x) hist[i] = 0;  // hist + hist2
   if (threadIdx.x != 0) return;
   double Tm[16], Tmi[16];
   for (int i = 0; i < 16; ++i) { Tm[i] = (i % 5 == 0) ? 1.0 : 0.0; Tmi[i] = Tm[i]; }
@@ -132,14 +132,6 @@ __global__ void apply_g0_kernel(const double* __restrict__ in, double* __restric
   vals[i] = (uint32_t)i;
 }
 
-__global__ void visits_key_kernel(const uint8_t* __restrict__ visits, int n, uint64_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  keys[i] = visits[i];
-  vals[i] = (uint32_t)i;
-}
-
 // queries in Morton order: neighbouring threads walk the same tree lines and hit the same
 // buckets.  Only sums are formed over the source, so its order is free.
 __global__ void gather_source_kernel(const double* __restrict__ in, double* __restrict__ out,
@@ -151,218 +143,36 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 }
 
 // -------------------------------------------------------------------------------- phase A
-__global__ void __launch_bounds__(kKnnThreads)
-icp_knn_static_kernel(IcpBuffers b, IcpParams p) {
-  __shared__ double T[16];
+// ApplyTransform + FindClosests (icp_fast.cc:486-493, 169-180) + the 2048-bin histogram of the
+// squared distances.  Persistent CTAs of 1024 threads, one per SM; each stages the tree's node
+// arrays into shared memory with bulk async copies (knn_smem.cuh) while its threads load and
+// transform their queries, then every thread searches its queries (contiguous, Morton-ordered
+// range per CTA, so neighbouring threads walk the same nodes and buckets).
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kKnnCtaThreads, 1)
+icp_knn_smem_kernel(IcpBuffers b, IcpParams p, int per_cta) {
+  extern __shared__ __align__(128) unsigned char knn_smem[];
   if (b.state->done) return;
-  // measured: keeping the first 4 pending subtrees per thread in shared memory is SLOWER
-  // (2.34 vs 2.00 ms per 30 launches): the 37 KB per block come out of the L1 that caches the
-  // tree lines.  The stack therefore stays in (L1-cached) local memory.
+  uint64_t* bar; double* T;
+  const SmemTree tree = stage_tree(b.kc, knn_smem, &bar, &T);
   if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
   __syncthreads();
-  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
-  if (i < p.n_source) {
-    double px, py, pz;
-    transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+  const int begin = blockIdx.x * per_cta, end = min(begin + per_cta, p.n_source);
+  int i = begin + threadIdx.x;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (i < end) transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+  mbar_wait(bar, 0);                       // tree resident (every thread waits: the CTA must not
+                                           // retire while the copy engine still writes its smem)
+  while (i < end) {
     int slot; double d2;
-    if (p.debug_knn_mode == 0 || p.debug_knn_mode >= 10) {
-      int rounds = 0;
-      knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2,
-           p.debug_knn_mode >= 10 ? p.debug_knn_mode - 10 : (1 << 30), &rounds);
-      if (b.visits) b.visits[i] = (uint8_t)min(rounds, 255);
-    } else {   // profiling aid: truncated variants (results are NOT the k-NN)
-      slot = 0; d2 = px * px + py * py + pz * pz + 1.0;
-      if (p.debug_knn_mode >= 2) {
-        int idx = 0;
-        KdNode nd = load_node(b.nodes, 0);
-        while (nd.dim != 3) {
-          const double q = nd.dim == 0 ? px : (nd.dim == 1 ? py : pz);
-          idx = child_idx(idx, (q > nd.cut) ? 1 : 0);
-          nd = load_node(b.nodes, idx);
-        }
-        slot = (int)(__double_as_longlong(nd.cut) & 0xffffffffll);
-        if (p.debug_knn_mode >= 3) {
-          double head = __longlong_as_double(0x7ff0000000000000ll);
-          scan_leaf(b.bpts, nd, px, py, pz, head, slot);
-          d2 = head;
-        }
-      }
-    }
+    knn1_smem<kAllSmem>(tree, px, py, pz, p.max_error2, slot, d2);
     b.slot[i] = slot;
     b.d2[i] = d2;
-    // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident);
-    // no block-level staging, so a warp retires as soon as its own queries are done
+    // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident)
     if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
+    i += kKnnCtaThreads;
+    if (i < end) transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
   }
-}
-
-// Phase A with work sharing.  The search of one query is the same sequence of passes as in knn1 /
-// visit_subtree (pass 0: read-only descent + first bucket; then one pass per far visit), but a
-// lane whose query is finished does not idle until the slowest lane of its warp is done: the warp
-// claims further 32-query chunks (Morton-consecutive, so still coherent) and hands their queries
-// to lanes as they become free.  Chunk c belongs to warp c ("home"); a warp claims its home chunk
-// with one atomicExch on the chunk's own stamp (no shared address), and steals from the END of
-// the chunk list through a cursor.  With one alignment in flight every warp is resident at once,
-// claims its home chunk and finds nothing to steal: the kernel behaves like the static one.  With
-// many alignments in flight the warps of late blocks start late, early warps take over their
-// chunks, late blocks find them claimed and retire at once: lanes stay busy and a warp slot is
-// released as soon as the work runs out (profiles/knn_profile.py: 14 of 32 lanes are active on
-// average in the static kernel).
-// MEASURED: slower than the static kernel in both regimes — 2.26 vs 1.87 ms
-// of k-NN per alignment with one in flight (58 vs 40 registers, the claim round trips, the
-// per-pass ballots) and 777 vs 1050 alignments/s with 16 in flight (lanes of one warp end up in
-// distant tree regions, every pass waits for more distinct lines).  Option knn_refill, default off.
-// Results do not depend on who runs a query: each query's search is self-contained.
-constexpr int kRefillMin = 8;   // free lanes before a warp looks for more work
-
-__global__ void __launch_bounds__(kKnnThreads)
-icp_knn_kernel(IcpBuffers b, IcpParams p) {
-  __shared__ double T[16];
-  if (b.state->done) return;
-  if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
-  const uint32_t stamp = (uint32_t)b.state->iteration + 1u;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt = (1u << lane) - 1u;
-  const int n = p.n_source;
-  const int nchunks = (n + 31) >> 5;
-  const int home = (blockIdx.x * kKnnThreads + threadIdx.x) >> 5;
-  uint32_t* cursor = b.hist + 2 * kHistBins;
-  uint32_t* started = cursor + 1;        // blocks of this launch that have begun
-  if (threadIdx.x == 0) atomicAdd(started, 1u);
-  const KdNode* __restrict__ nodes = b.nodes;
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  const double me2 = p.max_error2;
-  // the warp's window of claimed, not yet started queries (warp-uniform)
-  int win_next = 0, win_end = 0;
-  bool tried_home = false, exhausted = false;
-  // per-lane search state
-  bool active = false;
-  int qi = 0, phase = 0, best = -1, idx = 0, sp = 0, rounds = 0;
-  double qx = 0, qy = 0, qz = 0, head = inf, rd = 0, ox = 0, oy = 0, oz = 0, min_rd = inf;
-  StackEntry stack[kMaxStack];
-  while (true) {
-    // ---- hand queries to free lanes --------------------------------------------------------
-    uint32_t freem = __ballot_sync(0xffffffffu, !active);
-    while (freem != 0u) {
-      if (win_next >= win_end) {
-        if (exhausted || (__popc(freem) < kRefillMin && freem != 0xffffffffu)) break;
-        int c = -1;
-        if (lane == 0) {
-          if (!tried_home && home < nchunks && atomicExch(&b.knn_claim[home], stamp) != stamp) {
-            c = home;
-          } else {
-            // steal from the end of the list, but never from a block that has already started: its
-            // own warps are claiming those chunks (with one alignment in flight every block has
-            // started and this ends after one look)
-            while (true) {
-              const uint32_t k = atomicAdd(cursor, 1u);
-              const int cand = nchunks - 1 - (int)k;
-              const int s = (int)*reinterpret_cast<volatile uint32_t*>(started);
-              if (cand < 0 || cand < s * (kKnnThreads / 32)) { c = -2; break; }
-              if (atomicExch(&b.knn_claim[cand], stamp) != stamp) { c = cand; break; }
-            }
-          }
-        }
-        tried_home = true;
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c < 0) { exhausted = true; break; }
-        win_next = c << 5;
-        win_end = min(win_next + 32, n);
-      }
-      const int avail = win_end - win_next;
-      const int rank = __popc(freem & lt);
-      if (!active && rank < avail) {
-        qi = win_next + rank;
-        transform_point(T, b.src0[qi], b.src0[b.sstride + qi], b.src0[2 * b.sstride + qi], qx, qy, qz);
-        active = true; phase = 0; best = -1; idx = 0; sp = 0; rounds = 0;
-        head = inf; rd = 0.0; ox = 0.0; oy = 0.0; oz = 0.0; min_rd = inf;
-      }
-      win_next += min(__popc(freem), avail);
-      freem = __ballot_sync(0xffffffffu, !active);
-    }
-    if (!__any_sync(0xffffffffu, active)) break;
-    // ---- one pass: descend to a bucket, scan it, pick the next pending subtree ---------------
-    if (active) {
-      KdNode nd = load_node(nodes, idx);
-      int guard = 0;
-      while (nd.dim != 3 && ++guard < 64) {
-        const int cd = nd.dim;
-        const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-        const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
-        const int right = q > nd.cut ? 1 : 0;
-        const int next = child_idx(idx, right);
-        const KdNode nd_next = load_node(nodes, next);
-        const double new_off = dsub(q, nd.cut);
-        const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-        if (phase == 0) {
-          min_rd = fmin(min_rd, rd_new);     // == new_off^2 on the first descent (rd = 0, offsets 0)
-        } else if (dmul(rd_new, me2) < head && sp < kMaxStack) {
-          StackEntry e;
-          e.rd = rd_new;
-          e.ox = cd == 0 ? new_off : ox;
-          e.oy = cd == 1 ? new_off : oy;
-          e.oz = cd == 2 ? new_off : oz;
-          e.idx = child_idx(idx, 1 - right);
-          stack[sp++] = e;
-        }
-        idx = next;
-        nd = nd_next;
-      }
-      if (nd.dim == 3) scan_leaf(b.bpts, nd, qx, qy, qz, head, best);
-      bool fin;
-      if (phase == 0) {
-        // no far subtree can qualify if even the closest cut plane fails the test (see knn1)
-        fin = !(dmul(min_rd, me2) < head);
-        phase = 1; idx = 0; rd = 0.0; ox = 0.0; oy = 0.0; oz = 0.0; sp = 0;   // else: replay from the root
-      } else {
-        ++rounds;
-        fin = true;
-        while (sp > 0) {
-          const StackEntry e = stack[--sp];
-          if (dmul(e.rd, me2) < head) {
-            idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
-            fin = false;
-            break;
-          }
-        }
-      }
-      if (fin) {
-        b.slot[qi] = best;
-        b.d2[qi] = head;
-        if (b.visits) b.visits[qi] = (uint8_t)min(rounds, 255);
-        if (finite_d2(head)) atomicAdd(&b.hist[dist_bin(head)], 1u);
-        active = false;
-      }
-    }
-  }
-}
-
-// Diagnostics (sm_debug_knn_profile): the phase-A search with per-thread clocks.
-__global__ void __launch_bounds__(kKnnThreads)
-icp_knn_profile_kernel(IcpBuffers b, IcpParams p, int identity, uint32_t* __restrict__ cycles,
-                       uint8_t* __restrict__ rounds_out, uint8_t* __restrict__ smid_out,
-                       unsigned long long* __restrict__ t0_out, unsigned long long* __restrict__ t1_out) {
-  __shared__ double T[16];
-  if (threadIdx.x < 16) T[threadIdx.x] = identity ? ((threadIdx.x % 5 == 0) ? 1.0 : 0.0) : b.state->T_iter[threadIdx.x];
-  __syncthreads();
-  const int i = blockIdx.x * kKnnThreads + threadIdx.x;
-  if (i >= p.n_source) return;
-  unsigned long long g0, g1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-  const long long c0 = clock64();
-  double px, py, pz;
-  transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
-  int slot, rounds = 0; double d2;
-  knn1(b.nodes, b.bpts, px, py, pz, p.max_error2, slot, d2, 1 << 30, &rounds);
-  const long long c1 = clock64();
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-  uint32_t sm;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-  cycles[i] = (uint32_t)(c1 - c0) + (slot < 0 ? 0u : 0u) + (d2 < 0.0 ? 1u : 0u);
-  rounds_out[i] = (uint8_t)min(rounds, 255);
-  smid_out[i] = (uint8_t)sm;
-  t0_out[i] = g0; t1_out[i] = g1;
 }
 
 // -------------------------------------------------------------------------------- phase B
@@ -404,10 +214,11 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
     bin[r] = finite_d2(d2[r]) ? dist_bin(d2[r]) : kHistBins;
     use[r] = sel.bin >= 0 && slot[r] >= 0 && bin[r] <= sel.bin;
     const int s = use[r] ? slot[r] : 0;
-    qxy[r] = __ldg(reinterpret_cast<const double2*>(b.bpts + s));
-    qz[r] = __ldg(reinterpret_cast<const double*>(b.bpts + s) + 2);
-    nxy[r] = __ldg(reinterpret_cast<const double2*>(b.bnrm + s));
-    nz[r] = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
+    const double* pq = b.kc.pb + (int64_t)(s >> 3) * 24 + (s & 7);     // padded bucket: x[8] y[8] z[8]
+    qxy[r] = make_double2(__ldg(pq), __ldg(pq + 8));
+    qz[r] = __ldg(pq + 16);
+    nxy[r] = __ldg(reinterpret_cast<const double2*>(b.kc.pn + s));
+    nz[r] = __ldg(reinterpret_cast<const double*>(b.kc.pn + s) + 2);
   }
   double acc[kNumSums];
 #pragma unroll
@@ -453,16 +264,21 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
   block_reduce_sums<kAccThreads>(acc, red, b.partials + (int64_t)blockIdx.x * 32);
 }
 
-__global__ void __launch_bounds__(256)
-knn_query_kernel(const KdNode* __restrict__ nodes, const BucketPoint* __restrict__ bpts,
-                 const double* __restrict__ query, int64_t qstride, int nq, double max_error2,
-                 int tree_levels, int32_t* __restrict__ ids, double* __restrict__ d2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  int slot; double d;
-  knn1(nodes, bpts, query[i], query[qstride + i], query[2 * qstride + i], max_error2, slot, d);
-  ids[i] = slot >= 0 ? (int32_t)bpts[slot].id : -1;
-  d2[i] = d;
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kKnnCtaThreads, 1)
+knn_query_smem_kernel(KdCompact kc, const double* __restrict__ query, int64_t qstride, int nq,
+                      double max_error2, int per_cta, int32_t* __restrict__ ids, double* __restrict__ d2) {
+  extern __shared__ __align__(128) unsigned char knn_smem[];
+  uint64_t* bar; double* extra;
+  const SmemTree tree = stage_tree(kc, knn_smem, &bar, &extra);
+  const int begin = blockIdx.x * per_cta, end = min(begin + per_cta, nq);
+  mbar_wait(bar, 0);
+  for (int i = begin + threadIdx.x; i < end; i += kKnnCtaThreads) {
+    int slot; double d;
+    knn1_smem<kAllSmem>(tree, query[i], query[qstride + i], query[2 * qstride + i], max_error2, slot, d);
+    ids[i] = slot >= 0 ? kc.pid[slot] : -1;
+    d2[i] = d;
+  }
 }
 
 }  // namespace
@@ -478,14 +294,42 @@ int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int
   return 0;
 }
 
-int knn_configure() { return 0; }
+// Launch geometry of the shared-memory-tree search kernels: `per_cta` consecutive queries per CTA.
+// queries_per_cta == 0 spreads the queries over all 148 SMs (lowest latency for one alignment in
+// flight: 120 000 queries = 148 CTAs x 26 warps); a positive value packs that many queries per
+// CTA (1024 fills a CTA and leaves whole SMs to the kernels of other alignments in flight).
+static void knn_geometry(int nq, int queries_per_cta, int* grid, int* per_cta) {
+  int per = queries_per_cta > 0 ? queries_per_cta : ceil_div(nq, kNumSMs);
+  per = ((per + 31) / 32) * 32;
+  if (per < 64) per = 64;
+  *per_cta = per;
+  *grid = ceil_div(nq, per);
+}
 
-int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
-              int nq, double max_error2, int tree_levels, int32_t* ids, double* d2,
-              cudaStream_t stream) {
+static bool g_knn_attr_set[64] = {};   // per device (function attributes are per device)
+int knn_configure() {
+  int dev = 0;
+  SMB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_knn_attr_set[dev]) return 0;
+  const int max_bytes = (int)knn_smem_bytes(kKnnSmemLevels);
+  SMB_CUDA_OK(cudaFuncSetAttribute(icp_knn_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+  SMB_CUDA_OK(cudaFuncSetAttribute(icp_knn_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+  SMB_CUDA_OK(cudaFuncSetAttribute(knn_query_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+  SMB_CUDA_OK(cudaFuncSetAttribute(knn_query_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+  if (dev >= 0 && dev < 64) g_knn_attr_set[dev] = true;
+  return 0;
+}
+
+int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
+              int32_t* ids, double* d2, cudaStream_t stream) {
   if (nq <= 0) return 0;
-  knn_query_kernel<<<ceil_div(nq, 256), 256, 0, stream>>>(
-      nodes, bpts, query, qstride, nq, max_error2, tree_levels, ids, d2);
+  int grid, per;
+  knn_geometry(nq, 0, &grid, &per);
+  const size_t smem = knn_smem_bytes(kc.levels);
+  if (kc.levels <= kKnnSmemLevels)
+    knn_query_smem_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
+  else
+    knn_query_smem_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -498,11 +342,12 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   mean_partial_kernel<<<nparts, 256, 0, stream>>>(b.tgt_raw, b.tstride, nt, b.mean_partials);
   center_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(b.tgt_raw, b.tgt, b.tstride, nt,
                                                       b.mean_partials, nparts, b.state);
-  int rc = kd_build(b.tgt, b.tstride, nt, 8, ws, b.nodes, b.leaf_order, stream);
+  int rc = kd_build(b.tgt, b.tstride, nt, 8, ws, b.nodes, b.leaf_order, stream, b.ccut, b.cdim);
   if (rc) return rc;
-  rc = kd_fill_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, b.bpts, b.bnrm, stream);
+  rc = kd_compact_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, 8, p.tree_levels, b.cpb, b.cpn,
+                          nullptr, stream);
   if (rc) return rc;
-  icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist, b.knn_claim, ceil_div(p.n_source, 32));
+  icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist);
   apply_g0_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_raw, b.src_g0, b.sstride, ns, b.state,
                                                         b.src_keys[0], b.src_vals[0]);
   rc = radix_sort_pairs_u64(b.src_keys[0], b.src_vals[0], b.src_keys[1], b.src_vals[1], ns, 1,
@@ -514,50 +359,25 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   return 0;
 }
 
-// Iterations start_iteration .. start_iteration+count-1 of one Align.  The k-NN of iteration 0
-// records how many buckets every query visited; right after it the queries are re-ordered by
-// that count (stable: Morton order survives inside a class), so that the lanes of a warp need
-// about the same number of sequential traversal rounds in all later iterations (the pose moves
-// little between iterations).  Only sums are formed over the source, so its order is free.
-int icp_enqueue_iterations(const IcpBuffers& b_in, const IcpParams& p, int start_iteration, int count,
+// Iterations start_iteration .. start_iteration+count-1 of one Align: three launches each.
+int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_iteration, int count,
                            cudaStream_t stream, cudaEvent_t* events) {
   const int nb = icp_accum_blocks(p.n_source);
-  const bool resort = p.resort_by_visits != 0;
-  IcpBuffers b = b_in;
-  IcpBuffers b_sorted = b_in;       // what iterations >= 1 read once the re-ordering happened
-  b_sorted.src0 = b_in.src_g0;
-  b_sorted.visits = nullptr;
-  if (!resort) b.visits = nullptr;
+  int grid, per;
+  knn_geometry(p.n_source, p.knn_queries_per_cta, &grid, &per);
+  const size_t smem = knn_smem_bytes(p.tree_levels);
   for (int it = 0; it < count; ++it) {
-    const int global_it = start_iteration + it;
-    const IcpBuffers& bb = (resort && global_it >= 1) ? b_sorted : b;
     if (events) cudaEventRecord(events[4 * it + 0], stream);
-    if (p.knn_refill && p.debug_knn_mode == 0)
-      icp_knn_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
+    if (p.tree_levels <= kKnnSmemLevels)
+      icp_knn_smem_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
     else
-      icp_knn_static_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(bb, p);
+      icp_knn_smem_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
     if (events) cudaEventRecord(events[4 * it + 1], stream);
-    icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(bb, p);
+    icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
     if (events) cudaEventRecord(events[4 * it + 2], stream);
-    icp_finish_launch(bb, p, nb, stream);
-    if (resort && global_it == 0) {
-      visits_key_kernel<<<ceil_div(p.n_source, 256), 256, 0, stream>>>(b.visits, p.n_source, b.src_keys[0], b.src_vals[0]);
-      int rc = radix_sort_pairs_u64(b.src_keys[0], b.src_vals[0], b.src_keys[1], b.src_vals[1], p.n_source, 1,
-                                    b.sstride, b.src_scratch, stream, 1);   // 1 pass: result in [1]
-      if (rc) return rc;
-      gather_source_kernel<<<ceil_div(p.n_source, 256), 256, 0, stream>>>(b.src0, b.src_g0, b.sstride, p.n_source,
-                                                                         b.src_vals[1]);
-    }
+    icp_finish_launch(b, p, nb, stream);
     if (events) cudaEventRecord(events[4 * it + 3], stream);
   }
-  SMB_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int icp_knn_profile(const IcpBuffers& b, const IcpParams& p, int identity, uint32_t* cycles, uint8_t* rounds,
-                    uint8_t* smid, unsigned long long* t0, unsigned long long* t1, cudaStream_t stream) {
-  icp_knn_profile_kernel<<<ceil_div(p.n_source, kKnnThreads), kKnnThreads, 0, stream>>>(b, p, identity, cycles, rounds,
-                                                                                       smid, t0, t1);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -283,27 +283,6 @@ __device__ __forceinline__ void add_terms(double* acc, const double* F, double d
   acc[27] += sqrt(d2);
   acc[28] += 1.0;
 }
-__device__ __forceinline__ void accumulate_match(double* acc, double px, double py, double pz,
-                                                 const BucketPoint& q, const BucketNormal& n,
-                                                 double d2) {
-  double F[6], dot;
-  match_terms(px, py, pz, q, n, F, dot);
-  add_terms(acc, F, dot, d2);
-}
-
-__device__ __forceinline__ void load_match(const IcpBuffers& b, const double* T, int i,
-                                           double& px, double& py, double& pz, BucketPoint& q,
-                                           BucketNormal& n) {
-  transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
-  const int s = b.slot[i];
-  const double2 qxy = __ldg(reinterpret_cast<const double2*>(b.bpts + s));
-  q.x = qxy.x; q.y = qxy.y;
-  q.z = __ldg(reinterpret_cast<const double*>(b.bpts + s) + 2);
-  const double2 nxy = __ldg(reinterpret_cast<const double2*>(b.bnrm + s));
-  n.x = nxy.x; n.y = nxy.y;
-  n.z = __ldg(reinterpret_cast<const double*>(b.bnrm + s) + 2);
-}
-
 // acc += pred ? terms : 0 (adding +0.0 leaves a sum unchanged, so no branch is needed and the
 // loads feeding several matches can be in flight together); sq = sqrt(d2)
 __device__ __forceinline__ void add_terms_if(double* acc, const double* Fin, double dot_in, double sq,

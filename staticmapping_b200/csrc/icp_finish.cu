@@ -487,7 +487,7 @@ icp_finish_kernel(IcpBuffers b, IcpParams p, int nblocks_b) {
     if (lane < kNumSums) red[w][lane] = v;
   }
 #pragma unroll 1
-  for (int k = t; k < 2 * kHistBins + 2; k += kSelThreads) b.hist[k] = 0;   // hist, hist2, phase-A steal cursor + started blocks
+  for (int k = t; k < 2 * kHistBins; k += kSelThreads) b.hist[k] = 0;   // hist, hist2
   __syncthreads();
   if (t == 0) sst.stamps[5] = clock64();
 #pragma unroll 1

@@ -62,7 +62,8 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
                                const uint32_t* __restrict__ lists, int64_t lstride, int n,
                                int bucket, int L, const double* __restrict__ bounds_in,
                                double* __restrict__ bounds_out, int* __restrict__ level_dim,
-                               KdNode* __restrict__ nodes) {
+                               KdNode* __restrict__ nodes, double* __restrict__ ccut,
+                               uint8_t* __restrict__ cdim) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (1 << L)) return;
   const Seg s = locate_node(j, L, n, bucket);
@@ -74,6 +75,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
     leaf.dim = 3; leaf.pad = 0;
     nodes[blocked_index(h)] = leaf;
     level_dim[j] = 3;
+    if (cdim) cdim[h] = 3;
     return;
   }
   double mn[3], mx[3];
@@ -95,6 +97,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
   KdNode nd; nd.cut = cut; nd.dim = dim; nd.pad = 0;
   nodes[blocked_index(h)] = nd;
   level_dim[j] = dim;
+  if (ccut) { ccut[h] = cut; cdim[h] = (uint8_t)dim; }
   double* bl = bounds_out + (int64_t)(2 * j) * 6;
   double* br = bounds_out + (int64_t)(2 * j + 1) * 6;
   for (int d = 0; d < 3; ++d) {
@@ -238,6 +241,42 @@ __global__ void kd_leaf_kernel(const uint32_t* __restrict__ list0, int n, int bu
   for (int k = 0; k < s.count; ++k) leaf_order[s.first + k] = ids[k];
 }
 
+// ---- compact search layout (KdCompact, kernels.h): padded buckets ------------------------
+// Entry e = bucket * 8 + k of the padded bucket space; bucket = in-level index of a leaf at
+// level `levels`, or (index << 1) of a leaf one level higher (its odd twin stays empty).
+// Coordinates are stored per bucket as x[8] y[8] z[8]; empty entries hold +inf, so their
+// squared distance is +inf (or NaN) and the strict '<' of the search never takes them.
+__global__ void kd_compact_buckets_kernel(const double* __restrict__ coord, int64_t cstride,
+                                          const double* __restrict__ nrm, int64_t nstride,
+                                          const uint32_t* __restrict__ leaf_order, int n, int bucket,
+                                          int levels, double* __restrict__ pb,
+                                          BucketNormal* __restrict__ pn, int32_t* __restrict__ pid) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ((int64_t)8 << levels)) return;
+  const int jL = (int)(e >> 3), k = (int)(e & 7);
+  int first = 0, count = n, l = 0;
+  while (l < levels && count > bucket) {
+    const int right = count >> 1, left = count - right;
+    if ((jL >> (levels - 1 - l)) & 1) { first += left; count = right; } else { count = left; }
+    ++l;
+  }
+  const bool owner = (jL & ((1 << (levels - l)) - 1)) == 0;   // left-most descendant slot of the leaf
+  const bool valid = owner && k < count;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double x = inf, y = inf, z = inf;
+  BucketNormal q; q.x = 0.0; q.y = 0.0; q.z = 0.0; q.pad = 0.0;
+  int32_t id = -1;
+  if (valid) {
+    id = (int32_t)leaf_order[first + k];
+    x = coord[id]; y = coord[cstride + id]; z = coord[2 * cstride + id];
+    if (nrm) { q.x = nrm[id]; q.y = nrm[nstride + id]; q.z = nrm[2 * nstride + id]; }
+  }
+  double* o = pb + (int64_t)jL * 24 + k;
+  o[0] = x; o[8] = y; o[16] = z;
+  if (pn) pn[e] = q;
+  if (pid) pid[e] = id;
+}
+
 __global__ void kd_keys_kernel(const double* __restrict__ coord, int64_t cstride, int n,
                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                int64_t lstride) {
@@ -293,7 +332,7 @@ void KdWorkspace::carve(void* base, int n, int bucket) {
 // coord: SoA [3][cstride] doubles (already centred).  Writes nodes (heap layout,
 // 2^(levels+1)-1 entries) and leaf_order[n] (point ids in bucket order).
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
-             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream) {
+             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut, uint8_t* cdim) {
   if (n <= 0) return -1;
   const int levels = kd_num_levels(n, bucket);
   const int64_t ls = ws.lstride;
@@ -308,7 +347,7 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
     const int nodes_l = 1 << L;
     kd_node_kernel<<<ceil_div(nodes_l, 128), 128, 0, stream>>>(
         coord, cstride, ws.lists[cur], ls, n, bucket, L, ws.bounds[L & 1], ws.bounds[(L + 1) & 1],
-        ws.level_dim, nodes);
+        ws.level_dim, nodes, ccut, cdim);
     kd_flag_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(ws.lists[cur], ls, n, bucket, L,
                                                         ws.level_dim, ws.flag);
     kd_part_count_kernel<<<dim3(nblk, 3), kPartThreads, 0, stream>>>(
@@ -326,6 +365,22 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
   const int total = (1 << (levels + 1)) - 1;
   kd_leaf_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(ws.lists[cur], n, bucket, levels,
                                                           nodes, leaf_order);
+  SMB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t kd_compact_node_slots(int levels) {
+  const size_t n = (size_t)1 << levels;      // 2^levels - 1 inner-capable nodes, rounded up
+  return n < 16 ? 16 : n;                    // bulk copies move multiples of 16 bytes
+}
+
+int kd_compact_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
+                       const uint32_t* leaf_order, int n, int bucket, int levels, double* pb,
+                       BucketNormal* pn, int32_t* pid, cudaStream_t stream) {
+  if (bucket > 8) return -1;
+  const int64_t total = (int64_t)8 << levels;
+  kd_compact_buckets_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(coord, cstride, nrm, nstride, leaf_order, n,
+                                                                     bucket, levels, pb, pn, pid);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -31,8 +31,33 @@ struct KdWorkspace {
   static size_t bytes_needed(int n, int bucket);
   void carve(void* base, int n, int bucket);
 };
+// ccut / cdim (optional): the compact search layout's node arrays, see KdCompact
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
-             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream);
+             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut = nullptr,
+             uint8_t* cdim = nullptr);
+
+// Compact search layout of the same tree, shaped for a shared-memory resident traversal:
+//   cut[h], dim[h]  heap order (children of h: 2h+1, 2h+2) for the levels above the deepest
+//                   leaf level; dim 3 = leaf.  8 + 1 bytes per node: the 14 inner levels of a
+//                   ~107 k-point target are 144 KB and are staged into shared memory with bulk
+//                   async copies (cp.async.bulk + mbarrier) once per CTA;
+//   pb              padded buckets, x[8] y[8] z[8] doubles per leaf slot of the deepest level
+//                   (+inf padding), so a leaf's bucket address is pure index arithmetic and a
+//                   bucket scan is 12 aligned 16-byte loads;
+//   pn, pid         normals / original ids per padded entry (entry = bucket * 8 + k).
+struct KdCompact {
+  const double* cut;
+  const uint8_t* dim;
+  const double* pb;
+  const BucketNormal* pn;
+  const int32_t* pid;
+  int levels;
+};
+size_t kd_compact_node_slots(int levels);     // entries of cut[] / dim[] (multiple of 16)
+inline size_t kd_compact_bucket_entries(int levels) { return (size_t)8 << levels; }
+int kd_compact_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
+                       const uint32_t* leaf_order, int n, int bucket, int levels, double* pb,
+                       BucketNormal* pn, int32_t* pid, cudaStream_t stream);
 
 // ---- icp.cu ----------------------------------------------------------------------------
 constexpr int kHistBins = 2048;
@@ -66,9 +91,7 @@ struct IcpParams {
   double max_error2;       // (1+eps)^2
   int disable_convergence;
   int tree_levels;         // kd_num_levels(n_target, 8): depth of the root-to-leaf path
-  int resort_by_visits;    // re-order the queries by their iteration-0 bucket count
-  int debug_knn_mode;      // 0 = normal; 1..3 = truncated k-NN kernel variants (profiling aid only)
-  int knn_refill;          // phase A: lanes that finish their query take the next unclaimed one (default 0: measured slower)
+  int knn_queries_per_cta; // phase A: 0 = spread the queries over all SMs, else queries per 1024-thread CTA
 };
 
 struct IcpBuffers {
@@ -77,11 +100,14 @@ struct IcpBuffers {
   double* tgt_raw;        // [3][tstride] as uploaded (un-centred)
   double* nrm;            // [3][tstride]
   int64_t tstride;
-  // tree
+  // tree: build-time node array (blocked layout), leaf order, and the compact search layout
   KdNode* nodes;
   uint32_t* leaf_order;
-  BucketPoint* bpts;
-  BucketNormal* bnrm;
+  double* ccut;           // writable views of kc.cut / kc.dim / kc.pb / kc.pn (filled by the prologue)
+  uint8_t* cdim;
+  double* cpb;
+  BucketNormal* cpn;
+  KdCompact kc;
   // source
   double* src_raw;        // [3][sstride] as uploaded
   double* src_g0;         // [3][sstride] after G0, caller order
@@ -91,11 +117,8 @@ struct IcpBuffers {
   uint32_t* src_scratch;  // radix scratch
   int64_t sstride;
   // per-iteration
-  uint8_t* visits;        // [n_source] buckets visited by the query in iteration 0 (or null)
-  int32_t* slot;          // [n_source] bucket slot of the match
+  int32_t* slot;          // [n_source] padded bucket entry of the match (kc.pb / kc.pn index)
   double* d2;             // [n_source]
-  uint32_t* knn_claim;    // [ceil(n_source / 32)] claim stamp of every 32-query chunk (phase A work sharing);
-                          // the steal cursor is hist[2 * kHistBins], cleared with the histograms
   uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
   uint32_t* hist2;        // [kHistBins] second-level histogram inside the quantile bin (phase B)
   double* sums;           // [32] reduced normal-equation sums of the iteration (phase C1 -> C2)
@@ -115,14 +138,11 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
 int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_iteration, int count,
                            cudaStream_t stream, cudaEvent_t* events);
 void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, cudaStream_t stream);
-// stand-alone k-NN over an already built tree (parity tests): ids = original indices
-int knn_query(const KdNode* nodes, const BucketPoint* bpts, const double* query, int64_t qstride,
-              int nq, double max_error2, int tree_levels, int32_t* ids, double* d2,
-              cudaStream_t stream);
+// stand-alone k-NN over an already built tree (compact layout incl. pid): ids = original indices
+int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
+              int32_t* ids, double* d2, cudaStream_t stream);
+// once per process and device context: opt the search kernels into > 48 KB of dynamic shared memory
 int knn_configure();
-// diagnostics: phase-A search with per-thread clocks (device output arrays of n_source entries)
-int icp_knn_profile(const IcpBuffers& b, const IcpParams& p, int identity, uint32_t* cycles, uint8_t* rounds,
-                    uint8_t* smid, unsigned long long* t0, unsigned long long* t1, cudaStream_t stream);
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);

@@ -1,0 +1,258 @@
+// libnabo-compatible 1-NN (KDTREE_LINEAR_HEAP, k = 1, allowSelfMatch, maxRadius = inf;
+// call site registrators/icp_fast.cc:177-178) over the compact tree layout (KdCompact), with
+// the node arrays resident in SHARED MEMORY.
+//
+// B200 formulation
+//   * a ~107 k-point target has 14 inner levels = 16 383 nodes; as {cut f64}[h] + {dim u8}[h]
+//     that is 144 KB, which fits the 227 KB of one SM.  Each (persistent) CTA stages the arrays
+//     once with bulk async copies (cp.async.bulk.shared::cluster.global + mbarrier
+//     complete_tx; SASS UBLKCP / SYNCS) while its threads fetch and transform their queries,
+//     so a descent step is two shared-memory loads (~30 cycles) instead of an L1/L2 line;
+//     deeper trees keep their top 14 levels in shared memory and read the rest from global;
+//   * leaves carry no payload: a leaf's bucket is (in-level index << (levels - level)) in the
+//     padded bucket array, one bucket = x[8] y[8] z[8] = 12 aligned 16-byte loads;
+//   * the heap index of the reached leaf encodes the whole root path, so the far-side tests of
+//     the root frame (rd = 0, off = 0 => rd_new = new_off^2 exactly) are re-derived from it after
+//     the first bucket, deepest level first, as the recursion would test them: no replay of the
+//     descent and no stack for the root frame.  Only far subtrees that are actually visited
+//     run the general stack-based traversal (their own far children are rare).
+// The visit ORDER and every comparison are those of libnabo's recurseKnn, so index sets and
+// squared distances are bit-identical to the oracle for any epsilon (tests/test_gpu_icp.py).
+#ifndef SM_B200_KNN_SMEM_CUH_
+#define SM_B200_KNN_SMEM_CUH_
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+namespace dev {
+
+constexpr int kKnnCtaThreads = 1024;
+constexpr int kKnnSmemLevels = 14;                     // 2^14 slots * 9 B = 144 KB
+constexpr int kKnnMaxStack = 32;
+
+struct SmemTree {
+  const double* s_cut;      // shared memory
+  const uint8_t* s_dim;     // shared memory
+  int n_smem;               // heap indices < n_smem are resident in shared memory
+  const double* g_cut;      // global (all nodes)
+  const uint8_t* g_dim;
+  const double* pb;         // padded buckets
+  int levels;
+};
+
+// ---- mbarrier + bulk async copy (TMA engine, non-tensor form) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// shared-memory footprint of the staged tree: cut[slots] + dim[slots] + barrier + 16 doubles
+__host__ __device__ __forceinline__ int knn_smem_slots(int levels) {
+  const int ls = levels < kKnnSmemLevels ? levels : kKnnSmemLevels;
+  const int n = 1 << ls;
+  return n < 16 ? 16 : n;
+}
+__host__ __device__ __forceinline__ size_t knn_smem_bytes(int levels) {
+  return (size_t)knn_smem_slots(levels) * 9 + 8 + 16 * sizeof(double) + 16;
+}
+
+// Called by ALL threads of the CTA (contains __syncthreads).  Thread 0 arms the barrier and
+// issues the copies; everyone may then do independent work and must call mbar_wait(bar, 0)
+// before the first tree access.
+__device__ __forceinline__ SmemTree stage_tree(const KdCompact& t, unsigned char* smem, uint64_t** bar_out,
+                                               double** extra_out) {
+  const int slots = knn_smem_slots(t.levels);
+  double* s_cut = reinterpret_cast<double*>(smem);
+  uint8_t* s_dim = smem + (size_t)slots * 8;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)slots * 9);
+  *extra_out = reinterpret_cast<double*>(bar + 1);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_proxy_async_smem(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t cut_bytes = (uint32_t)slots * 8u, dim_bytes = (uint32_t)slots;
+    mbar_arrive_expect_tx(bar, cut_bytes + dim_bytes);
+    constexpr uint32_t kChunk = 32768u;
+    for (uint32_t off = 0; off < cut_bytes; off += kChunk)
+      bulk_copy_g2s(smem + off, reinterpret_cast<const unsigned char*>(t.cut) + off,
+                    cut_bytes - off < kChunk ? cut_bytes - off : kChunk, bar);
+    bulk_copy_g2s(s_dim, t.dim, dim_bytes, bar);
+  }
+  *bar_out = bar;
+  SmemTree st;
+  st.s_cut = s_cut; st.s_dim = s_dim; st.n_smem = slots;
+  st.g_cut = t.cut; st.g_dim = t.dim; st.pb = t.pb; st.levels = t.levels;
+  return st;
+}
+
+template <bool kAllSmem>
+__device__ __forceinline__ void tree_node(const SmemTree& t, int h, double& cut, int& dim) {
+  if (kAllSmem || h < t.n_smem) { cut = t.s_cut[h]; dim = t.s_dim[h]; }
+  else { cut = __ldg(t.g_cut + h); dim = __ldg(t.g_dim + h); }
+}
+
+__device__ __forceinline__ double2 ldg_nc_f64x2(const void* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// One padded bucket: 12 back-to-back 16-byte loads, 8 squared distances in the reference's
+// operation order, then a tournament on the bit patterns in which the lower index wins ties
+// (libnabo walks the bucket in order and replaces the head on a strict '<').  Padding entries
+// are +inf: their distance is +inf or NaN, never below the head.
+__device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int bucket, double qx, double qy,
+                                            double qz, double& head, int& best) {
+  const char* base = reinterpret_cast<const char*>(pb + (int64_t)bucket * 24);
+  double2 v[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) v[k] = ldg_nc_f64x2(base + 16 * k);
+  unsigned long long key[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double x = (k & 1) ? v[k >> 1].y : v[k >> 1].x;
+    const double y = (k & 1) ? v[4 + (k >> 1)].y : v[4 + (k >> 1)].x;
+    const double z = (k & 1) ? v[8 + (k >> 1)].y : v[8 + (k >> 1)].x;
+    const double dx = dsub(qx, x), dy = dsub(qy, y), dz = dsub(qz, z);
+    key[k] = (unsigned long long)__double_as_longlong(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
+  }
+  int arg[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) arg[k] = k;
+#pragma unroll
+  for (int step = 1; step < 8; step <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2 * step) {
+      const bool take = key[k + step] < key[k];      // strict: the lower index keeps a tie
+      key[k] = take ? key[k + step] : key[k];
+      arg[k] = take ? arg[k + step] : arg[k];
+    }
+  }
+  if (key[0] < (unsigned long long)__double_as_longlong(head)) {
+    head = __longlong_as_double((long long)key[0]);
+    best = bucket * 8 + arg[0];
+  }
+}
+
+struct KnnStackEntry {
+  double rd, ox, oy, oz;
+  int h, pad;
+};
+
+// recurseKnn on the subtree rooted at heap node h with the recursion's (rd, off) at entry:
+// near child first; a far child is pushed if it passes rd_new*(1+eps)^2 < head now (the head only
+// shrinks) and re-tested when popped, which is when the recursion tests it.
+template <bool kAllSmem>
+__device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, double qy, double qz, double me2,
+                                              int h, double rd, double ox, double oy, double oz,
+                                              double& head, int& best) {
+  KnnStackEntry stack[kKnnMaxStack];
+  int sp = 0;
+  while (true) {
+    int l = 31 - __clz(h + 1);
+    while (l < t.levels) {
+      double cut; int cd;
+      tree_node<kAllSmem>(t, h, cut, cd);
+      if (cd == 3) break;
+      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
+      const int right = q > cut ? 1 : 0;              // == (q - cut > 0) for IEEE doubles
+      const double new_off = dsub(q, cut);
+      const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+      if (dmul(rd_new, me2) < head && sp < kKnnMaxStack) {
+        KnnStackEntry e;
+        e.rd = rd_new;
+        e.ox = cd == 0 ? new_off : ox;
+        e.oy = cd == 1 ? new_off : oy;
+        e.oz = cd == 2 ? new_off : oz;
+        e.h = 2 * h + 2 - right; e.pad = 0;
+        stack[sp++] = e;
+      }
+      h = 2 * h + 1 + right;
+      ++l;
+    }
+    scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
+    bool found = false;
+    while (sp > 0) {
+      const KnnStackEntry e = stack[--sp];
+      if (dmul(e.rd, me2) < head) {
+        h = e.h; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+}
+
+// best: padded entry index (bucket * 8 + k) or -1; d2: squared distance (+inf if none)
+template <bool kAllSmem>
+__device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double qy, double qz, double me2,
+                                          int& best_out, double& d2_out) {
+  double head = __longlong_as_double(0x7ff0000000000000ll);
+  int best = -1;
+  int h = 0, l = 0;
+  while (l < t.levels) {
+    double cut; int cd;
+    tree_node<kAllSmem>(t, h, cut, cd);
+    if (cd == 3) break;
+    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+    h = 2 * h + 1 + (q > cut ? 1 : 0);
+    ++l;
+  }
+  scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
+  // Root frame.  Path node of level a: ((h+1) >> (l-a)) - 1.  rd = 0 and off = 0 along the whole
+  // root path, so rd_new(a) = 0 + (-(0*0) + new_off^2) = new_off^2 exactly.  First a mask of the
+  // levels that pass with the head of the first bucket (independent iterations), then those levels
+  // deepest first, each re-tested with the head of that moment.
+  const int hp1 = h + 1, ll = l;
+  uint32_t mask = 0u;
+#pragma unroll 2
+  for (int a = 0; a < ll; ++a) {
+    double cut; int cd;
+    tree_node<kAllSmem>(t, (hp1 >> (ll - a)) - 1, cut, cd);
+    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+    const double off = dsub(q, cut);
+    if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
+  }
+  while (mask != 0u) {
+    const int a = 31 - __clz(mask);
+    mask &= ~(1u << a);
+    double cut; int cd;
+    tree_node<kAllSmem>(t, (hp1 >> (ll - a)) - 1, cut, cd);
+    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
+    const double off = dsub(q, cut);
+    const double rd_new = dmul(off, off);
+    if (dmul(rd_new, me2) < head) {
+      const int near_p1 = hp1 >> (ll - a - 1);       // path node of level a+1, plus one
+      visit_subtree<kAllSmem>(t, qx, qy, qz, me2, (near_p1 ^ 1) - 1, rd_new, cd == 0 ? off : 0.0,
+                              cd == 1 ? off : 0.0, cd == 2 ? off : 0.0, head, best);
+    }
+  }
+  best_out = best;
+  d2_out = head;
+}
+
+}  // namespace dev
+}  // namespace smb
+
+#endif  // SM_B200_KNN_SMEM_CUH_

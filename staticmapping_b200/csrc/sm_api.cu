@@ -157,11 +157,8 @@ struct IcpOptions {
   bool disable_convergence_check = false;
   bool profile_kernels = false;
   bool use_graphs = true;
-  int32_t debug_knn_mode = 0;
-  bool resort_by_visits = false;   // measured slower (2.19 vs 2.00 ms): spatial coherence matters more
+  int32_t knn_queries_per_cta = 0; // phase A geometry: 0 = spread over all SMs, else queries per 1024-thread CTA
   // type 1 (IcpUsingPointMatcher stand-in) only, icp_pointmatcher.cc:166-247
-  bool knn_refill = false;         // phase A work sharing (icp.cu icp_knn_kernel): measured SLOWER (777 vs 1050
-                                   // alignments/s, 2.26 vs 1.87 ms k-NN per alignment); kept as an option
   float reading_sample_prob = 0.9f;      // RandomSamplingDataPointsFilter prob (:173)
   float accept_min_score = 0.6f;         // Align returns false below it (:145)
   int32_t sample_seed = 1;
@@ -191,7 +188,7 @@ struct sm_handle {
   double final_score = 0.0;
   sm_align_info info;
   // device memory
-  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, src_g0, src_sort, nodes, leaf_order, bpts, bnrm, slot, d2, hist,
+  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, src_g0, src_sort, nodes, leaf_order, bpts, bnrm, ccut, cdim, cpb, cpn, slot, d2, hist,
       cand_idx, cand_key, cand_cnt, partials, mean_partials, state, guess, kdws;
   int64_t n_source = 0, n_target = 0, sstride = 0, tstride = 0;
   bool has_source = false, has_target = false;
@@ -233,9 +230,7 @@ const OptionDef kIcpOptions[] = {
     {"disable_convergence_check", kOptBool, offsetof(IcpOptions, disable_convergence_check)},
     {"profile_kernels", kOptBool, offsetof(IcpOptions, profile_kernels)},
     {"use_graphs", kOptBool, offsetof(IcpOptions, use_graphs)},
-    {"debug_knn_mode", kOptInt, offsetof(IcpOptions, debug_knn_mode)},
-    {"resort_by_visits", kOptBool, offsetof(IcpOptions, resort_by_visits)},
-    {"knn_refill", kOptBool, offsetof(IcpOptions, knn_refill)},
+    {"knn_queries_per_cta", kOptInt, offsetof(IcpOptions, knn_queries_per_cta)},
     {"reading_sample_prob", kOptFloat, offsetof(IcpOptions, reading_sample_prob)},
     {"accept_min_score", kOptFloat, offsetof(IcpOptions, accept_min_score)},
     {"sample_seed", kOptInt, offsetof(IcpOptions, sample_seed)},
@@ -402,11 +397,13 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->src_sort.reserve((size_t)h->sstride * 24 + radix_sort_scratch_bytes(ns, 1) + 1024));
   H_RC(h->nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
-  H_RC(h->bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
-  H_RC(h->bnrm.reserve((size_t)nt * sizeof(BucketNormal)));
-  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + (size_t)ns + 64));
+  H_RC(h->ccut.reserve(kd_compact_node_slots(levels) * sizeof(double)));
+  H_RC(h->cdim.reserve(kd_compact_node_slots(levels)));
+  H_RC(h->cpb.reserve(kd_compact_bucket_entries(levels) * 3 * sizeof(double)));
+  H_RC(h->cpn.reserve(kd_compact_bucket_entries(levels) * sizeof(BucketNormal)));
+  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + 64));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
-  H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double) + ((size_t)ceil_div(ns, 32) + 8) * sizeof(uint32_t)));
+  H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
   H_RC(h->cand_idx.reserve((size_t)nb * 512 * 8 * sizeof(double)));   // cand_terms
   H_RC(h->cand_key.reserve((size_t)nb * 512 * sizeof(unsigned long long)));
   H_RC(h->cand_cnt.reserve((size_t)nb * sizeof(uint32_t)));
@@ -422,17 +419,18 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.tgt = (double*)h->tgt.p; b.tgt_raw = (double*)h->tgt_raw.p; b.nrm = (double*)h->nrm.p;
   b.tstride = h->tstride;
   b.nodes = (KdNode*)h->nodes.p; b.leaf_order = (uint32_t*)h->leaf_order.p;
-  b.bpts = (BucketPoint*)h->bpts.p; b.bnrm = (BucketNormal*)h->bnrm.p;
+  b.ccut = (double*)h->ccut.p; b.cdim = (uint8_t*)h->cdim.p;
+  b.cpb = (double*)h->cpb.p; b.cpn = (BucketNormal*)h->cpn.p;
+  b.kc.cut = b.ccut; b.kc.dim = b.cdim; b.kc.pb = b.cpb; b.kc.pn = b.cpn; b.kc.pid = nullptr; b.kc.levels = levels;
   b.src_raw = (double*)h->src_raw.p; b.src0 = (double*)h->src0.p; b.sstride = h->sstride;
   b.src_g0 = (double*)h->src_g0.p;
   b.src_keys[0] = (uint64_t*)h->src_sort.p; b.src_keys[1] = b.src_keys[0] + h->sstride;
   b.src_vals[0] = (uint32_t*)(b.src_keys[1] + h->sstride); b.src_vals[1] = b.src_vals[0] + h->sstride;
   b.src_scratch = b.src_vals[1] + h->sstride;
   b.slot = (int32_t*)h->slot.p;
-  b.visits = (uint8_t*)((int32_t*)h->slot.p + ns); b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
+  b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
-  b.knn_claim = (uint32_t*)(b.sums + 32);
   b.cand_terms = (double*)h->cand_idx.p;
   b.cand_key = (unsigned long long*)h->cand_key.p; b.cand_cnt = (uint32_t*)h->cand_cnt.p;
   b.partials = (double*)h->partials.p; b.mean_partials = (double*)h->mean_partials.p;
@@ -444,10 +442,8 @@ int icp_begin(sm_handle* h, const double* guess) {
   const double eps = (double)h->icp.knn_epsilon;
   p.max_error2 = (1.0 + eps) * (1.0 + eps);
   p.disable_convergence = h->icp.disable_convergence_check ? 1 : 0;
-  p.debug_knn_mode = h->icp.debug_knn_mode;
-  p.knn_refill = h->icp.knn_refill ? 1 : 0;
+  p.knn_queries_per_cta = h->icp.knn_queries_per_cta;
   p.tree_levels = levels;
-  p.resort_by_visits = h->icp.resort_by_visits ? 1 : 0;
   if (levels > 24) return fail(h, SM_ERR_BAD_ARGUMENT, "target too large (tree deeper than 24 levels)");
 
   memcpy(h->host_guess, guess, 16 * sizeof(double));   // pinned: the caller's array may go away
@@ -1029,7 +1025,7 @@ int sm_destroy(sm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->src_g0, &h->src_sort, &h->nodes,
-                    &h->leaf_order, &h->bpts, &h->bnrm, &h->slot, &h->d2, &h->hist, &h->cand_idx, &h->cand_key,
+                    &h->leaf_order, &h->bpts, &h->bnrm, &h->ccut, &h->cdim, &h->cpb, &h->cpn, &h->slot, &h->d2, &h->hist, &h->cand_idx, &h->cand_key,
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1183,31 +1179,6 @@ int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
 
 const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
 
-// Diagnostics, not part of include/sm_b200.h: re-run the phase-A search of the last IcpFast Align
-// with per-thread clocks (profiles/knn_profile.py).  Host arrays of n_source entries each.
-int sm_debug_knn_profile(sm_handle* h, int identity, uint32_t* cycles, uint8_t* rounds, uint8_t* smid,
-                         unsigned long long* t0_ns, unsigned long long* t1_ns) {
-  if (!h || !cycles || !rounds || !smid || !t0_ns || !t1_ns || h->run.p.n_source <= 0) return SM_ERR_BAD_ARGUMENT;
-  H_CUDA(cudaSetDevice(h->device));
-  const size_t n = (size_t)h->run.p.n_source;
-  DevBuf d;
-  H_RC(d.reserve(n * (4 + 1 + 1 + 8 + 8) + 256));
-  unsigned long long* t0 = (unsigned long long*)d.p;
-  unsigned long long* t1 = t0 + n;
-  uint32_t* cyc = (uint32_t*)(t1 + n);
-  uint8_t* rd = (uint8_t*)(cyc + n);
-  uint8_t* sm = rd + n;
-  int rc = icp_knn_profile(h->run.b, h->run.p, identity, cyc, rd, sm, t0, t1, h->stream);
-  if (rc == 0 && (cudaMemcpyAsync(cycles, cyc, n * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                  cudaMemcpyAsync(rounds, rd, n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                  cudaMemcpyAsync(smid, sm, n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                  cudaMemcpyAsync(t0_ns, t0, n * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                  cudaMemcpyAsync(t1_ns, t1, n * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                  cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = SM_ERR_CUDA;
-  d.release();
-  return rc;
-}
-
 // Diagnostics, not part of include/sm_b200.h: clock64 stamps of the sections of the last
 // icp_finish_kernel of the last IcpFast Align (profiles/finish_sections.py).
 int sm_debug_icp_stamps(const sm_handle* h, long long* out12) {
@@ -1269,17 +1240,21 @@ int sm_calculate_normals(int device, const double* points, int64_t n, double* ou
 
 int sm_knn1(int device, const double* target, int64_t nt, const double* query, int64_t nq,
             double epsilon, int bucket, int32_t* ids, double* d2) {
-  if (!target || !query || nt <= 0 || nq < 0 || bucket < 2 || bucket > 16) return SM_ERR_BAD_ARGUMENT;
+  // buckets hold at most 8 points (one padded bucket = x[8] y[8] z[8]); libnabo's default is 8
+  if (!target || !query || nt <= 0 || nt > (1 << 30) || nq < 0 || nq > (1 << 30) || bucket < 2 || bucket > 8 ||
+      !(epsilon >= 0.0))
+    return SM_ERR_BAD_ARGUMENT;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
   SMB_CUDA_OK(cudaSetDevice(device));
   cudaStream_t s = nullptr;
   const int64_t ts = pad64(nt), qs = pad64(nq > 0 ? nq : 1);
   const int levels = kd_num_levels((int)nt, bucket);
-  DevBuf stage, tgt, qry, nodes, order, bpts, kdws, ids_d, d2_d;
+  if (levels > 24) return SM_ERR_BAD_ARGUMENT;
+  DevBuf stage, tgt, qry, nodes, order, kdws, ids_d, d2_d, ccut, cdim, cpb, cpid;
   int rc = 0;
   auto cleanup = [&]() {
-    DevBuf* bufs[] = {&stage, &tgt, &qry, &nodes, &order, &bpts, &kdws, &ids_d, &d2_d};
+    DevBuf* bufs[] = {&stage, &tgt, &qry, &nodes, &order, &kdws, &ids_d, &d2_d, &ccut, &cdim, &cpb, &cpid};
     for (DevBuf* b : bufs) b->release();
   };
 #define K_OK(expr) do { if ((rc = (expr)) != 0) { cleanup(); return rc < 0 ? rc : SM_ERR_CUDA; } } while (0)
@@ -1289,8 +1264,11 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_OK(qry.reserve((size_t)3 * qs * sizeof(double)));
   K_OK(nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   K_OK(order.reserve((size_t)nt * sizeof(uint32_t)));
-  K_OK(bpts.reserve((size_t)(nt + 8) * sizeof(BucketPoint)));
   K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)nt, bucket)));
+  K_OK(ccut.reserve(kd_compact_node_slots(levels) * sizeof(double)));
+  K_OK(cdim.reserve(kd_compact_node_slots(levels)));
+  K_OK(cpb.reserve(kd_compact_bucket_entries(levels) * 3 * sizeof(double)));
+  K_OK(cpid.reserve(kd_compact_bucket_entries(levels) * sizeof(int32_t)));
   K_OK(ids_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(int32_t)));
   K_OK(d2_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
   K_CUDA(cudaMemcpyAsync(stage.p, target, (size_t)3 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1299,14 +1277,18 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_OK(knn_configure());
   KdWorkspace ws;
   ws.carve(kdws.p, (int)nt, bucket);
-  K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s));
-  K_OK(kd_fill_buckets((const double*)tgt.p, ts, nullptr, 0, (const uint32_t*)order.p, (int)nt,
-                       (BucketPoint*)bpts.p, nullptr, s));
+  K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s,
+                (double*)ccut.p, (uint8_t*)cdim.p));
+  K_OK(kd_compact_buckets((const double*)tgt.p, ts, nullptr, 0, (const uint32_t*)order.p, (int)nt, bucket, levels,
+                          (double*)cpb.p, nullptr, (int32_t*)cpid.p, s));
   if (nq > 0) {
+    KdCompact kc;
+    kc.cut = (const double*)ccut.p; kc.dim = (const uint8_t*)cdim.p; kc.pb = (const double*)cpb.p;
+    kc.pn = nullptr; kc.pid = (const int32_t*)cpid.p; kc.levels = levels;
     K_CUDA(cudaMemcpyAsync(stage.p, query, (size_t)3 * nq * sizeof(double), cudaMemcpyHostToDevice, s));
     deinterleave3_kernel<<<ceil_div(nq, 256), 256, 0, s>>>((const double*)stage.p, (double*)qry.p, qs, (int)nq);
-    K_OK(knn_query((const KdNode*)nodes.p, (const BucketPoint*)bpts.p, (const double*)qry.p, qs,
-                   (int)nq, (1.0 + epsilon) * (1.0 + epsilon), levels, (int32_t*)ids_d.p, (double*)d2_d.p, s));
+    K_OK(knn_query(kc, (const double*)qry.p, qs, (int)nq, (1.0 + epsilon) * (1.0 + epsilon), (int32_t*)ids_d.p,
+                   (double*)d2_d.p, s));
     K_CUDA(cudaMemcpyAsync(ids, ids_d.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     K_CUDA(cudaMemcpyAsync(d2, d2_d.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, s));
   }

@@ -24,6 +24,37 @@ def test_knn_index_sets_bit_exact(nt, nq, eps):
     assert np.array_equal(d2_g, d2_o)          # bit-exact squared distances
 
 
+@pytest.mark.parametrize("bucket", [2, 3, 4, 5, 7])
+def test_knn_other_bucket_sizes(bucket):
+    # libnabo's bucketSize parameter; one padded bucket of the compact layout holds up to 8 points
+    rng = np.random.default_rng(100 + bucket)
+    T = rng.normal(size=(3000, 3)) * np.array([20.0, 10.0, 2.0])
+    Q = rng.normal(size=(4000, 3)) * np.array([22.0, 11.0, 2.5])
+    for eps in (0.0, 3.16):
+        ids_o, d2_o = O.knn1(T, Q, epsilon=eps, bucket_size=bucket)
+        ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, bucket_size=bucket)
+        assert np.array_equal(ids_g, ids_o)
+        assert np.array_equal(d2_g, d2_o)
+
+
+def test_knn_bucket_above_8_is_rejected():
+    T = np.zeros((100, 3)); Q = np.zeros((10, 3))
+    with pytest.raises(RuntimeError):
+        smb.knn1(T, Q, bucket_size=16)
+
+
+@pytest.mark.parametrize("eps", [0.0, 3.16])
+def test_knn_deep_tree_top_levels_in_shared_memory(eps):
+    # 300 000 points = 16 levels: the top 14 are staged in shared memory, the rest is read from global
+    rng = np.random.default_rng(77)
+    T = rng.normal(size=(300_000, 3)) * np.array([30.0, 30.0, 3.0])
+    Q = rng.normal(size=(30_000, 3)) * np.array([33.0, 33.0, 3.5])
+    ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
+    ids_g, d2_g = smb.knn1(T, Q, epsilon=eps)
+    assert np.array_equal(ids_g, ids_o)
+    assert np.array_equal(d2_g, d2_o)
+
+
 def test_knn_duplicates_and_ties():
     rng = np.random.default_rng(5)
     base = np.round(rng.normal(size=(300, 3)) * 4.0, 1)       # many exact duplicates
