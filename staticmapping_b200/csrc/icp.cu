@@ -144,13 +144,13 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 
 // -------------------------------------------------------------------------------- phase A
 // ApplyTransform + FindClosests (icp_fast.cc:486-493, 169-180) + the 2048-bin histogram of the
-// squared distances.  Persistent CTAs of 1024 threads, one per SM; each stages the tree's node
-// arrays into shared memory with bulk async copies (knn_smem.cuh) while its threads load and
-// transform their queries, then every thread searches its queries (contiguous, Morton-ordered
-// range per CTA, so neighbouring threads walk the same nodes and buckets).
+// squared distances.  One query per thread over a contiguous, Morton-ordered range per CTA
+// (neighbouring threads walk the same nodes and buckets); every CTA stages the top levels of the
+// tree into shared memory with bulk async copies while its threads load and transform their
+// queries (knn_smem.cuh).
 template <bool kAllSmem>
-__global__ void __launch_bounds__(kKnnCtaThreads, 1)
-icp_knn_smem_kernel(IcpBuffers b, IcpParams p, int per_cta) {
+__global__ void __launch_bounds__(kKnnCtaThreads)
+icp_knn_kernel(IcpBuffers b, IcpParams p, int per_cta) {
   extern __shared__ __align__(128) unsigned char knn_smem[];
   if (b.state->done) return;
   uint64_t* bar; double* T;
@@ -161,8 +161,7 @@ icp_knn_smem_kernel(IcpBuffers b, IcpParams p, int per_cta) {
   int i = begin + threadIdx.x;
   double px = 0.0, py = 0.0, pz = 0.0;
   if (i < end) transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
-  mbar_wait(bar, 0);                       // tree resident (every thread waits: the CTA must not
-                                           // retire while the copy engine still writes its smem)
+  mbar_wait(bar, 0);      // every thread waits: the CTA must not retire while the copy engine writes its smem
   while (i < end) {
     int slot; double d2;
     knn1_smem<kAllSmem>(tree, px, py, pz, p.max_error2, slot, d2);
@@ -265,9 +264,9 @@ icp_accum_kernel(IcpBuffers b, IcpParams p) {
 }
 
 template <bool kAllSmem>
-__global__ void __launch_bounds__(kKnnCtaThreads, 1)
-knn_query_smem_kernel(KdCompact kc, const double* __restrict__ query, int64_t qstride, int nq,
-                      double max_error2, int per_cta, int32_t* __restrict__ ids, double* __restrict__ d2) {
+__global__ void __launch_bounds__(kKnnCtaThreads)
+knn_query_kernel(KdCompact kc, const double* __restrict__ query, int64_t qstride, int nq,
+                 double max_error2, int per_cta, int32_t* __restrict__ ids, double* __restrict__ d2) {
   extern __shared__ __align__(128) unsigned char knn_smem[];
   uint64_t* bar; double* extra;
   const SmemTree tree = stage_tree(kc, knn_smem, &bar, &extra);
@@ -285,6 +284,7 @@ knn_query_smem_kernel(KdCompact kc, const double* __restrict__ query, int64_t qs
 
 int icp_accum_blocks(int n_source) { return ceil_div(n_source, kAccTile); }
 
+
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream) {
@@ -294,31 +294,19 @@ int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int
   return 0;
 }
 
-// Launch geometry of the shared-memory-tree search kernels: `per_cta` consecutive queries per CTA.
-// queries_per_cta == 0 spreads the queries over all 148 SMs (lowest latency for one alignment in
-// flight: 120 000 queries = 148 CTAs x 26 warps); a positive value packs that many queries per
-// CTA (1024 fills a CTA and leaves whole SMs to the kernels of other alignments in flight).
+// Launch geometry of the search kernels: `per_cta` consecutive queries per 256-thread CTA.
+// queries_per_cta == 0: one query per thread (120 000 queries = 469 CTAs, ~3 per SM, all
+// resident at once); a larger value makes a CTA loop over its range, which amortises the staging
+// of the tree top over more queries.
 static void knn_geometry(int nq, int queries_per_cta, int* grid, int* per_cta) {
-  int per = queries_per_cta > 0 ? queries_per_cta : ceil_div(nq, kNumSMs);
+  int per = queries_per_cta > 0 ? queries_per_cta : kKnnCtaThreads;
   per = ((per + 31) / 32) * 32;
   if (per < 64) per = 64;
   *per_cta = per;
   *grid = ceil_div(nq, per);
 }
 
-static bool g_knn_attr_set[64] = {};   // per device (function attributes are per device)
-int knn_configure() {
-  int dev = 0;
-  SMB_CUDA_OK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && g_knn_attr_set[dev]) return 0;
-  const int max_bytes = (int)knn_smem_bytes(kKnnSmemLevels);
-  SMB_CUDA_OK(cudaFuncSetAttribute(icp_knn_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-  SMB_CUDA_OK(cudaFuncSetAttribute(icp_knn_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-  SMB_CUDA_OK(cudaFuncSetAttribute(knn_query_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-  SMB_CUDA_OK(cudaFuncSetAttribute(knn_query_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-  if (dev >= 0 && dev < 64) g_knn_attr_set[dev] = true;
-  return 0;
-}
+int knn_configure() { return 0; }   // the staged tree top needs < 48 KB of dynamic shared memory: no opt-in
 
 int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
               int32_t* ids, double* d2, cudaStream_t stream) {
@@ -327,9 +315,9 @@ int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq,
   knn_geometry(nq, 0, &grid, &per);
   const size_t smem = knn_smem_bytes(kc.levels);
   if (kc.levels <= kKnnSmemLevels)
-    knn_query_smem_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
+    knn_query_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
   else
-    knn_query_smem_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
+    knn_query_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -369,9 +357,9 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_it
   for (int it = 0; it < count; ++it) {
     if (events) cudaEventRecord(events[4 * it + 0], stream);
     if (p.tree_levels <= kKnnSmemLevels)
-      icp_knn_smem_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+      icp_knn_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
     else
-      icp_knn_smem_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+      icp_knn_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
     if (events) cudaEventRecord(events[4 * it + 1], stream);
     icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
     if (events) cudaEventRecord(events[4 * it + 2], stream);

@@ -91,7 +91,7 @@ struct IcpParams {
   double max_error2;       // (1+eps)^2
   int disable_convergence;
   int tree_levels;         // kd_num_levels(n_target, 8): depth of the root-to-leaf path
-  int knn_queries_per_cta; // phase A: 0 = spread the queries over all SMs, else queries per 1024-thread CTA
+  int knn_queries_per_cta; // phase A: 0 = one query per thread, else queries per 256-thread CTA
 };
 
 struct IcpBuffers {
@@ -141,7 +141,6 @@ void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, c
 // stand-alone k-NN over an already built tree (compact layout incl. pid): ids = original indices
 int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
               int32_t* ids, double* d2, cudaStream_t stream);
-// once per process and device context: opt the search kernels into > 48 KB of dynamic shared memory
 int knn_configure();
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,

@@ -3,19 +3,20 @@
 // the node arrays resident in SHARED MEMORY.
 //
 // B200 formulation
-//   * a ~107 k-point target has 14 inner levels = 16 383 nodes; as {cut f64}[h] + {dim u8}[h]
-//     that is 144 KB, which fits the 227 KB of one SM.  Each (persistent) CTA stages the arrays
-//     once with bulk async copies (cp.async.bulk.shared::cluster.global + mbarrier
-//     complete_tx; SASS UBLKCP / SYNCS) while its threads fetch and transform their queries,
-//     so a descent step is two shared-memory loads (~30 cycles) instead of an L1/L2 line;
-//     deeper trees keep their top 14 levels in shared memory and read the rest from global;
+//   * nodes are {cut f64}[h] + {dim u8}[h] in heap order.  Every CTA stages the TOP levels
+//     (kKnnSmemLevels = 11: 2047 nodes, 18 KB — the part of the tree every query walks) into
+//     shared memory with bulk async copies (cp.async.bulk.shared::cluster.global + mbarrier
+//     complete_tx; SASS UBLKCP / SYNCS) while its threads fetch and transform their queries;
+//     the deeper levels are read through the read-only path (L1).  Staging all 14 inner levels
+//     of a ~107 k-point target (144 KB, one 1024-thread CTA per SM) was measured too: the same
+//     57-60 us per launch, but 850 instead of ~1000 alignments/s with 16 alignments in flight,
+//     because one CTA per SM leaves no room for the kernels of other alignments;
 //   * leaves carry no payload: a leaf's bucket is (in-level index << (levels - level)) in the
 //     padded bucket array, one bucket = x[8] y[8] z[8] = 12 aligned 16-byte loads;
-//   * the heap index of the reached leaf encodes the whole root path, so the far-side tests of
-//     the root frame (rd = 0, off = 0 => rd_new = new_off^2 exactly) are re-derived from it after
-//     the first bucket, deepest level first, as the recursion would test them: no replay of the
-//     descent and no stack for the root frame.  Only far subtrees that are actually visited
-//     run the general stack-based traversal (their own far children are rare).
+//   * the heap index of a reached leaf encodes its whole path, so the far-side tests of a frame
+//     are re-derived from it after the bucket, deepest level first, as the recursion would test
+//     them (knn1_frames): no per-level bookkeeping during a descent, and the frame stack is
+//     touched only by nested far visits.
 // The visit ORDER and every comparison are those of libnabo's recurseKnn, so index sets and
 // squared distances are bit-identical to the oracle for any epsilon (tests/test_gpu_icp.py).
 #ifndef SM_B200_KNN_SMEM_CUH_
@@ -27,9 +28,15 @@
 namespace smb {
 namespace dev {
 
-constexpr int kKnnCtaThreads = 1024;
-constexpr int kKnnSmemLevels = 14;                     // 2^14 slots * 9 B = 144 KB
-constexpr int kKnnMaxStack = 32;
+#ifndef SMB_KNN_THREADS
+#define SMB_KNN_THREADS 256
+#endif
+#ifndef SMB_KNN_SMEM_LEVELS
+#define SMB_KNN_SMEM_LEVELS 11
+#endif
+constexpr int kKnnCtaThreads = SMB_KNN_THREADS;        // threads (= traversal slots) per CTA
+constexpr int kKnnSmemLevels = SMB_KNN_SMEM_LEVELS;    // tree levels staged in shared memory: 2^11 * 9 B = 18 KB
+constexpr int kKnnCtasPerSm = 1024 / kKnnCtaThreads;   // 64 registers per thread -> 1024 threads per SM
 
 struct SmemTree {
   const double* s_cut;      // shared memory
@@ -73,7 +80,7 @@ __host__ __device__ __forceinline__ int knn_smem_slots(int levels) {
   return n < 16 ? 16 : n;
 }
 __host__ __device__ __forceinline__ size_t knn_smem_bytes(int levels) {
-  return (size_t)knn_smem_slots(levels) * 9 + 8 + 16 * sizeof(double) + 16;
+  return (size_t)knn_smem_slots(levels) * 9 + 16 + 16 * sizeof(double);   // nodes, barrier (+pad), 16 doubles
 }
 
 // Called by ALL threads of the CTA (contains __syncthreads).  Thread 0 arms the barrier and
@@ -85,7 +92,7 @@ __device__ __forceinline__ SmemTree stage_tree(const KdCompact& t, unsigned char
   double* s_cut = reinterpret_cast<double*>(smem);
   uint8_t* s_dim = smem + (size_t)slots * 8;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)slots * 9);
-  *extra_out = reinterpret_cast<double*>(bar + 1);
+  *extra_out = reinterpret_cast<double*>(bar + 2);
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_proxy_async_smem(); }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -153,6 +160,7 @@ __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int b
   }
 }
 
+constexpr int kKnnMaxStack = 32;
 struct KnnStackEntry {
   double rd, ox, oy, oz;
   int h, pad;

@@ -157,7 +157,7 @@ struct IcpOptions {
   bool disable_convergence_check = false;
   bool profile_kernels = false;
   bool use_graphs = true;
-  int32_t knn_queries_per_cta = 0; // phase A geometry: 0 = spread over all SMs, else queries per 1024-thread CTA
+  int32_t knn_queries_per_cta = 0; // phase A geometry: 0 = one query per thread, else queries per 256-thread CTA
   // type 1 (IcpUsingPointMatcher stand-in) only, icp_pointmatcher.cc:166-247
   float reading_sample_prob = 0.9f;      // RandomSamplingDataPointsFilter prob (:173)
   float accept_min_score = 0.6f;         // Align returns false below it (:145)
@@ -1178,6 +1178,7 @@ int sm_get_align_info(const sm_handle* h, sm_align_info* out) {
 }
 
 const char* sm_last_error(const sm_handle* h) { return h ? h->error.c_str() : "null handle"; }
+
 
 // Diagnostics, not part of include/sm_b200.h: clock64 stamps of the sections of the last
 // icp_finish_kernel of the last IcpFast Align (profiles/finish_sections.py).
