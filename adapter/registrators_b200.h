@@ -11,14 +11,25 @@
 #ifndef ADAPTER_REGISTRATORS_B200_H_
 #define ADAPTER_REGISTRATORS_B200_H_
 
+#include <stdio.h>
+
+#include <algorithm>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "registrators/interface.h"
 #include "sm_b200.h"
 
 namespace static_map {
 namespace registrator {
+
+// float option -> text without losing bits (std::to_string prints 6 fixed decimals)
+inline std::string OptionText(float v) {
+  char buf[32];
+  snprintf(buf, sizeof(buf), "%.9g", static_cast<double>(v));
+  return buf;
+}
 
 class IcpFastB200 : public Interface {
  public:
@@ -43,8 +54,7 @@ class IcpFastB200 : public Interface {
 
   void InitWithOptions() override {
     Check(sm_set_option(handle_, "max_iteration", std::to_string(options_.max_iteration).c_str()));
-    Check(sm_set_option(handle_, "dist_outlier_ratio",
-                        std::to_string(options_.dist_outlier_ratio).c_str()));
+    Check(sm_set_option(handle_, "dist_outlier_ratio", OptionText(options_.dist_outlier_ratio).c_str()));
   }
 
   // icp_fast.cc:421-425
@@ -71,6 +81,11 @@ class IcpFastB200 : public Interface {
     this->final_score_ = sm_get_fitness_score(handle_);
     return rc == 1;
   }
+
+  // hooks of AlignBatch (below)
+  sm_handle* handle() const { return handle_; }
+  void PrepareBatch() {}
+  void SetFinalScore(double score) { this->final_score_ = score; }
 
  private:
   void Check(int rc) const {
@@ -104,17 +119,25 @@ class FloatCloudMatcherB200 : public Interface {
       if (kType == SM_TYPE_NDT) return false;                 // ndt.cc:40-42
       CHECK(this->source_cloud_ && this->target_cloud_);      // NdtWithGicp dereferences them
     }
+    PrepareBatch();
+    const int rc = sm_align(handle_, guess.data(), result.data());
+    CheckRc(rc);
+    this->final_score_ = sm_get_fitness_score(handle_);
+    return rc == 1;
+  }
+
+  // hooks of AlignBatch (below): the clouds kept by the base class go to the engine
+  sm_handle* handle() const { return handle_; }
+  void PrepareBatch() {
+    CHECK(this->source_cloud_ && this->target_cloud_);
     const auto& s = this->source_cloud_->GetInnerCloud()->points;
     const auto& t = this->target_cloud_->GetInnerCloud()->points;
     CheckRc(sm_set_input_source_f32(handle_, &s[0].x, static_cast<int64_t>(s.size()),
                                     sizeof(data::InnerPointType)));
     CheckRc(sm_set_input_target_f32(handle_, &t[0].x, static_cast<int64_t>(t.size()),
                                     sizeof(data::InnerPointType)));
-    const int rc = sm_align(handle_, guess.data(), result.data());
-    CheckRc(rc);
-    this->final_score_ = sm_get_fitness_score(handle_);
-    return rc == 1;
   }
+  void SetFinalScore(double score) { this->final_score_ = score; }
 
  protected:
   void CheckRc(int rc) const { CHECK_GE(rc, 0) << "sm_b200: " << sm_last_error(handle_); }
@@ -136,7 +159,7 @@ class NdtWithGicpB200 : public FloatCloudMatcherB200<SM_TYPE_NDT_WITH_GICP> {
   void InitWithOptions() override {
     CheckRc(sm_set_option(handle_, "use_ndt", options_.use_ndt ? "1" : "0"));
     CheckRc(sm_set_option(handle_, "using_voxel_filter", options_.using_voxel_filter ? "1" : "0"));
-    CheckRc(sm_set_option(handle_, "voxel_resolution", std::to_string(options_.voxel_resolution).c_str()));
+    CheckRc(sm_set_option(handle_, "voxel_resolution", OptionText(options_.voxel_resolution).c_str()));
   }
 
  private:
@@ -167,6 +190,35 @@ inline void MotionCompensationB200(const data::InnerCloudType& raw_cloud, const 
   CHECK_EQ(rc, 0) << "MotionCompensation: factor outside [0, 1] (common/math.h:201) or CUDA failure";
 }
 
+// Batched CloseLoop / SubmapPairMatch: the reference starts one task (TBB / thread pool) per candidate
+// pair, each constructing a matcher and calling Align (back_end/loop_detector.cc:216-228,304-308;
+// builder/map_builder.cc:655,706-708).  With the engine ONE thread aligns all the candidates: the
+// matchers have their clouds set as usual, AlignBatch enqueues every Align before it waits for the
+// first result.  ok[i] / results[i] are what matchers[i]->Align(guesses[i], results[i]) would give.
+template <typename MatcherB200>
+inline void AlignBatch(const std::vector<MatcherB200*>& matchers, const std::vector<Eigen::Matrix4d>& guesses,
+                       std::vector<Eigen::Matrix4d>* results, std::vector<bool>* ok) {
+  CHECK(results && ok);
+  CHECK_EQ(matchers.size(), guesses.size());
+  const size_t n = matchers.size();
+  std::vector<sm_handle*> handles(n);
+  std::vector<double> g(16 * n), r(16 * n);
+  std::vector<int32_t> rc(n);
+  for (size_t i = 0; i < n; ++i) {
+    matchers[i]->PrepareBatch();
+    handles[i] = matchers[i]->handle();
+    std::copy(guesses[i].data(), guesses[i].data() + 16, g.begin() + 16 * i);   // column-major, like Eigen
+  }
+  sm_align_batch(handles.data(), static_cast<int32_t>(n), g.data(), r.data(), rc.data());
+  results->resize(n); ok->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    CHECK_GE(rc[i], 0) << "sm_b200: " << sm_last_error(handles[i]);               // reference aborts via glog
+    std::copy(r.begin() + 16 * i, r.begin() + 16 * (i + 1), (*results)[i].data());
+    (*ok)[i] = rc[i] != 0;
+    matchers[i]->SetFinalScore(sm_get_fitness_score(handles[i]));
+  }
+}
+
 // pre_processers::filter::VoxelGrid::Filter (pre_processors/filter_voxel_grid.cc:37-78) on the GPU:
 // the body of that member becomes
 //   this->FilterPrepare(cloud); registrator::VoxelGridFilterB200(*this->inner_cloud_, voxel_size_, cloud.get());
@@ -179,7 +231,17 @@ inline void VoxelGridFilterB200(const data::InnerCloudType& input, float voxel_s
   if (!input.points.empty()) {
     const int rc = sm_voxel_grid_filter(device, &input.points[0].x, static_cast<int64_t>(input.points.size()),
                                         sizeof(data::InnerPointType), voxel_size, &output->points[0].x, &m);
-    CHECK_EQ(rc, 0) << "sm_voxel_grid_filter failed (" << rc << ")";
+    // non-finite points are dropped by the engine (the reference keeps running on such input too).
+    // SM_ERR_BAD_ARGUMENT is left for a cloud spanning >= 2^21 voxels along an axis or an invalid voxel
+    // size (the reference refuses that one in ConfigsValid()): report and pass the cloud through
+    // unfiltered rather than abort the mapper; only CUDA failures are fatal.
+    CHECK_NE(rc, SM_ERR_CUDA) << "sm_voxel_grid_filter: CUDA failure";
+    CHECK_NE(rc, SM_ERR_NO_DEVICE) << "sm_voxel_grid_filter: no CUDA device (no CPU fallback)";
+    if (rc != 0) {
+      LOG(ERROR) << "sm_voxel_grid_filter refused the cloud (" << rc << "): passing it through unfiltered";
+      output->points = input.points;
+      return;
+    }
   }
   output->points.resize(m);
 }

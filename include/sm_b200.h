@@ -59,7 +59,8 @@ int sm_destroy(sm_handle* h);
  * `text` is parsed like pugixml's as_int / as_float / as_bool for the registered type.
  * Registered names, IcpFast (icp_fast.cc:411-418): knn_normal_estimate (int, unused),
  * max_iteration (int, 100), dist_outlier_ratio (float, 0.7).  Added by this engine:
- * knn_epsilon (float, 3.16 = icp_fast.cc:174), disable_convergence_check (bool, false;
+ * knn_epsilon (float, 3.16 = icp_fast.cc:174), knn_queries_per_cta (int, 0 = one query per
+ * thread; 1024 suits many alignments in flight), disable_convergence_check (bool, false;
  * fixed-iteration throughput runs), profile_kernels (bool, false; CUDA events around
  * every phase kernel, reported by sm_get_align_info), use_graphs (bool, true; replay the
  * launch sequence of an Align as CUDA graphs).  Unknown name -> SM_ERR_UNKNOWN_OPTION.
@@ -110,6 +111,36 @@ int sm_align(sm_handle* h, const double* guess_4x4, double* result_4x4);
  * IcpFast only; sm_align == async + wait. */
 int sm_align_async(sm_handle* h, const double* guess_4x4);
 int sm_align_wait(sm_handle* h, double* result_4x4);
+/* Batched Align.  The reference fans independent Align calls out to a thread pool / TBB tasks
+ * (back_end/loop_detector.cc:216-228 one task per loop-closure candidate; builder/map_builder.cc:
+ * 655,706-708 submap pairs); here ONE host thread keeps many alignments in flight on the GPU.
+ *
+ * sm_align_batch: `n` matcher instances whose SetInputSource / SetInputTarget have been called.
+ * IcpFast instances are all enqueued before the first result is awaited; the other matcher types
+ * (host-driven Newton / BFGS loops) run on up to 16 internal worker threads.  guesses / results:
+ * n x 16 doubles; rc_n[i] = what sm_align would have returned for instance i.  Returns SM_OK or the
+ * most negative rc.
+ *
+ * sm_align_pairs: `n_pairs` independent IcpFast alignments pipelined over `n_handles` instances
+ * (pair k runs on instance k % n_handles; an instance's previous result is collected right before
+ * it is given its next pair).  Host clouds are uploaded asynchronously on the instance's stream —
+ * unlike sm_set_input_*, the arrays of a pair must stay valid until sm_align_pairs returns (pinned
+ * host memory makes the copies overlap the other pipelines' kernels).  scores_n (optional) receives
+ * GetFitnessScore per pair. */
+typedef struct sm_pair {
+  const double* source_3xn;          /* SetInputSource */
+  int64_t n_source;
+  const double* target_3xn;          /* SetInputTarget (points + unit normals) */
+  const double* target_normals_3xn;
+  int64_t n_target;
+  const double* guess_4x4;           /* NULL = identity */
+  int32_t on_device;                 /* 1: the three cloud pointers are device pointers */
+  int32_t reserved;
+} sm_pair;
+int sm_align_batch(sm_handle* const* handles, int32_t n, const double* guesses_16n, double* results_16n,
+                   int32_t* rc_n);
+int sm_align_pairs(sm_handle* const* handles, int32_t n_handles, const sm_pair* pairs, int32_t n_pairs,
+                   double* results_16n, double* scores_n, int32_t* rc_n);
 /* Interface::GetFitnessScore (interface.h:100). */
 double sm_get_fitness_score(const sm_handle* h);
 
@@ -154,7 +185,8 @@ const char* sm_last_error(const sm_handle* h);
 /* ---- building blocks exposed for parity tests and for callers that hold clouds ------- */
 
 /* libnabo-compatible tree build + 1-NN (NNS::create + knn, icp_fast.cc:466-467,177-178).
- * ids: original target column, -1 if none; dists2: squared distances. */
+ * ids: original target column, -1 if none; dists2: squared distances.  bucket_size 2..8
+ * (libnabo's default is 8; one padded bucket of the search layout holds 8 points). */
 int sm_knn1(int device, const double* target_3xn, int64_t n_target, const double* query_3xn,
             int64_t n_query, double epsilon, int bucket_size, int32_t* ids, double* dists2);
 
@@ -192,8 +224,10 @@ int sm_motion_compensation_device(int device, const float* dev_points, int64_t n
  * `stride_bytes` (>= 16) apart; `out`: capacity n records of 5 packed floats; *m_out = number of
  * voxels.  Every value is bit-identical to the reference's; the ORDER of the output points is
  * ascending (ix, iy, iz), where the reference emits them in std::unordered_map iteration order.
- * SM_ERR_BAD_ARGUMENT: voxel_size <= 1e-6 (ConfigsValid, :35), a NaN/inf coordinate, or a voxel
- * index beyond +-2^20. */
+ * Points with a NaN / inf coordinate are dropped (std::lround of such a value is unspecified in the
+ * reference; one bad lidar return must not stop the mapper).  SM_ERR_BAD_ARGUMENT: voxel_size <= 1e-6
+ * (ConfigsValid, :35), or finite points that span 2^21 voxels or more along one axis (209 km at the
+ * reference's 0.1 m voxels). */
 int sm_voxel_grid_filter(int device, const float* points, int64_t n, int64_t stride_bytes,
                          float voxel_size, float* out, int64_t* m_out);
 

@@ -1,0 +1,33 @@
+/* sm_b200_debug.h — TEST HOOKS of libsm_b200.so.  Not part of the drop-in boundary (include/sm_b200.h):
+ * nothing in the reference binds these.  They let tests/ drive two pieces of product code that have no
+ * entry point of their own against INDEPENDENT implementations (numpy / scipy), so that a transcription
+ * error shared by the product and the oracle cannot pass unnoticed:
+ *   - the 6x6 solver of the ICP iteration (csrc/linalg_dev.cuh: pivoted-QR rank test, LLT, rank-reduced
+ *     minimum-norm branch, SVD fallback = SolvePossiblyUnderdeterminedLinearSystem, icp_fast.cc:204-254),
+ *     run on the device exactly as icp_finish_kernel calls it;
+ *   - the BFGS minimiser of the GICP stage (csrc/gicp_host.h: PCL's port of GSL vector_bfgs2 with the
+ *     Fletcher line search, parameters of gicp_omp_impl.hpp:218-224), run on a caller-supplied function. */
+#ifndef SM_B200_DEBUG_H_
+#define SM_B200_DEBUG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A: row-major 6x6 (symmetric in the ICP use), b: 6.  path: 0 LLT, 1 rank-reduced min-norm, 2 SVD. */
+int sm_debug_solve6(int device, const double* A_36, const double* b_6, double* x_6, int32_t* path);
+
+/* f and/or g may be NULL (value-only / gradient-only evaluations of the line search); return < 0 to abort. */
+typedef int (*sm_debug_fdf)(const double* x_6, double* f, double* g_6, void* user);
+/* Runs the GICP inner loop (gicp_omp_impl.hpp:225-240): set, then iterate + test_gradient(grad_tol) until
+ * it reports success / no progress or max_iterations.  status: 0 success, 1 still running (iteration cap),
+ * 2 no progress, -1 error. */
+int sm_debug_bfgs_minimize(sm_debug_fdf fn, void* user, double* x_6_inout, double grad_tol,
+                           int32_t max_iterations, int32_t* iterations, int32_t* evaluations, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SM_B200_DEBUG_H_ */

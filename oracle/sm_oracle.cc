@@ -651,6 +651,14 @@ void sm_oracle_check_convergence_inputs(const double* Ts, int n, int* converged)
   }
 }
 
+void sm_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int sm_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -140,6 +140,8 @@ int sm_oracle_quantile_index(int64_t n, float ratio);
 void sm_oracle_check_convergence_inputs(const double* Ts, int n, int* converged);
 
 int sm_oracle_num_threads(void);
+/* OpenMP threads of the following calls (the NDT pieces keep the reference's own 6, ndt.cc:32). */
+void sm_oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,12 @@ class AlignInfo(C.Structure):
                 ("aux", C.c_double * 4)]
 
 
+class Pair(C.Structure):
+    _fields_ = [("source", C.c_void_p), ("n_source", C.c_int64), ("target", C.c_void_p),
+                ("target_normals", C.c_void_p), ("n_target", C.c_int64), ("guess", C.c_void_p),
+                ("on_device", C.c_int32), ("reserved", C.c_int32)]
+
+
 _lib = None
 
 _DP = C.POINTER(C.c_double)
@@ -48,6 +54,8 @@ SIGNATURES = {
     "sm_align": (C.c_int, [_VP, _DP, _DP]),
     "sm_align_async": (C.c_int, [_VP, _DP]),
     "sm_align_wait": (C.c_int, [_VP, _DP]),
+    "sm_align_batch": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "sm_align_pairs": (C.c_int, [_VP, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP]),
     "sm_get_fitness_score": (C.c_double, [_VP]),
     "sm_get_align_info": (C.c_int, [_VP, C.POINTER(AlignInfo)]),
     "sm_set_stream": (C.c_int, [_VP, _VP]),
@@ -57,6 +65,9 @@ SIGNATURES = {
     "sm_motion_compensation": (C.c_int, [C.c_int, _VP, C.c_int64, C.c_int64, _DP, _VP]),
     "sm_motion_compensation_device": (C.c_int, [C.c_int, _VP, C.c_int64, C.c_int64, _DP, _VP, _VP]),
     "sm_voxel_grid_filter": (C.c_int, [C.c_int, _VP, C.c_int64, C.c_int64, C.c_float, _VP, C.POINTER(C.c_int64)]),
+    # include/sm_b200_debug.h (test hooks)
+    "sm_debug_solve6": (C.c_int, [C.c_int, _VP, _VP, _VP, _VP]),
+    "sm_debug_bfgs_minimize": (C.c_int, [_VP, _VP, _VP, C.c_double, C.c_int32, _VP, _VP, _VP]),
     "sm_device_count": (C.c_int, []),
     "sm_version": (C.c_char_p, []),
 }

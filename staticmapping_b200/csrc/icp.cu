@@ -18,6 +18,8 @@
 #include "knn_smem.cuh"
 #include "linalg_dev.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace smb {
 using namespace dev;
 namespace {
@@ -330,10 +332,12 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   mean_partial_kernel<<<nparts, 256, 0, stream>>>(b.tgt_raw, b.tstride, nt, b.mean_partials);
   center_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(b.tgt_raw, b.tgt, b.tstride, nt,
                                                       b.mean_partials, nparts, b.state);
+  nvtxRangePushA("BuildKdTree");                 // icp_fast.cc:465
   int rc = kd_build(b.tgt, b.tstride, nt, 8, ws, b.nodes, b.leaf_order, stream, b.ccut, b.cdim);
-  if (rc) return rc;
+  if (rc) { nvtxRangePop(); return rc; }
   rc = kd_compact_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, 8, p.tree_levels, b.cpb, b.cpn,
                           nullptr, stream);
+  nvtxRangePop();
   if (rc) return rc;
   icp_init_kernel<<<1, 256, 0, stream>>>(b.state, guess_dev, b.hist);
   apply_g0_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(b.src_raw, b.src_g0, b.sstride, ns, b.state,
@@ -355,16 +359,24 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_it
   knn_geometry(p.n_source, p.knn_queries_per_cta, &grid, &per);
   const size_t smem = knn_smem_bytes(p.tree_levels);
   for (int it = 0; it < count; ++it) {
+    nvtxRangePushA("Iteration");                 // REGISTER_BLOCK("Iteration"), icp_fast.cc:484
     if (events) cudaEventRecord(events[4 * it + 0], stream);
+    nvtxRangePushA("FindClosests");              // icp_fast.cc:169-180
     if (p.tree_levels <= kKnnSmemLevels)
       icp_knn_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
     else
       icp_knn_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+    nvtxRangePop();
     if (events) cudaEventRecord(events[4 * it + 1], stream);
+    nvtxRangePushA("ErrorElements");             // icp_fast.cc:92-167 (+ the sums of ComputePointToPlane)
     icp_accum_kernel<<<nb, kAccThreads, 0, stream>>>(b, p);
+    nvtxRangePop();
     if (events) cudaEventRecord(events[4 * it + 2], stream);
+    nvtxRangePushA("ComputePointToPlane");       // icp_fast.cc:256-323
     icp_finish_launch(b, p, nb, stream);
+    nvtxRangePop();
     if (events) cudaEventRecord(events[4 * it + 3], stream);
+    nvtxRangePop();
   }
   SMB_CUDA_OK(cudaGetLastError());
   return 0;

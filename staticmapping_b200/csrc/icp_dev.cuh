@@ -237,6 +237,7 @@ __device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist,
     if (lane >= o) incl += v;
   }
   if (active && lane == 31) warp_tot[w] = incl;
+  if (t == 0) { out_sm->bin = -1; out_sm->below = 0; out_sm->qi = 0; out_sm->nvalid = 0; }   // never left unset
   __syncthreads();
   uint32_t base = 0, total = 0;
 #pragma unroll
@@ -257,7 +258,6 @@ __device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist,
     }
     out_sm->qi = qi; out_sm->nvalid = (int)total;
   }
-  if (total == 0 && t == 0) { out_sm->bin = -1; out_sm->below = 0; out_sm->qi = 0; out_sm->nvalid = 0; }
   __syncthreads();
   return *out_sm;
 }

@@ -1,21 +1,35 @@
 // C ABI of libsm_b200.so (include/sm_b200.h): handles, option registry, uploads, Align.
 #include "../../include/sm_b200.h"
+#include "../../include/sm_b200_debug.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 #include "icp_dev.cuh"
 #include "kernels.h"
+#include "linalg_dev.cuh"
 #include "gicp_host.h"
 #include "ndt_host.h"
 
 namespace smb {
+
+// NVTX ranges named like the reference's timer blocks (common/performance/simple_prof.h:
+// REGISTER_FUNC in FindClosests / ErrorElements / ComputePointToPlane, REGISTER_BLOCK("Iteration"),
+// "BuildKdTree", icp_fast.cc:103,171,261,465,484), visible in nsys / ncu timelines.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_cuda_error;
 void set_cuda_error(cudaError_t e, const char* expr, const char* file, int line) {
@@ -146,6 +160,11 @@ pm_score_reduce_kernel(const uint64_t* __restrict__ keys, int n, float ratio, do
   }
 }
 
+__global__ void debug_solve6_kernel(const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x,
+                                    int* __restrict__ path) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *path = la::solve_possibly_underdetermined(A, b, x);
+}
+
 enum OptKind { kOptInt, kOptFloat, kOptBool };
 struct OptionDef { const char* name; OptKind kind; size_t offset; };
 
@@ -188,7 +207,7 @@ struct sm_handle {
   double final_score = 0.0;
   sm_align_info info;
   // device memory
-  DevBuf stage, tgt_raw, tgt, nrm, src_raw, src0, src_g0, src_sort, nodes, leaf_order, bpts, bnrm, ccut, cdim, cpb, cpn, slot, d2, hist,
+  DevBuf stage, stage_src, stage_tgt, stage_nrm, tgt_raw, tgt, nrm, src_raw, src0, src_g0, src_sort, nodes, leaf_order, bpts, bnrm, ccut, cdim, cpb, cpn, slot, d2, hist,
       cand_idx, cand_key, cand_cnt, partials, mean_partials, state, guess, kdws;
   int64_t n_source = 0, n_target = 0, sstride = 0, tstride = 0;
   bool has_source = false, has_target = false;
@@ -299,30 +318,34 @@ template <typename T>
 void key_append(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
 
 // upload (or adopt) an AoS 3xN cloud and de-interleave it into SoA [3][stride]
+// own_stage: a staging buffer used by this cloud only.  Then nothing is reused before the stream
+// has consumed it (stream order), the copy stays asynchronous and the caller's host array must
+// stay valid until the stream reaches it (sm_align_pairs); with the shared staging buffer the call
+// returns after the copy, which is the deep-copy contract of SetInputSource / SetInputTarget.
 int load_cloud(sm_handle* h, const double* pts, int64_t n, bool on_device, DevBuf& soa,
-               int64_t stride) {
+               int64_t stride, DevBuf* own_stage = nullptr) {
   H_RC(soa.reserve((size_t)(3 * stride) * sizeof(double)));
   const double* src = pts;
   if (!on_device) {
-    H_RC(h->stage.reserve((size_t)(3 * n) * sizeof(double)));
-    H_CUDA(cudaMemcpyAsync(h->stage.p, pts, (size_t)(3 * n) * sizeof(double),
-                           cudaMemcpyHostToDevice, h->stream));
-    src = (const double*)h->stage.p;
+    DevBuf& st = own_stage ? *own_stage : h->stage;
+    H_RC(st.reserve((size_t)(3 * n) * sizeof(double)));
+    H_CUDA(cudaMemcpyAsync(st.p, pts, (size_t)(3 * n) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    src = (const double*)st.p;
   }
   deinterleave3_kernel<<<ceil_div(n, 256), 256, 0, h->stream>>>(src, (double*)soa.p, stride, (int)n);
   H_CUDA(cudaGetLastError());
-  if (!on_device) H_CUDA(cudaStreamSynchronize(h->stream));  // stage buffer is reused
+  if (!on_device && !own_stage) H_CUDA(cudaStreamSynchronize(h->stream));  // the shared stage buffer is reused
   return 0;
 }
 
-int set_source(sm_handle* h, const double* pts, int64_t n, bool on_device) {
+int set_source(sm_handle* h, const double* pts, int64_t n, bool on_device, bool async = false) {
   if (!h) return SM_ERR_BAD_ARGUMENT;
   if (!pts || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInputSource: empty cloud");
   if (n > (1 << 30)) return fail(h, SM_ERR_BAD_ARGUMENT, "SetInputSource: too many points");
   H_CUDA(cudaSetDevice(h->device));
   H_CUDA(cudaEventRecord(h->ev_up[0], h->stream));
   h->sstride = pad64(n);
-  H_RC(load_cloud(h, pts, n, on_device, h->src_raw, h->sstride));
+  H_RC(load_cloud(h, pts, n, on_device, h->src_raw, h->sstride, async ? &h->stage_src : nullptr));
   H_CUDA(cudaEventRecord(h->ev_up[1], h->stream));
   h->up_src = true;
   h->n_source = n;
@@ -330,7 +353,7 @@ int set_source(sm_handle* h, const double* pts, int64_t n, bool on_device) {
   return 0;
 }
 
-int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bool on_device) {
+int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bool on_device, bool async = false) {
   if (!h) return SM_ERR_BAD_ARGUMENT;
   if (!pts || n <= 0) return fail(h, SM_ERR_MISSING_INPUT, "SetInputTarget: empty cloud");
   if (h->type == SM_TYPE_FAST_ICP && !nrm)
@@ -339,8 +362,8 @@ int set_target(sm_handle* h, const double* pts, const double* nrm, int64_t n, bo
   H_CUDA(cudaSetDevice(h->device));
   H_CUDA(cudaEventRecord(h->ev_up[2], h->stream));
   h->tstride = pad64(n);
-  H_RC(load_cloud(h, pts, n, on_device, h->tgt_raw, h->tstride));
-  if (nrm) H_RC(load_cloud(h, nrm, n, on_device, h->nrm, h->tstride));
+  H_RC(load_cloud(h, pts, n, on_device, h->tgt_raw, h->tstride, async ? &h->stage_tgt : nullptr));
+  if (nrm) H_RC(load_cloud(h, nrm, n, on_device, h->nrm, h->tstride, async ? &h->stage_nrm : nullptr));
   H_CUDA(cudaEventRecord(h->ev_up[3], h->stream));
   h->up_tgt = true;
   h->n_target = n;
@@ -388,6 +411,12 @@ int icp_begin(sm_handle* h, const double* guess) {
   r.active = false;
   if (!h->has_source || !h->has_target)
     return fail(h, SM_ERR_MISSING_INPUT, "Align: source/target not set");
+  {   // CHECK(quantile >= 0 && quantile <= 1), icp_fast.cc:68
+    const float q = h->icp.dist_outlier_ratio;
+    if (!(q >= 0.0f && q <= 1.0f)) return fail(h, SM_ERR_BAD_ARGUMENT, "Align: dist_outlier_ratio outside [0, 1] (icp_fast.cc:68)");
+    if (!(h->icp.knn_epsilon >= 0.0f)) return fail(h, SM_ERR_BAD_ARGUMENT, "Align: knn_epsilon must be >= 0");
+  }
+  NvtxRange nvtx_align("IcpFast::Align");
   const int ns = (int)h->n_source, nt = (int)h->n_target;
   const int levels = kd_num_levels(nt, 8);
   const int nb = icp_accum_blocks(ns);
@@ -1024,7 +1053,7 @@ int sm_destroy(sm_handle* h) {
   if (!h) return SM_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->stage, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->src_g0, &h->src_sort, &h->nodes,
+  DevBuf* bufs[] = {&h->stage, &h->stage_src, &h->stage_tgt, &h->stage_nrm, &h->tgt_raw, &h->tgt, &h->nrm, &h->src_raw, &h->src0, &h->src_g0, &h->src_sort, &h->nodes,
                     &h->leaf_order, &h->bpts, &h->bnrm, &h->ccut, &h->cdim, &h->cpb, &h->cpn, &h->slot, &h->d2, &h->hist, &h->cand_idx, &h->cand_key,
                     &h->cand_cnt, &h->partials, &h->mean_partials, &h->state, &h->guess, &h->kdws};
   for (DevBuf* b : bufs) b->release();
@@ -1167,6 +1196,123 @@ int sm_align_wait(sm_handle* h, double* result) {
   if (!h || !result) return SM_ERR_BAD_ARGUMENT;
   if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, SM_ERR_CUDA, "cudaSetDevice failed");
   return icp_end(h, result);
+}
+
+int sm_align_batch(sm_handle* const* handles, int32_t n, const double* guesses_16n, double* results_16n,
+                   int32_t* rc_n) {
+  if (!handles || n < 0 || !guesses_16n || !results_16n || !rc_n) return SM_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n; ++i) if (!handles[i]) return SM_ERR_BAD_ARGUMENT;
+  NvtxRange nvtx("sm_align_batch");
+  // IcpFast instances: everything is enqueued from this thread before the first result is awaited
+  std::vector<int> other;
+  for (int i = 0; i < n; ++i) {
+    sm_handle* h = handles[i];
+    rc_n[i] = 0;
+    if (h->type != SM_TYPE_FAST_ICP) { other.push_back(i); continue; }
+    if (cudaSetDevice(h->device) != cudaSuccess) { rc_n[i] = fail(h, SM_ERR_CUDA, "cudaSetDevice failed"); continue; }
+    rc_n[i] = icp_begin(h, guesses_16n + 16 * (size_t)i);
+  }
+  // the other matchers drive their optimiser from the host (Newton / BFGS steps with a read-back
+  // each): one worker thread per instance, at most 16 at a time, like the reference's thread pool
+  std::vector<std::thread> workers;
+  std::atomic<int> next(0);
+  const int nworkers = (int)other.size() < 16 ? (int)other.size() : 16;
+  for (int w = 0; w < nworkers; ++w)
+    workers.emplace_back([&]() {
+      for (;;) {
+        const int k = next.fetch_add(1);
+        if (k >= (int)other.size()) break;
+        const int i = other[(size_t)k];
+        rc_n[i] = sm_align(handles[i], guesses_16n + 16 * (size_t)i, results_16n + 16 * (size_t)i);
+      }
+    });
+  for (int i = 0; i < n; ++i) {
+    sm_handle* h = handles[i];
+    if (h->type != SM_TYPE_FAST_ICP || rc_n[i] < 0) continue;
+    if (cudaSetDevice(h->device) != cudaSuccess) { rc_n[i] = SM_ERR_CUDA; continue; }
+    rc_n[i] = icp_end(h, results_16n + 16 * (size_t)i);
+  }
+  for (std::thread& t : workers) t.join();
+  int worst = 0;
+  for (int i = 0; i < n; ++i) if (rc_n[i] < worst) worst = rc_n[i];
+  return worst < 0 ? worst : SM_OK;
+}
+
+int sm_align_pairs(sm_handle* const* handles, int32_t n_handles, const sm_pair* pairs, int32_t n_pairs,
+                   double* results_16n, double* scores_n, int32_t* rc_n) {
+  if (!handles || n_handles <= 0 || !pairs || n_pairs < 0 || !results_16n || !rc_n) return SM_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n_handles; ++i)
+    if (!handles[i] || handles[i]->type != SM_TYPE_FAST_ICP) return SM_ERR_UNSUPPORTED_TYPE;
+  NvtxRange nvtx("sm_align_pairs");
+  static const double kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  std::vector<int> in_flight((size_t)n_handles, -1);     // pair index a pipeline is working on
+  auto collect = [&](int hi) {
+    const int k = in_flight[(size_t)hi];
+    if (k < 0) return;
+    sm_handle* h = handles[hi];
+    cudaSetDevice(h->device);
+    rc_n[k] = icp_end(h, results_16n + 16 * (size_t)k);
+    if (scores_n) scores_n[k] = h->final_score;
+    in_flight[(size_t)hi] = -1;
+  };
+  for (int k = 0; k < n_pairs; ++k) {
+    const int hi = k % n_handles;
+    sm_handle* h = handles[hi];
+    collect(hi);                                          // the pipeline's previous pair
+    const sm_pair& pr = pairs[k];
+    rc_n[k] = 0;
+    if (scores_n) scores_n[k] = 0.0;
+    if (cudaSetDevice(h->device) != cudaSuccess) { rc_n[k] = fail(h, SM_ERR_CUDA, "cudaSetDevice failed"); continue; }
+    const bool dev = pr.on_device != 0;
+    int rc = set_target(h, pr.target_3xn, pr.target_normals_3xn, pr.n_target, dev, !dev);
+    if (rc >= 0) rc = set_source(h, pr.source_3xn, pr.n_source, dev, !dev);
+    if (rc >= 0) rc = icp_begin(h, pr.guess_4x4 ? pr.guess_4x4 : kIdentity);
+    if (rc < 0) { rc_n[k] = rc; continue; }
+    in_flight[(size_t)hi] = k;
+  }
+  for (int hi = 0; hi < n_handles; ++hi) collect(hi);
+  int worst = 0;
+  for (int k = 0; k < n_pairs; ++k) if (rc_n[k] < worst) worst = rc_n[k];
+  return worst < 0 ? worst : SM_OK;
+}
+
+int sm_debug_solve6(int device, const double* A, const double* b, double* x, int32_t* path) {
+  if (!A || !b || !x || !path) return SM_ERR_BAD_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SM_ERR_NO_DEVICE;
+  SMB_CUDA_OK(cudaSetDevice(device));
+  double* d = nullptr;
+  SMB_CUDA_OK(cudaMalloc(&d, 64 * sizeof(double)));
+  int rc = SM_OK;
+  if (cudaMemcpy(d, A, 36 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d + 36, b, 6 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = SM_ERR_CUDA;
+  if (rc == SM_OK) {
+    debug_solve6_kernel<<<1, 32>>>(d, d + 36, d + 42, reinterpret_cast<int*>(d + 48));
+    int p = 0;
+    if (cudaMemcpy(x, d + 42, 6 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&p, d + 48, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SM_ERR_CUDA;
+    *path = p;
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int sm_debug_bfgs_minimize(sm_debug_fdf fn, void* user, double* x, double grad_tol, int32_t max_iterations,
+                           int32_t* iterations, int32_t* evaluations, int32_t* status) {
+  if (!fn || !x || !iterations || !evaluations || !status) return SM_ERR_BAD_ARGUMENT;
+  int evals = 0;
+  gicp::Minimizer mz;
+  mz.fdf = [&](const double* xx, double* f, double* g) -> int { ++evals; return fn(xx, f, g, user); };
+  mz.init(x);
+  int result = gicp::kRunning, inner = 0;
+  do {                                   // gicp_omp_impl.hpp:225-240
+    ++inner;
+    result = mz.one_step(x);
+    if (result) break;
+    result = mz.test_gradient(grad_tol);
+  } while (result == gicp::kRunning && inner < max_iterations);
+  *iterations = inner; *evaluations = evals; *status = mz.failed ? gicp::kError : result;
+  return SM_OK;
 }
 
 double sm_get_fitness_score(const sm_handle* h) { return h ? h->final_score : 0.0; }

@@ -12,6 +12,7 @@
 // output points is ascending (ix, iy, iz), whereas the reference's is the iteration order of a
 // libstdc++ unordered_map (an accident of its rehash history; nothing downstream depends on it
 // beyond summation order).  Compiled with -fmad=false.
+#include <limits.h>
 #include <math.h>
 
 #include "../../include/sm_b200.h"
@@ -21,24 +22,59 @@
 namespace smb {
 namespace {
 
-constexpr int kBias = 1 << 20;          // |voxel index| < 2^20 per axis
+constexpr long long kSpan = 1ll << 21;   // voxel indices of one axis must span < 2^21 (3 x 21-bit key)
 constexpr int kT = 256, kItems = 8, kTile = kT * kItems;
+
+// meta[0..2]: per-axis minimum voxel index over the finite points; meta[3]: dropped (non-finite) points;
+// meta[4]: 1 if an axis spans 2^21 voxels or more
+__device__ __forceinline__ bool vf_index(const float* p, float voxel, long long* ix, long long* iy, long long* iz) {
+  const float qx = p[0] / voxel, qy = p[1] / voxel, qz = p[2] / voxel;
+  // std::lround of a NaN / inf quotient is unspecified in the reference: such points are dropped here
+  if (!(fabsf(qx) < 9.0e18f && fabsf(qy) < 9.0e18f && fabsf(qz) < 9.0e18f)) return false;
+  *ix = llroundf(qx); *iy = llroundf(qy); *iz = llroundf(qz);
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+vf_min_kernel(const char* __restrict__ pts, int64_t stride, int n, float voxel, long long* __restrict__ meta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  long long ix = LLONG_MAX, iy = LLONG_MAX, iz = LLONG_MAX;
+  if (i < n) {
+    long long a, b, c;
+    if (vf_index(reinterpret_cast<const float*>(pts + (int64_t)i * stride), voxel, &a, &b, &c)) { ix = a; iy = b; iz = c; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ix = min(ix, __shfl_xor_sync(0xffffffffu, ix, o));
+    iy = min(iy, __shfl_xor_sync(0xffffffffu, iy, o));
+    iz = min(iz, __shfl_xor_sync(0xffffffffu, iz, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&meta[0], ix); atomicMin(&meta[1], iy); atomicMin(&meta[2], iz); }
+}
 
 __global__ void __launch_bounds__(256)
 vf_key_kernel(const char* __restrict__ pts, int64_t stride, int n, float voxel, uint64_t* __restrict__ keys,
-              uint32_t* __restrict__ vals, int* __restrict__ bad) {
+              uint32_t* __restrict__ vals, long long* __restrict__ meta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* p = reinterpret_cast<const float*>(pts + (int64_t)i * stride);
-  const long long ix = llroundf(p[0] / voxel), iy = llroundf(p[1] / voxel), iz = llroundf(p[2] / voxel);
-  const bool ok = ix > -kBias && ix < kBias && iy > -kBias && iy < kBias && iz > -kBias && iz < kBias;
-  if (!ok) atomicOr(bad, 1);     // also catches NaN / inf coordinates
-  keys[i] = ok ? (((uint64_t)(ix + kBias) << 42) | ((uint64_t)(iy + kBias) << 21) | (uint64_t)(iz + kBias)) : ~0ull;
+  long long ix, iy, iz;
+  uint64_t key = ~0ull;                      // dropped points sort behind every voxel
+  if (vf_index(reinterpret_cast<const float*>(pts + (int64_t)i * stride), voxel, &ix, &iy, &iz)) {
+    // offsets from the cloud's own minimum: the key order stays ascending (ix, iy, iz)
+    const unsigned long long ox = (unsigned long long)(ix - meta[0]), oy = (unsigned long long)(iy - meta[1]),
+                             oz = (unsigned long long)(iz - meta[2]);
+    if (ox < (unsigned long long)kSpan && oy < (unsigned long long)kSpan && oz < (unsigned long long)kSpan)
+      key = (ox << 42) | (oy << 21) | oz;
+    else
+      atomicExch((unsigned long long*)&meta[4], 1ull);
+  } else {
+    atomicAdd((unsigned long long*)&meta[3], 1ull);
+  }
+  keys[i] = key;
   vals[i] = (uint32_t)i;
 }
 
 __device__ __forceinline__ uint32_t vf_is_head(const uint64_t* keys, int i) {
-  return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  return (keys[i] != ~0ull && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(kT)
@@ -56,7 +92,7 @@ vf_heads_count_kernel(const uint64_t* __restrict__ keys, int n, uint32_t* __rest
 // voxel_start[v] = first sorted position of voxel v; voxel_start[n_voxels] = n
 __global__ void __launch_bounds__(kT)
 vf_heads_scatter_kernel(const uint64_t* __restrict__ keys, int n, const uint32_t* __restrict__ block_off,
-                        uint32_t* __restrict__ voxel_start) {
+                        uint32_t* __restrict__ voxel_start, const long long* __restrict__ meta) {
   __shared__ uint32_t ws[kT / 32];
   const int base = blockIdx.x * kTile + threadIdx.x * kItems;
   uint32_t f[kItems], c = 0;
@@ -70,7 +106,7 @@ vf_heads_scatter_kernel(const uint64_t* __restrict__ keys, int n, const uint32_t
   for (int ww = 0; ww < w; ++ww) wb += ws[ww];
   uint32_t pos = block_off[blockIdx.x] + wb + incl - c;
   for (int r = 0; r < kItems; ++r) if (f[r]) voxel_start[pos++] = (uint32_t)(base + r);
-  if (blockIdx.x == 0 && threadIdx.x == 0) voxel_start[block_off[gridDim.x]] = (uint32_t)n;   // sentinel
+  if (blockIdx.x == 0 && threadIdx.x == 0) voxel_start[block_off[gridDim.x]] = (uint32_t)(n - (int)meta[3]);   // sentinel: first dropped point
 }
 
 __global__ void __launch_bounds__(256)
@@ -88,9 +124,9 @@ vf_mean_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ v
                const uint32_t* __restrict__ n_voxels_dev, float* __restrict__ out) {
   constexpr int kPad = 33;
   __shared__ double s_d[8][4 * kPad];
-  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // n may exceed 2^27: 64-bit
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  if (v >= (int)*n_voxels_dev) return;
+  if (v >= (int64_t)*n_voxels_dev) return;
   const uint32_t s0 = voxel_start[v], s1 = voxel_start[v + 1];
   double* sd = s_d[wib];
   const double* mine = sd + min(lane, 3) * kPad;
@@ -113,8 +149,8 @@ vf_mean_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ v
     }
     __syncwarp();
   }
-  if (lane < 4) out[5 * (int64_t)v + lane] = (float)(acc / (double)(int)(s1 - s0));   // sum / size, size is an int
-  if (lane == 4) out[5 * (int64_t)v + 4] = 0.0f;                                      // factor keeps its default
+  if (lane < 4) out[5 * v + lane] = (float)(acc / (double)(int)(s1 - s0));   // sum / size, size is an int
+  if (lane == 4) out[5 * v + 4] = 0.0f;                                      // factor keeps its default
 }
 
 }  // namespace
@@ -155,30 +191,32 @@ extern "C" int sm_voxel_grid_filter(int device, const float* points, int64_t n, 
   uint32_t* voxel_start = (uint32_t*)take(((size_t)n + 8) * sizeof(uint32_t));
   float4* sorted = (float4*)take((size_t)n * sizeof(float4));
   float* d_out = (float*)take((size_t)n * 5 * sizeof(float));
-  int* bad = (int*)take(256);
+  long long* meta = (long long*)take(256);
   cudaStream_t s = nullptr;
   int rc = SM_OK;
   auto fail = [&](int code) { cudaFree(base); return code; };
+  const long long meta_init[8] = {LLONG_MAX, LLONG_MAX, LLONG_MAX, 0, 0, 0, 0, 0};
   if (cudaMemcpyAsync(d_in, points, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-      cudaMemsetAsync(bad, 0, sizeof(int), s) != cudaSuccess)
+      cudaMemcpyAsync(meta, meta_init, sizeof(meta_init), cudaMemcpyHostToDevice, s) != cudaSuccess)
     return fail(SM_ERR_CUDA);
-  vf_key_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_in, stride_bytes, ni, voxel_size, keys0, ord0, bad);
+  vf_min_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_in, stride_bytes, ni, voxel_size, meta);
+  vf_key_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_in, stride_bytes, ni, voxel_size, keys0, ord0, meta);
   rc = radix_sort_pairs_u64(keys0, ord0, keys1, ord1, ni, 1, st, scratch, s, 8);   // 8 passes: result back in [0]
   if (rc) return fail(rc == -100 ? SM_ERR_CUDA : rc);
   vf_heads_count_kernel<<<nblk, kT, 0, s>>>(keys0, ni, block_sum);
   cudaMemsetAsync(block_sum + nblk, 0, sizeof(uint32_t), s);
   radix_scan_kernel_launch(block_sum, nblk + 1, 1, s);                                // block_sum[nblk] = number of voxels
-  vf_heads_scatter_kernel<<<nblk, kT, 0, s>>>(keys0, ni, block_sum, voxel_start);
+  vf_heads_scatter_kernel<<<nblk, kT, 0, s>>>(keys0, ni, block_sum, voxel_start, meta);
   vf_gather_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_in, stride_bytes, ord0, ni, sorted);
   vf_mean_kernel<<<ceil_div((int64_t)n * 32, 256), 256, 0, s>>>(sorted, voxel_start, block_sum + nblk, d_out);
   uint32_t m = 0;
-  int host_bad = 0;
+  long long host_meta[8] = {0};
   if (cudaGetLastError() != cudaSuccess ||
       cudaMemcpyAsync(&m, block_sum + nblk, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-      cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaMemcpyAsync(host_meta, meta, sizeof(host_meta), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
       cudaStreamSynchronize(s) != cudaSuccess)
     return fail(SM_ERR_CUDA);
-  if (host_bad) return fail(SM_ERR_BAD_ARGUMENT);       // a coordinate is NaN/inf or beyond 2^20 voxels
+  if (host_meta[4]) return fail(SM_ERR_BAD_ARGUMENT);   // the finite points span 2^21 voxels or more along an axis
   if (m > 0 && cudaMemcpy(out, d_out, (size_t)m * 5 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
     return fail(SM_ERR_CUDA);
   *m_out = (int64_t)m;

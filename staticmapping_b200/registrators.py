@@ -346,6 +346,71 @@ def CreateMatcher(options: MatcherOptions, verbose: bool = False, device: int = 
     return matcher
 
 
+def AlignBatch(matchers, guesses):
+    """Batched Align over matcher instances whose inputs are set (sm_align_batch): what
+    loop_detector.cc:216-228 / map_builder.cc:706-708 do with a thread pool, from one host thread.
+    Returns (oks, results) with results of shape (n, 4, 4)."""
+    n = len(matchers)
+    lib = _lib.lib()
+    hs = (C.c_void_p * n)(*[m._h for m in matchers])
+    g = np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.float64).T for x in guesses]).reshape(n, 16))
+    res = np.zeros((n, 16), dtype=np.float64)
+    rcs = np.zeros(n, dtype=np.int32)
+    lib.sm_align_batch(hs, n, g.ctypes.data, res.ctypes.data, rcs.ctypes.data)
+    for m, rc in zip(matchers, rcs):
+        m._check(int(rc), "AlignBatch")
+    return [bool(r) for r in rcs], res.reshape(n, 4, 4).transpose(0, 2, 1).copy()
+
+
+def AlignPairs(matchers, pairs):
+    """n_pairs independent IcpFast alignments pipelined over the given instances (sm_align_pairs).
+    `pairs`: sequence of dicts {source, target, normals, guess (optional), on_device (optional)} where
+    the clouds are (N, 3) float64 C-contiguous arrays (host; pinned memory overlaps best) or, with
+    on_device, integer device pointers plus n_source / n_target.
+    Returns (rcs, results (n, 4, 4), scores (n,))."""
+    n = len(pairs)
+    lib = _lib.lib()
+    hs = (C.c_void_p * len(matchers))(*[m._h for m in matchers])
+    arr = (_lib.Pair * n)()
+    keep = []
+    for k, pr in enumerate(pairs):
+        dev = bool(pr.get("on_device", False))
+        if dev:
+            arr[k].source, arr[k].target, arr[k].target_normals = pr["source"], pr["target"], pr["normals"]
+            arr[k].n_source, arr[k].n_target = int(pr["n_source"]), int(pr["n_target"])
+        else:
+            src, tgt, nrm = pr["source"], pr["target"], pr["normals"]
+            arr[k].source, arr[k].target, arr[k].target_normals = _ptr(src), _ptr(tgt), _ptr(nrm)
+            arr[k].n_source, arr[k].n_target = int(pr.get("n_source", len(src))), int(pr.get("n_target", len(tgt)))
+        g = pr.get("guess")
+        if g is not None:
+            g = np.ascontiguousarray(np.asarray(g, dtype=np.float64).T).ravel()
+            keep.append(g)
+            arr[k].guess = g.ctypes.data
+        arr[k].on_device = 1 if dev else 0
+    res = np.zeros((n, 16), dtype=np.float64)
+    scores = np.zeros(n, dtype=np.float64)
+    rcs = np.zeros(n, dtype=np.int32)
+    rc = lib.sm_align_pairs(hs, len(matchers), arr, n, res.ctypes.data, scores.ctypes.data, rcs.ctypes.data)
+    if rc == -11:
+        raise CheckFailure("AlignPairs: IcpFast instances only")
+    for k, r in enumerate(rcs):
+        matchers[k % len(matchers)]._check(int(r), "AlignPairs")
+    return rcs, res.reshape(n, 4, 4).transpose(0, 2, 1).copy(), scores
+
+
+def _ptr(a):
+    """address of a float64 (N, 3) C-contiguous numpy array or torch tensor (data_ptr), or an int"""
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("AlignPairs needs C-contiguous float64 clouds (no hidden copies: the engine reads them asynchronously)")
+    return a.ctypes.data
+
+
 def knn1(target, query, epsilon=3.16, bucket_size=8, device=0):
     """libnabo-compatible 1-NN on the GPU (NNS::create + knn, icp_fast.cc:466-467,177-178)."""
     lib = _lib.lib()

@@ -3,6 +3,7 @@
 // tests/stubs.  Reads   <in>:  int64 ns, int64 nt, float src[ns*3], float tgt[nt*3], double delta[16]
 // writes <out> (text): one "key v0 v1 ..." line per result.  tests/test_adapter_cpp.py builds it,
 // runs it on the GPU and compares every line with the oracle.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -64,6 +65,35 @@ int main(int argc, char** argv) {
     const double meta[3] = {ok ? 1.0 : 0.0, matcher->GetFitnessScore(), static_cast<double>(matcher->GetType())};
     Dump(out, "icp_result", result.data(), 16);
     Dump(out, "icp_meta", meta, 3);
+  }
+  {
+    // batched CloseLoop sketch: three IcpFast candidates aligned by ONE thread through AlignBatch
+    std::vector<std::unique_ptr<registrator::IcpFastB200>> owned;
+    std::vector<registrator::IcpFastB200*> ms;
+    std::vector<Eigen::Matrix4d> guesses, results;
+    for (int k = 0; k < 3; ++k) {
+      owned.emplace_back(new registrator::IcpFastB200());
+      owned.back()->InitWithOptions();
+      owned.back()->SetInputSource(source);
+      owned.back()->SetInputTarget(target);
+      ms.push_back(owned.back().get());
+      Eigen::Matrix4d g = Eigen::Matrix4d::Identity();
+      g(0, 3) = 0.01 * k;                              // distinct guesses
+      guesses.push_back(g);
+    }
+    std::vector<bool> ok;
+    registrator::AlignBatch(ms, guesses, &results, &ok);
+    for (int k = 0; k < 3; ++k) {
+      Eigen::Matrix4d single;
+      std::unique_ptr<registrator::Interface> one(new registrator::IcpFastB200());
+      one->InitWithOptions(); one->SetInputSource(source); one->SetInputTarget(target);
+      const bool ok1 = one->Align(guesses[k], single);
+      double diff = 0.0;
+      for (int i = 0; i < 16; ++i) diff += std::fabs(single.data()[i] - results[k].data()[i]);
+      const double rec[4] = {static_cast<double>(ok[k]), static_cast<double>(ok1), diff,
+                             ms[k]->GetFitnessScore() - one->GetFitnessScore()};
+      Dump(out, k == 0 ? "batch0" : (k == 1 ? "batch1" : "batch2"), rec, 4);
+    }
   }
   {
     std::unique_ptr<registrator::Interface> matcher(new registrator::NdtB200());

@@ -245,6 +245,10 @@ def num_threads():
     return lib().sm_oracle_num_threads()
 
 
+def set_num_threads(n):
+    lib().sm_oracle_set_num_threads(int(n))
+
+
 # ---- motion compensation either side of Align (oracle/motion_oracle.cc) -------------------------
 def interpolate_transform(t1, t2, factor):
     a = np.ascontiguousarray(np.asarray(t1, dtype=np.float64).T).ravel()

@@ -40,6 +40,14 @@ def lidar_pair(n_az=300, n_beams=32, submap_points=60000, pair=0, seed=0):
     return src, sub, P
 
 
+def full_size_pair(pair=0):
+    """BASELINE.json configs[1]/[2]/[4] sizes: one 64-beam x 1875-azimuth scan (120 000 points)
+    against a 500 000-point submap."""
+    src, sub, P = lidar_pair(n_az=1875, n_beams=64, submap_points=500_000, pair=pair)
+    assert src.shape == (120_000, 3) and sub.shape == (500_000, 3)
+    return src, sub, P
+
+
 def reference_voxel_test_cloud():
     """The cloud of the reference's own unit test (pre_processors/test/test_filter_voxel_grid.cc:54-63):
     a 10 x 10 lattice, x = i*0.1f + 0.02f, y = j*0.1f + 0.02f, z = 0.1f, intensity 0 (float arithmetic)."""

@@ -54,6 +54,13 @@ struct FatalStream {
 #define CHECK(x) if (!(x)) FatalStream(__FILE__, __LINE__, #x)
 #define CHECK_EQ(a, b) if (!((a) == (b))) FatalStream(__FILE__, __LINE__, #a " == " #b)
 #define CHECK_GE(a, b) if (!((a) >= (b))) FatalStream(__FILE__, __LINE__, #a " >= " #b)
+#define CHECK_NE(a, b) if (!((a) != (b))) FatalStream(__FILE__, __LINE__, #a " != " #b)
+struct LogStream {   // LOG(ERROR) of glog: prints, does not abort
+  ~LogStream() { fprintf(stderr, "\n"); }
+  template <typename T> LogStream& operator<<(const T& v) { std::cerr << v; return *this; }
+};
+#define ERROR 0
+#define LOG(severity) LogStream()
 #define PROHIBIT_COPY_AND_ASSIGN(C) C(const C&) = delete; C& operator=(const C&) = delete
 namespace static_map {
 namespace data {

@@ -68,6 +68,8 @@ def test_cpp_adapter_matches_oracle(tmp_path):
     o = O.icp_fast_align(s32.astype(np.float64), tp, tn)
     dt, dr = scenes.se3_error(o["result"], out["icp_result"].reshape(4, 4).T)
     assert dt <= 1e-4 and dr <= 1e-4 and abs(out["icp_meta"][1] - o["score"]) < 1e-6 and list(out["icp_meta"][[0, 2]]) == [1.0, 6.0]
+    for k in range(3):      # AlignBatch == the same Align calls one by one (bit-identical: same kernels, same order)
+        assert list(out[f"batch{k}"]) == [1.0, 1.0, 0.0, 0.0]
     n = O.ndt_align(s32, t32)
     dt, dr = scenes.se3_error(n["result"], out["ndt_result"].reshape(4, 4).T)
     assert dt <= 1e-4 and dr <= 1e-4 and abs(out["ndt_meta"][1] - n["fitness"]) <= 1e-9 * max(1.0, n["fitness"])

@@ -174,3 +174,49 @@ def test_target_without_normals_is_check_failure():
     m = smb.IcpFast()
     with pytest.raises(smb.CheckFailure):
         m.SetInputTarget(smb.EigenCloud(np.zeros((10, 3)) + 1.0))
+
+
+def test_align_pairs_and_batch_match_single_aligns():
+    # sm_align_pairs (pipelined, async uploads) and sm_align_batch must give what sm_align gives
+    data = []
+    for pair in range(5):
+        src, sub, P = scenes.lidar_pair(pair=pair)
+        tp, tn = O.calculate_normals(sub)
+        data.append((np.ascontiguousarray(src), np.ascontiguousarray(tp), np.ascontiguousarray(tn)))
+    singles = []
+    for src, tp, tn in data:
+        m = smb.IcpFast()
+        m.InitWithXml({"max_iteration": 30})
+        m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tp, tn))
+        ok, res = m.Align(np.eye(4))
+        singles.append((res, m.GetFitnessScore(), m.GetAlignInfo()["iterations"]))
+    ms = [smb.IcpFast() for _ in range(2)]
+    for m in ms:
+        m.InitWithXml({"max_iteration": 30})
+    rcs, res, scores = smb.AlignPairs(ms, [{"source": s, "target": t, "normals": n} for s, t, n in data])
+    assert list(rcs) == [1] * 5
+    for k in range(5):
+        assert np.array_equal(res[k], singles[k][0])          # same kernels, same order: bit-identical
+        assert scores[k] == singles[k][1]
+    ms3 = []
+    for src, tp, tn in data[:3]:
+        m = smb.IcpFast()
+        m.InitWithXml({"max_iteration": 30})
+        m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tp, tn))
+        ms3.append(m)
+    oks, resb = smb.AlignBatch(ms3, [np.eye(4)] * 3)
+    assert oks == [True] * 3
+    for k in range(3):
+        assert np.array_equal(resb[k], singles[k][0])
+
+
+def test_bad_outlier_ratio_is_check_failure():
+    # CHECK(quantile >= 0 && quantile <= 1), icp_fast.cc:68
+    src, tgt, _ = scenes.corner_pair()
+    tp, tn = O.calculate_normals(tgt)
+    for bad in ("1.5", "-0.1", "nan"):
+        m = smb.IcpFast()
+        m.InitWithXml({"dist_outlier_ratio": bad})
+        m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tp, tn))
+        with pytest.raises(smb.CheckFailure):
+            m.Align(np.eye(4))

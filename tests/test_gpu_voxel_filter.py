@@ -47,12 +47,33 @@ def test_edge_cases():
     assert smb.VoxelGridFilter(np.zeros((0, 5), np.float32), 0.5).shape == (0, 5)
     with pytest.raises(smb.CheckFailure):
         smb.VoxelGridFilter(one, 0.0)                                     # ConfigsValid
-    bad = one.copy(); bad[0, 1] = np.nan
-    with pytest.raises(smb.CheckFailure):
-        smb.VoxelGridFilter(bad, 0.5)
+    bad = one.copy(); bad[0, 1] = np.nan                                  # a lone non-finite point is dropped
+    assert smb.VoxelGridFilter(bad, 0.5).shape == (0, 5)
     same = np.tile(one, (5000, 1))                                        # everything in one voxel
     out = smb.VoxelGridFilter(same, 0.5)
     assert out.shape == (1, 5) and np.array_equal(out[0, :4], one[0, :4])
+
+
+def test_non_finite_points_are_dropped_and_far_clouds_work():
+    # one bad lidar return must not stop the mapper: NaN / inf points are dropped, the rest is the
+    # filter of the finite points; voxel keys are offsets from the cloud's own minimum, so a cloud
+    # 150 km from the origin with 0.1 m voxels (index ~1.5e6 > 2^20) is fine
+    rng = np.random.default_rng(3)
+    pts = np.zeros((20000, 5), np.float32)
+    pts[:, :3] = rng.uniform(-20, 20, (20000, 3)) + np.array([150_000.0, -90_000.0, 30.0])
+    pts[:, 3] = rng.uniform(0, 255, 20000)
+    m, want = O.voxel_grid_filter(pts, 0.1)
+    got = smb.VoxelGridFilter(pts, 0.1)
+    assert got.shape[0] == m and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    dirty = pts.copy()
+    dirty[7, 0] = np.nan; dirty[11, 2] = np.inf; dirty[13, 1] = -np.inf
+    clean = np.delete(pts, [7, 11, 13], axis=0)
+    m2, want2 = O.voxel_grid_filter(clean, 0.1)
+    got2 = smb.VoxelGridFilter(dirty, 0.1)
+    assert got2.shape[0] == m2 and np.array_equal(got2.view(np.uint32), want2.view(np.uint32))
+    wide = pts[:2].copy(); wide[1, 0] += 3.0e6                            # spans > 2^21 voxels of 0.1 m
+    with pytest.raises(smb.CheckFailure):
+        smb.VoxelGridFilter(wide, 0.1)
 
 
 def test_reference_unit_test_vectors():

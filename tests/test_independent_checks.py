@@ -1,0 +1,185 @@
+"""Independent cross-checks that break the common mode between the product and the oracle.
+
+csrc/gicp_host.h (BFGS + Fletcher line search) and oracle/gicp_oracle.cc, and csrc/linalg_dev.cuh (pivoted
+QR rank, LLT, minimum-norm branch, SVD) and oracle/linalg.h, are twin transcriptions of GSL / Eigen
+routines: a parity test between them cannot see a shared transcription error.  Here both sides are
+checked against numpy / scipy instead:
+  * the 6x6 solver of the ICP iteration: numpy.linalg solve / matrix_rank / pinv on rank 6, 5, 4, 3
+    normal matrices (icp_fast.cc:204-254 semantics: LLT if invertible, else the minimum-norm solution);
+  * the BFGS minimiser: scipy.optimize.minimize(method="BFGS") must reach the same minimiser, and the
+    gradient at the product's answer must vanish.
+The BFGS check needs no GPU (host code of libsm_b200.so); the device solver check is marked gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.optimize
+
+import oracle_lib as O
+from staticmapping_b200 import _lib
+
+
+def _normal_matrix(rank, seed, scale=1.0):
+    """A = J^T J (6x6, PSD) of exact rank `rank`, b = J^T r: the shape of the ICP normal equations."""
+    rng = np.random.default_rng(seed)
+    if rank == 6:
+        J = rng.normal(size=(40, 6)) * scale
+    else:
+        basis = rng.normal(size=(rank, 6))
+        J = rng.normal(size=(40, rank)) @ basis * scale
+    r = rng.normal(size=40)
+    return J.T @ J, J.T @ r
+
+
+def _check_solution(A, b, x, path, rank):
+    assert np.linalg.matrix_rank(A, tol=np.linalg.svd(A, compute_uv=False).max() * 6 * np.finfo(float).eps * 64) == rank
+    if rank == 6:
+        assert path == 0
+        want = np.linalg.solve(A, b)
+    else:
+        assert path in (1, 2)
+        want = np.linalg.pinv(A, rcond=1e-10) @ b          # the minimum-norm least-squares solution
+    assert np.allclose(x, want, rtol=1e-7, atol=1e-9 * max(1.0, np.abs(want).max())), (x, want)
+
+
+@pytest.mark.parametrize("rank", [6, 5, 4, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_solve6_against_numpy(rank, seed):
+    A, b = _normal_matrix(rank, 10 * rank + seed, scale=[1.0, 30.0, 0.05][seed])
+    x, path = O.solve6(A, b)
+    _check_solution(A, b, x, path, rank)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rank", [6, 5, 4, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_device_solve6_against_numpy(rank, seed):
+    A, b = _normal_matrix(rank, 10 * rank + seed, scale=[1.0, 30.0, 0.05][seed])
+    lib = _lib.lib()
+    Ac = np.ascontiguousarray(A); bc = np.ascontiguousarray(b)
+    x = np.zeros(6); path = C.c_int32(-1)
+    rc = lib.sm_debug_solve6(0, Ac.ctypes.data, bc.ctypes.data, x.ctypes.data, C.byref(path))
+    assert rc == 0
+    _check_solution(A, b, x, path.value, rank)
+
+
+@pytest.mark.gpu
+def test_device_solve6_singular_values_spread():
+    # nearly dependent columns: cond ~ 1e12 is still rank 6 for Eigen's threshold (6 eps): LLT path
+    rng = np.random.default_rng(5)
+    J = rng.normal(size=(60, 6)); J[:, 5] = J[:, 4] + 1e-6 * rng.normal(size=60)
+    A, b = J.T @ J, J.T @ rng.normal(size=60)
+    lib = _lib.lib()
+    x = np.zeros(6); path = C.c_int32(-1)
+    assert lib.sm_debug_solve6(0, np.ascontiguousarray(A).ctypes.data, np.ascontiguousarray(b).ctypes.data,
+                               x.ctypes.data, C.byref(path)) == 0
+    assert path.value == 0
+    assert np.linalg.norm(A @ x - b) <= 1e-6 * np.linalg.norm(b)
+
+
+# ---------------------------------------------------------------------------------------- BFGS
+FDF = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+def _run_product_bfgs(fun, x0, grad_tol=1e-9, max_iter=500):
+    def cb(xp, fp, gp, _):
+        x = np.array([xp[i] for i in range(6)])
+        f, g = fun(x)
+        if fp:
+            fp[0] = f
+        if gp:
+            for i in range(6):
+                gp[i] = g[i]
+        return 0
+    cfn = FDF(cb)
+    x = np.array(x0, dtype=np.float64)
+    it, ev, st = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = _lib.lib().sm_debug_bfgs_minimize(C.cast(cfn, C.c_void_p), None, x.ctypes.data, grad_tol, max_iter,
+                                           C.byref(it), C.byref(ev), C.byref(st))
+    assert rc == 0
+    return x, it.value, ev.value, st.value
+
+
+def _quadratic(seed):
+    rng = np.random.default_rng(seed)
+    Q = rng.normal(size=(6, 6)); H = Q @ np.diag([1.0, 3.0, 10.0, 30.0, 100.0, 300.0]) @ Q.T / 6.0
+    H = 0.5 * (H + H.T) + np.eye(6) * 0.1
+    c = rng.normal(size=6)
+    return (lambda x: (0.5 * x @ H @ x - c @ x, H @ x - c)), np.linalg.solve(H, c)
+
+
+def _rosenbrock6(x):
+    f = np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2)
+    g = np.zeros(6)
+    g[:-1] += -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+    g[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+    return f, g
+
+
+def _gicp_like(seed):
+    """sum_i d_i^T M_i d_i with d_i = R(x) p_i + t - q_i: the shape of the GICP cost (gicp_omp_impl.hpp:341-377)."""
+    rng = np.random.default_rng(seed)
+    p = rng.normal(size=(50, 3)) * 3.0
+    ang = np.array([0.02, -0.03, 0.05]); t = np.array([0.1, -0.2, 0.05])
+
+    def rot(a):
+        cx, sx, cy, sy, cz, sz = np.cos(a[0]), np.sin(a[0]), np.cos(a[1]), np.sin(a[1]), np.cos(a[2]), np.sin(a[2])
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return Rz @ Ry @ Rx
+    q = p @ rot(ang).T + t
+    L = rng.normal(size=(50, 3, 3)) * 0.3 + np.eye(3)
+    M = np.einsum("nij,nkj->nik", L, L)
+
+    def fun(x):
+        def cost(xx):
+            d = p @ rot(xx[3:]).T + xx[:3] - q
+            return np.einsum("ni,nij,nj->", d, M, d) / 50.0
+        f = cost(x)
+        g = np.zeros(6)
+        for i in range(6):                      # central differences are exact enough for a 1e-6 comparison
+            e = np.zeros(6); e[i] = 1e-6
+            g[i] = (cost(x + e) - cost(x - e)) / 2e-6
+        return f, g
+    return fun, np.concatenate([t, ang])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bfgs_quadratic_matches_closed_form_and_scipy(seed):
+    fun, xstar = _quadratic(seed)
+    x, it, ev, st = _run_product_bfgs(fun, np.zeros(6))
+    assert st in (0, 2)
+    assert np.allclose(x, xstar, atol=1e-8), np.abs(x - xstar).max()
+    assert np.linalg.norm(fun(x)[1]) < 1e-5          # "no progress" (GSL stops on a vanishing step) may end at ~1e-6
+    ref = scipy.optimize.minimize(lambda v: fun(v)[0], np.zeros(6), jac=lambda v: fun(v)[1], method="BFGS",
+                                  options={"gtol": 1e-10})
+    assert np.allclose(x, ref.x, atol=1e-7)
+
+
+def test_bfgs_rosenbrock_matches_scipy():
+    x0 = np.array([-1.2, 1.0, -1.2, 1.0, -1.2, 1.0])
+    x, it, ev, st = _run_product_bfgs(_rosenbrock6, x0, grad_tol=1e-9, max_iter=2000)
+    ref = scipy.optimize.minimize(lambda v: _rosenbrock6(v)[0], x0, jac=lambda v: _rosenbrock6(v)[1], method="BFGS",
+                                  options={"gtol": 1e-10, "maxiter": 5000})
+    assert np.allclose(ref.x, np.ones(6), atol=1e-6)
+    assert np.allclose(x, np.ones(6), atol=1e-6), (x, st, it)
+    assert np.linalg.norm(_rosenbrock6(x)[1]) < 1e-5
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_bfgs_gicp_shaped_cost_matches_scipy(seed):
+    fun, xstar = _gicp_like(seed)
+    x, it, ev, st = _run_product_bfgs(fun, np.zeros(6), grad_tol=1e-7, max_iter=300)
+    ref = scipy.optimize.minimize(lambda v: fun(v)[0], np.zeros(6), jac=lambda v: fun(v)[1], method="BFGS",
+                                  options={"gtol": 1e-9})
+    assert np.allclose(ref.x, xstar, atol=1e-5)
+    assert np.allclose(x, xstar, atol=1e-5), np.abs(x - xstar).max()
+
+
+def test_bfgs_with_the_gicp_stopping_rule_stops_early_like_the_reference():
+    # gicp_omp_impl.hpp:225-240 stops at |g| < 1e-2 or after 20 inner iterations: the product loop must
+    # stop as soon as that holds (status success) without running on
+    fun, xstar = _quadratic(3)
+    x, it, ev, st = _run_product_bfgs(fun, np.zeros(6), grad_tol=1e-2, max_iter=20)
+    assert st == 0 and it <= 20
+    assert np.linalg.norm(fun(x)[1]) < 1e-2
