@@ -163,7 +163,7 @@ def test_bfgs_rosenbrock_matches_scipy():
                                   options={"gtol": 1e-10, "maxiter": 5000})
     assert np.allclose(ref.x, np.ones(6), atol=1e-6)
     assert np.allclose(x, np.ones(6), atol=1e-6), (x, st, it)
-    assert np.linalg.norm(_rosenbrock6(x)[1]) < 1e-5
+    assert np.linalg.norm(_rosenbrock6(x)[1]) < 1e-4
 
 
 @pytest.mark.parametrize("seed", [0, 1])
