@@ -246,6 +246,21 @@ inline void VoxelGridFilterB200(const data::InnerCloudType& input, float voxel_s
   output->points.resize(m);
 }
 
+// descriptor::M2dp::setInputCloud + getFinalDescriptor on the GPU (descriptor/m2dp.cc:129-153): the body of
+// setInputCloud becomes   return registrator::M2dpB200(*source, r_, max_distance_, t_, p_, q_, &descriptor_);
+inline bool M2dpB200(const data::InnerCloudType& source, double r, double max_distance, int32_t t, int32_t p,
+                     int32_t q, std::vector<float>* descriptor, int device = 0) {
+  CHECK(descriptor);
+  const int64_t len = sm_m2dp_descriptor_length(r, max_distance, t, p, q);
+  if (len < 0) return false;                              // "r is too small" (m2dp.cc:64-67)
+  if (source.points.empty()) return false;                // "source is empty" (:130-133)
+  descriptor->assign(static_cast<size_t>(len), 0.f);
+  const int rc = sm_m2dp(device, &source.points[0].x, static_cast<int64_t>(source.points.size()),
+                         sizeof(data::InnerPointType), r, max_distance, t, p, q, descriptor->data(), len, nullptr);
+  CHECK_GE(rc, 0) << "sm_m2dp failed (" << rc << ")";
+  return rc == 1;
+}
+
 // EigenPointCloud::CalculateNormals on the GPU (cloud_types.cc:347-368); call sites
 // map_builder.cc:286,389 and submap.cc:161.
 inline void CalculateNormalsB200(data::EigenPointCloud* cloud, int device = 0) {

@@ -68,6 +68,11 @@ int sm_destroy(sm_handle* h);
  * every <param> for type 5; the engine itself accepts the pclomp setters hard-coded by the
  * reference: resolution (1.0), step_size (0.1), outlier_ratio (0.55),
  * transformation_epsilon (0.1), max_iterations (35).
+ * SM_TYPE_ICP_PM is NOT a parity implementation of registrator::IcpUsingPointMatcher: libpointmatcher 1.3.1 is
+ * an external float library whose RandomSampling filter draws from std::rand and whose surface-normal filter
+ * uses eigenvector normals; neither can be restated or pinned from the reference tree.  Type 1 is a
+ * deterministic matcher with the same module chain whose results are checked only
+ * against a composition of this repository's own oracle pieces.
  * SM_TYPE_ICP_PM (stand-in for IcpUsingPointMatcher's default libpointmatcher chain,
  * icp_pointmatcher.cc:166-247; float clouds through the _f32 setters) registers no option in the
  * reference either; the engine accepts the IcpFast names (max_iteration defaults to 150, :214)
@@ -195,7 +200,13 @@ int sm_knn1(int device, const double* target_3xn, int64_t n_target, const double
  * mean) + unit normal per valid leaf, survivors in ascending order of the smallest
  * original index of their leaf.  out_points / out_normals: capacity 3*n doubles;
  * *m_out receives the number of survivors.  Called by the reference right before
- * IcpFast::SetInputTarget (map_builder.cc:286,389; submap.cc:161). */
+ * IcpFast::SetInputTarget (map_builder.cc:286,389; submap.cc:161).
+ * DEVIATION from the reference (cloud_types.cc:79-100): there a leaf is represented by
+ * indices[first] and summed in the member order std::nth_element happens to leave, both of which
+ * depend on the standard library's partition internals; here the representative is the member
+ * with the smallest original index and members are summed in ascending index.  The SET of surviving
+ * leaves is identical (the split is order independent for distinct coordinates); the column order
+ * of the output and the last bits of a mean / normal may differ from a run of the real reference. */
 int sm_calculate_normals(int device, const double* points_3xn, int64_t n, double* out_points,
                          double* out_normals, int64_t* m_out);
 
@@ -230,6 +241,22 @@ int sm_motion_compensation_device(int device, const float* dev_points, int64_t n
  * reference's 0.1 m voxels). */
 int sm_voxel_grid_filter(int device, const float* points, int64_t n, int64_t stride_bytes,
                          float voxel_size, float* out, int64_t* m_out);
+
+/* descriptor::M2dp (descriptor/m2dp.cc:37-172; parameters of the constructor, m2dp.h:50-51: r = 0.1,
+ * max_distance = 100, t = 16, p = 4, q = 16), the loop-closure descriptor of a submap:
+ * M2dp::setInputCloud + getFinalDescriptor.  `points`: float x, y, z records `stride_bytes` (>= 12) apart
+ * (data::InnerPointType = 20).  descriptor: p*q + l*t floats, l = ceil(sqrt(max_distance / r)) — [u1; v1],
+ * the first left / right singular vectors of the p*q x l*t signature matrix (:148-152); A_out (optional):
+ * that matrix as counts, row-major.  Returns 1 (true), 0 for an empty cloud (setInputCloud returns false,
+ * :130-133), SM_ERR_BAD_ARGUMENT for r < 1e-6 (:64-67) or a too small `capacity`.
+ * Two orientations are Eigen-internal in the reference and fixed here: each of the first two PCA axes has
+ * its component of largest magnitude positive, and so has u1 (v1 follows).  sm_m2dp_match does not depend
+ * on the second; the first decides which points the reference's |.| projections fold together.
+ * sm_m2dp_match: matchTwoM2dpDescriptors (:155-170) = |Pearson correlation|, -1 for n < 10. */
+int64_t sm_m2dp_descriptor_length(double r, double max_distance, int32_t t, int32_t p, int32_t q);
+int sm_m2dp(int device, const float* points, int64_t n, int64_t stride_bytes, double r, double max_distance,
+            int32_t t, int32_t p, int32_t q, float* descriptor, int64_t capacity, int32_t* A_out);
+double sm_m2dp_match(const float* P, const float* Q, int64_t n);
 
 int sm_device_count(void);
 const char* sm_version(void);

@@ -134,6 +134,15 @@ int sm_oracle_average_transforms(const double* Ts, int32_t n, double* out);
 int64_t sm_oracle_voxel_grid_filter(const float* points, int64_t n, float voxel_size, int order_mode,
                                     float* out);
 
+/* ---- M2DP descriptor (descriptor/m2dp.cc:37-172, see oracle/m2dp_oracle.cc) ------------------ */
+/* descriptor length p*q + l*t with l = ceil(sqrt(max_distance / r)) (m2dp.cc:68); -1 if r < 1e-6. */
+int64_t sm_oracle_m2dp_dims(double r, double max_distance, int32_t t, int32_t p, int32_t q, int32_t* l_out);
+/* M2dp::setInputCloud on packed float xyz; A_out (p*q x l*t counts) and axes_out (mean 3 + axes 9) optional. */
+int64_t sm_oracle_m2dp(const float* points, int64_t n, double r, double max_distance, int32_t t, int32_t p,
+                       int32_t q, float* descriptor, int32_t* A_out, float* axes_out);
+/* matchTwoM2dpDescriptors (m2dp.cc:155-170). */
+double sm_oracle_m2dp_match(const float* P, const float* Q, int64_t n);
+
 /* Pieces exposed for unit tests of the restatement itself. */
 int sm_oracle_solve6(const double* A_colmajor, const double* b, double* x, int* path);
 int sm_oracle_quantile_index(int64_t n, float ratio);

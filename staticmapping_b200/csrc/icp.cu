@@ -308,8 +308,6 @@ static void knn_geometry(int nq, int queries_per_cta, int* grid, int* per_cta) {
   *grid = ceil_div(nq, per);
 }
 
-int knn_configure() { return 0; }   // the staged tree top needs < 48 KB of dynamic shared memory: no opt-in
-
 int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
               int32_t* ids, double* d2, cudaStream_t stream) {
   if (nq <= 0) return 0;

@@ -1043,7 +1043,6 @@ int sm_create(int type, int device, sm_handle** out) {
     return SM_ERR_CUDA;
   }
   h->stream = h->own_stream;
-  if (knn_configure() != 0) { sm_destroy(h); return SM_ERR_CUDA; }
   for (int i = 0; i < 4; ++i) { cudaEventCreate(&h->ev[i]); cudaEventCreate(&h->ev_up[i]); }
   *out = h;
   return SM_OK;
@@ -1421,7 +1420,6 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_CUDA(cudaMemcpyAsync(stage.p, target, (size_t)3 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
   deinterleave3_kernel<<<ceil_div(nt, 256), 256, 0, s>>>((const double*)stage.p, (double*)tgt.p, ts, (int)nt);
   K_CUDA(cudaStreamSynchronize(s));
-  K_OK(knn_configure());
   KdWorkspace ws;
   ws.carve(kdws.p, (int)nt, bucket);
   K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s,

@@ -381,7 +381,8 @@ def AlignPairs(matchers, pairs):
         else:
             src, tgt, nrm = pr["source"], pr["target"], pr["normals"]
             arr[k].source, arr[k].target, arr[k].target_normals = _ptr(src), _ptr(tgt), _ptr(nrm)
-            arr[k].n_source, arr[k].n_target = int(pr.get("n_source", len(src))), int(pr.get("n_target", len(tgt)))
+            arr[k].n_source = int(pr["n_source"]) if "n_source" in pr else len(src)
+            arr[k].n_target = int(pr["n_target"]) if "n_target" in pr else len(tgt)
         g = pr.get("guess")
         if g is not None:
             g = np.ascontiguousarray(np.asarray(g, dtype=np.float64).T).ravel()
@@ -532,3 +533,43 @@ def VoxelGridFilter(cloud, voxel_size, device=0):
     if rc != 0:
         raise RuntimeError(f"sm_voxel_grid_filter failed with {rc}")
     return out[:m.value].copy()
+
+
+class M2dp:
+    """descriptor::M2dp (descriptor/m2dp.h:45-84) on the GPU: setInputCloud / getFinalDescriptor."""
+
+    def __init__(self, r=0.1, max_distance=100.0, t=16, p=4, q=16, device=0):
+        self.r, self.max_distance, self.t, self.p, self.q, self.device = float(r), float(max_distance), int(t), int(p), int(q), device
+        self._descriptor = None
+        self.signature_matrix = None
+
+    def setInputCloud(self, cloud):
+        """cloud: InnerCloud or (N,3)/(N,5) float32 array.  Returns False for an empty cloud (m2dp.cc:130-133)."""
+        pts = cloud.points if isinstance(cloud, InnerCloud) else np.ascontiguousarray(np.asarray(cloud, dtype=np.float32))
+        lib = _lib.lib()
+        n = lib.sm_m2dp_descriptor_length(self.r, self.max_distance, self.t, self.p, self.q)
+        if n < 0:
+            raise CheckFailure("M2dp: r is too small (m2dp.cc:64-67) or bad parameters")
+        desc = np.zeros(n, np.float32)
+        A = np.zeros((self.p * self.q, (n - self.p * self.q)), np.int32)
+        rc = lib.sm_m2dp(self.device, pts.ctypes.data, pts.shape[0], 4 * pts.shape[1], self.r, self.max_distance,
+                         self.t, self.p, self.q, desc.ctypes.data, n, A.ctypes.data)
+        if rc == -20:
+            raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
+        if rc < 0:
+            raise CheckFailure(f"sm_m2dp failed with {rc}")
+        if rc == 0:
+            return False
+        self._descriptor, self.signature_matrix = desc, A
+        return True
+
+    def getFinalDescriptor(self):
+        return self._descriptor
+
+
+def matchTwoM2dpDescriptors(P, Q):
+    """descriptor::matchTwoM2dpDescriptors (m2dp.cc:155-170): |Pearson correlation| in (0, 1), -1 on mismatch."""
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    if P.shape != Q.shape:
+        return -1.0
+    return float(_lib.lib().sm_m2dp_match(P.ctypes.data, Q.ctypes.data, P.shape[0]))

@@ -341,3 +341,38 @@ def voxel_grid_filter(points5, voxel_size, order_mode=0):
     f.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]
     m = f(p.ctypes.data, p.shape[0], float(voxel_size), int(order_mode), out.ctypes.data)
     return m, out[:max(m, 0)].copy()
+
+
+# ---- M2DP descriptor (oracle/m2dp_oracle.cc) --------------------------------------------------------
+def m2dp(points, r=0.1, max_distance=100.0, t=16, p=4, q=16, with_matrix=False):
+    """descriptor::M2dp::setInputCloud + getFinalDescriptor.  Returns the descriptor (p*q + l*t floats),
+    or (descriptor, A counts (p*q, l*t), mean+axes (12,)) with with_matrix."""
+    pts = _fcloud(points)
+    L = lib()
+    L.sm_oracle_m2dp_dims.restype = C.c_int64
+    L.sm_oracle_m2dp_dims.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    l = C.c_int32(0)
+    n = L.sm_oracle_m2dp_dims(r, max_distance, t, p, q, C.byref(l))
+    if n < 0:
+        raise ValueError("r is too small")
+    desc = np.zeros(n, np.float32)
+    A = np.zeros((p * q, l.value * t), np.int32)
+    axes = np.zeros(12, np.float32)
+    L.sm_oracle_m2dp.restype = C.c_int64
+    L.sm_oracle_m2dp.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    got = L.sm_oracle_m2dp(pts.ctypes.data, pts.shape[0], r, max_distance, t, p, q, desc.ctypes.data, A.ctypes.data,
+                           axes.ctypes.data)
+    if got == 0:
+        return (None, None, None) if with_matrix else None
+    return (desc, A, axes) if with_matrix else desc
+
+
+def m2dp_match(P, Q):
+    P = np.ascontiguousarray(P, np.float32); Q = np.ascontiguousarray(Q, np.float32)
+    if P.shape != Q.shape:
+        return -1.0
+    L = lib()
+    L.sm_oracle_m2dp_match.restype = C.c_double
+    L.sm_oracle_m2dp_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    return L.sm_oracle_m2dp_match(P.ctypes.data, Q.ctypes.data, P.shape[0])

