@@ -150,8 +150,11 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 // (neighbouring threads walk the same nodes and buckets); every CTA stages the top levels of the
 // tree into shared memory with bulk async copies while its threads load and transform their
 // queries (knn_smem.cuh).
+#ifndef SMB_KNN_MIN_CTAS
+#define SMB_KNN_MIN_CTAS 4
+#endif
 template <bool kAllSmem>
-__global__ void __launch_bounds__(kKnnCtaThreads)
+__global__ void __launch_bounds__(kKnnCtaThreads, SMB_KNN_MIN_CTAS)
 icp_knn_kernel(IcpBuffers b, IcpParams p, int per_cta) {
   extern __shared__ __align__(128) unsigned char knn_smem[];
   if (b.state->done) return;

@@ -46,6 +46,8 @@ struct SmemTree {
   const uint8_t* g_dim;
   const double* pb;         // padded buckets
   int levels;
+  double* sq;               // this thread's query: sq[d * kKnnCtaThreads] (shared memory, d = 0..2)
+  double* so;               // this thread's off[] of the recursion, same layout
 };
 
 // ---- mbarrier + bulk async copy (TMA engine, non-tensor form) --------------------------------
@@ -80,7 +82,8 @@ __host__ __device__ __forceinline__ int knn_smem_slots(int levels) {
   return n < 16 ? 16 : n;
 }
 __host__ __device__ __forceinline__ size_t knn_smem_bytes(int levels) {
-  return (size_t)knn_smem_slots(levels) * 9 + 16 + 16 * sizeof(double);   // nodes, barrier (+pad), 16 doubles
+  // nodes, barrier (+pad), 16 doubles, per-thread query / offset columns
+  return (size_t)knn_smem_slots(levels) * 9 + 16 + 16 * sizeof(double) + 6 * (size_t)kKnnCtaThreads * sizeof(double);
 }
 
 // Called by ALL threads of the CTA (contains __syncthreads).  Thread 0 arms the barrier and
@@ -108,6 +111,8 @@ __device__ __forceinline__ SmemTree stage_tree(const KdCompact& t, unsigned char
   SmemTree st;
   st.s_cut = s_cut; st.s_dim = s_dim; st.n_smem = slots;
   st.g_cut = t.cut; st.g_dim = t.dim; st.pb = t.pb; st.levels = t.levels;
+  st.sq = *extra_out + 16 + threadIdx.x;
+  st.so = st.sq + 3 * kKnnCtaThreads;
   return st;
 }
 
@@ -161,39 +166,41 @@ __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int b
 }
 
 constexpr int kKnnMaxStack = 32;
+
+// The coordinate of the query / the recursion's off[] along a node's cut dimension are read from
+// per-thread shared-memory columns indexed by that dimension (one LDS instead of a three-way select
+// on register pairs: the descent loop of a far visit shrank from 69 to ~30 SASS instructions a level).
 struct KnnStackEntry {
-  double rd, ox, oy, oz;
+  double rd;
+  double o[3];
   int h, pad;
 };
 
-// recurseKnn on the subtree rooted at heap node h with the recursion's (rd, off) at entry:
-// near child first; a far child is pushed if it passes rd_new*(1+eps)^2 < head now (the head only
-// shrinks) and re-tested when popped, which is when the recursion tests it.
-template <bool kAllSmem>
+// recurseKnn on the subtree rooted at heap node h with the recursion's rd at entry; its off[] is in
+// t.so.  Near child first; a far child is pushed if it passes rd_new*(1+eps)^2 < head now (the head
+// only shrinks) and re-tested when popped, which is when the recursion tests it.  Far subtrees start
+// deep in the tree: nodes come through the read-only path (L1).
 __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, double qy, double qz, double me2,
-                                              int h, double rd, double ox, double oy, double oz,
-                                              double& head, int& best) {
+                                              int h, double rd, double& head, int& best) {
   KnnStackEntry stack[kKnnMaxStack];
   int sp = 0;
   while (true) {
     int l = 31 - __clz(h + 1);
     while (l < t.levels) {
-      double cut; int cd;
-      tree_node<kAllSmem>(t, h, cut, cd);
+      const int cd = __ldg(t.g_dim + h);
       if (cd == 3) break;
-      const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-      const double old_off = cd == 0 ? ox : (cd == 1 ? oy : oz);
-      const int right = q > cut ? 1 : 0;              // == (q - cut > 0) for IEEE doubles
+      const double cut = __ldg(t.g_cut + h);
+      const double q = t.sq[cd * kKnnCtaThreads];
+      const double old_off = t.so[cd * kKnnCtaThreads];
       const double new_off = dsub(q, cut);
       const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+      const int right = q > cut ? 1 : 0;              // == (q - cut > 0) for IEEE doubles
       if (dmul(rd_new, me2) < head && sp < kKnnMaxStack) {
-        KnnStackEntry e;
+        KnnStackEntry& e = stack[sp++];
         e.rd = rd_new;
-        e.ox = cd == 0 ? new_off : ox;
-        e.oy = cd == 1 ? new_off : oy;
-        e.oz = cd == 2 ? new_off : oz;
-        e.h = 2 * h + 2 - right; e.pad = 0;
-        stack[sp++] = e;
+        e.o[0] = t.so[0]; e.o[1] = t.so[kKnnCtaThreads]; e.o[2] = t.so[2 * kKnnCtaThreads];
+        e.o[cd] = new_off;
+        e.h = 2 * h + 2 - right;
       }
       h = 2 * h + 1 + right;
       ++l;
@@ -201,9 +208,10 @@ __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, doub
     scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
     bool found = false;
     while (sp > 0) {
-      const KnnStackEntry e = stack[--sp];
+      const KnnStackEntry& e = stack[--sp];
       if (dmul(e.rd, me2) < head) {
-        h = e.h; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz;
+        h = e.h; rd = e.rd;
+        t.so[0] = e.o[0]; t.so[kKnnCtaThreads] = e.o[1]; t.so[2 * kKnnCtaThreads] = e.o[2];
         found = true;
         break;
       }
@@ -218,14 +226,23 @@ __device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double q
                                           int& best_out, double& d2_out) {
   double head = __longlong_as_double(0x7ff0000000000000ll);
   int best = -1;
+  t.sq[0] = qx; t.sq[kKnnCtaThreads] = qy; t.sq[2 * kKnnCtaThreads] = qz;
+  const int lsm = kAllSmem ? t.levels : min(t.levels, kKnnSmemLevels);    // levels staged in shared memory
   int h = 0, l = 0;
-  while (l < t.levels) {
-    double cut; int cd;
-    tree_node<kAllSmem>(t, h, cut, cd);
-    if (cd == 3) break;
-    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-    h = 2 * h + 1 + (q > cut ? 1 : 0);
+  bool leaf = false;
+  while (l < lsm) {
+    const int cd = t.s_dim[h];
+    if (cd == 3) { leaf = true; break; }
+    h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > t.s_cut[h] ? 1 : 0);
     ++l;
+  }
+  if (!kAllSmem && !leaf) {
+    while (l < t.levels) {
+      const int cd = __ldg(t.g_dim + h);
+      if (cd == 3) break;
+      h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > __ldg(t.g_cut + h) ? 1 : 0);
+      ++l;
+    }
   }
   scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
   // Root frame.  Path node of level a: ((h+1) >> (l-a)) - 1.  rd = 0 and off = 0 along the whole
@@ -234,26 +251,31 @@ __device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double q
   // deepest first, each re-tested with the head of that moment.
   const int hp1 = h + 1, ll = l;
   uint32_t mask = 0u;
+  const int lsm2 = min(ll, lsm);
 #pragma unroll 2
-  for (int a = 0; a < ll; ++a) {
-    double cut; int cd;
-    tree_node<kAllSmem>(t, (hp1 >> (ll - a)) - 1, cut, cd);
-    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-    const double off = dsub(q, cut);
+  for (int a = 0; a < lsm2; ++a) {
+    const int n = (hp1 >> (ll - a)) - 1;
+    const double off = dsub(t.sq[t.s_dim[n] * kKnnCtaThreads], t.s_cut[n]);
+    if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
+  }
+#pragma unroll 2
+  for (int a = lsm2; a < ll; ++a) {
+    const int n = (hp1 >> (ll - a)) - 1;
+    const double off = dsub(t.sq[__ldg(t.g_dim + n) * kKnnCtaThreads], __ldg(t.g_cut + n));
     if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
   }
   while (mask != 0u) {
     const int a = 31 - __clz(mask);
     mask &= ~(1u << a);
-    double cut; int cd;
-    tree_node<kAllSmem>(t, (hp1 >> (ll - a)) - 1, cut, cd);
-    const double q = cd == 0 ? qx : (cd == 1 ? qy : qz);
-    const double off = dsub(q, cut);
+    const int n = (hp1 >> (ll - a)) - 1;
+    const int cd = __ldg(t.g_dim + n);
+    const double off = dsub(t.sq[cd * kKnnCtaThreads], __ldg(t.g_cut + n));
     const double rd_new = dmul(off, off);
     if (dmul(rd_new, me2) < head) {
+      t.so[0] = 0.0; t.so[kKnnCtaThreads] = 0.0; t.so[2 * kKnnCtaThreads] = 0.0;
+      t.so[cd * kKnnCtaThreads] = off;
       const int near_p1 = hp1 >> (ll - a - 1);       // path node of level a+1, plus one
-      visit_subtree<kAllSmem>(t, qx, qy, qz, me2, (near_p1 ^ 1) - 1, rd_new, cd == 0 ? off : 0.0,
-                              cd == 1 ? off : 0.0, cd == 2 ? off : 0.0, head, best);
+      visit_subtree(t, qx, qy, qz, me2, (near_p1 ^ 1) - 1, rd_new, head, best);
     }
   }
   best_out = best;

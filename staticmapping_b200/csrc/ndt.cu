@@ -58,13 +58,24 @@ ndt_minmax_partial_kernel(const float* __restrict__ pts, int n, float* __restric
   }
 }
 
-__global__ void ndt_grid_params_kernel(const float* __restrict__ partial, int nparts, float resolution,
-                                       NdtGrid* __restrict__ grid) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256)
+ndt_grid_params_kernel(const float* __restrict__ partial, int nparts, float resolution, NdtGrid* __restrict__ grid) {
+  __shared__ float smn[3][8], smx[3][8];
   float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
   float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
-  for (int b = 0; b < nparts; ++b)
+  for (int b = threadIdx.x; b < nparts; b += 256)
     for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], partial[b * 6 + d]); mx[d] = fmaxf(mx[d], partial[b * 6 + 3 + d]); }
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[d][threadIdx.x >> 5] = mn[d]; smx[d][threadIdx.x >> 5] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int d = 0; d < 3; ++d)
+    for (int w = 0; w < 8; ++w) { mn[d] = fminf(mn[d], smn[d][w]); mx[d] = fmaxf(mx[d], smx[d][w]); }
   const float inv = 1.0f / resolution;
   grid->inv_leaf = inv;
   for (int d = 0; d < 3; ++d) {   // _impl.hpp:88-97
@@ -606,7 +617,7 @@ void NdtWorkspace::carve(void* base, int nt, int ns) {
 int ndt_build_grid(const float* tgt, int nt, float resolution, NdtWorkspace& ws, cudaStream_t stream) {
   const int nparts = nt < 256 * 512 ? ceil_div(nt, 256) : 512;
   ndt_minmax_partial_kernel<<<nparts, 256, 0, stream>>>(tgt, nt, ws.minmax);
-  ndt_grid_params_kernel<<<1, 32, 0, stream>>>(ws.minmax, nparts, resolution, ws.grid);
+  ndt_grid_params_kernel<<<1, 256, 0, stream>>>(ws.minmax, nparts, resolution, ws.grid);
   ndt_key_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(tgt, nt, ws.grid, ws.keys[0], ws.order[0]);
   int rc = radix_sort_pairs_u64(ws.keys[0], ws.order[0], ws.keys[1], ws.order[1], nt, 1, ws.stride,
                                 ws.scratch, stream, 4);

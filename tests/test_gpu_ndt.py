@@ -68,3 +68,25 @@ def test_ndt_rejects_any_xml_param():
 def test_create_matcher_ndt():
     m = smb.CreateMatcher(smb.MatcherOptions(type=smb.Type.kNdt))
     assert m.GetType() == smb.Type.kNdt
+
+
+def test_fitness_score_with_far_and_outside_points():
+    # getFitnessScore needs the EXACT nearest neighbour of every source point, however far: the grid ring
+    # search must agree with the oracle's k-d tree for points several cells away from any target point
+    # and for points outside the grid's bounding box
+    src, sub, P = _pair(1)
+    rng = np.random.default_rng(11)
+    far = np.concatenate([
+        sub[:50] + np.array([0.0, 0.0, 7.5], np.float32),            # a few metres above the scene
+        sub[:50] + np.array([0.0, 0.0, -3.2], np.float32),           # below the ground
+        rng.uniform(-1, 1, (40, 3)).astype(np.float32) * 5 + np.array([160.0, -140.0, 30.0], np.float32),   # far outside
+    ])
+    src2 = np.concatenate([src, far]).astype(np.float32)
+    m = smb.Ndt()
+    m.SetInputSource(smb.InnerCloud(src2))
+    m.SetInputTarget(smb.InnerCloud(sub))
+    ok, res = m.Align(np.eye(4))
+    o = O.ndt_align(src2, sub)
+    assert m.GetAlignInfo()["iterations"] == o["iterations"]
+    assert abs(m.GetFitnessScore() - o["fitness"]) <= 1e-9 * max(1.0, o["fitness"])
+    assert o["fitness"] > 10.0                                       # the far points dominate the mean: they were found
