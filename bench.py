@@ -52,9 +52,9 @@ ITERATIONS = 30
 BYTES_PER_POINT_ITER = 64           # whole iteration
 BYTES_KNN_PER_POINT = 40            # of which the k-NN kernel: 16 src + 16 matched + 8 write
 # dram__bytes_read + dram__bytes_write of ONE launch of icp_knn_kernel from the committed
-# `ncu --set full` capture (profiles/r02_ncu_full_icp_knn_kernel.txt; ncu flushes the caches
+# `ncu --set full` capture (profiles/r02_ncu_full_icp_knn_accum_finish.txt; ncu flushes the caches
 # before the launch, so this is the cold figure; the steady state of an alignment is lower)
-NCU_TRAFFIC_BYTES = 8_500_000
+NCU_TRAFFIC_BYTES = 6_284_288
 KNN_KERNEL = "icp_knn_kernel"
 METRIC = "scan-pair alignments/sec (120k->500k pts, 30 ICP iters)"
 UNIT = "alignments/s"
@@ -594,7 +594,7 @@ def run_extra(args, smb, torch, dist, parallel, dev, rank, local_rank, world, pa
         src, sub, _ = make_workload(rank * pairs_per_rank + k)
         clouds.append((InnerCloud(src.astype(np.float32)), InnerCloud(sub.astype(np.float32))))
     out = {}
-    for name, cls, total_pairs in (("ndt", smb.Ndt, 64 * world), ("ndt_gicp", smb.NdtWithGicp, NDT_GICP_PAIRS)):
+    for name, cls, total_pairs in (("ndt", smb.Ndt, 512 * world), ("ndt_gicp", smb.NdtWithGicp, NDT_GICP_PAIRS)):
         ms_ = []
         for k in range(npairs):
             m = cls(local_rank)
@@ -607,31 +607,39 @@ def run_extra(args, smb, torch, dist, parallel, dev, rank, local_rank, world, pa
         torch.cuda.synchronize()
         t0 = time.perf_counter(); ms_[0].Align(np.eye(4)); lat = time.perf_counter() - t0
         share = max(npairs, total_pairs // world)
-        if world > 1:
+        if world > 1:                                                  # warm the collective on this record size
+            t = torch.zeros((share, parallel.POSE_RECORD), dtype=torch.float64, device=dev)
+            dist.all_gather([torch.empty_like(t) for _ in range(world)], t)
             dist.barrier()
-        # wall time: these optimisers are driven from the host (Newton / BFGS steps with a read-back each)
+        torch.cuda.synchronize()
+        # wall time, barrier to the end of the pose all-gather: these optimisers are driven from the host
+        # (Newton / BFGS steps with a read-back each), so device events would miss the host part
         done, t0 = 0, time.perf_counter()
-        res = None
+        all_res, all_sc = [], []
         while done < share:
             oks, res = smb.AlignBatch(ms_, guesses)
+            all_res.extend(res); all_sc.extend(m.GetFitnessScore() for m in ms_)
             done += npairs
-        secs = time.perf_counter() - t0
-        sc = [m.GetFitnessScore() for m in ms_]
         ag_ms = 0.0
         if world > 1:
-            rec = parallel.pack_poses(list(res), list(sc))
+            rec = parallel.pack_poses(all_res, all_sc)                 # every pose of the shard: 136 B per pair
             t = torch.from_numpy(rec).to(dev)
             outl = [torch.empty_like(t) for _ in range(world)]
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); dist.all_gather(outl, t); e1.record(); e1.synchronize()
-            ag_ms = e0.elapsed_time(e1)
+            dist.all_gather(outl, t)
+            torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        if world > 1:
             tt = torch.tensor([secs], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             secs = float(tt.item())
-        rec = {"pairs_total": done * world, "pairs_per_s": done * world / (secs + ag_ms * 1e-3),
+            dist.barrier()                                             # the collective alone, ranks aligned
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); dist.all_gather(outl, t); e1.record(); e1.synchronize()
+            ag_ms = e0.elapsed_time(e1)
+        rec = {"pairs_total": done * world, "pairs_per_s": done * world / secs,
                "ms_per_alignment_one_in_flight": lat * 1e3, "instances_in_flight_per_gpu": npairs,
                "allgather_ms": ag_ms, "iterations": info["iterations"], "evaluations": info["evaluations"],
-               "timing": "wall clock between barriers, max over ranks",
+               "timing": "wall clock from a barrier to the end of the pose all-gather, max over ranks",
                "result_check": res1.tolist()}
         if name == "ndt":
             nbar = info["mean_neighbors"]

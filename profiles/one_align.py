@@ -1,0 +1,18 @@
+#!/usr/bin/env python
+"""N single IcpFast alignments of the benchmark pair (one in flight, default options, host buffers):
+the workload the ncu captures under profiles/ are taken from."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+import staticmapping_b200 as smb
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+src, sub, _ = bench.make_workload(0)
+tgt = smb.CalculateNormals(sub)
+m = smb.IcpFast(0)
+m.InitWithXml({"max_iteration": 30, "disable_convergence_check": 1, "use_graphs": 0})
+for _ in range(n):
+    m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tgt.points, tgt.normals))
+    ok, res = m.Align(np.eye(4))
+print("iterations", m.GetAlignInfo()["iterations"], "score", m.GetFitnessScore())
