@@ -216,6 +216,169 @@ kd_part_scatter_kernel(const uint32_t* __restrict__ lists, uint32_t* __restrict_
   lists_out[d * lstride + pos] = pid;
 }
 
+// ---- the bottom of the tree inside one CTA ------------------------------------------------------
+// Once a node's segment fits a CTA's shared memory (<= kSubMax points) its whole subtree is finished by
+// ONE CTA: the same four steps per level (nodes, side flags, stable partition of the three lists), with
+// __syncthreads between them instead of four launches per level.  For a 106 784-point target the global
+// passes stop at level 6 (segments of <= 1 669 points) and 64 CTAs do levels 6..13: 56 launches become 25.
+// The tree is the same one (same medians, same tie rule, same implicit bounds): it is checked through the
+// bit-exact k-NN tests and the CalculateNormals leaf counts.
+constexpr int kSubThreads = 256;
+constexpr int kSubItems = 8;
+constexpr int kSubMax = kSubThreads * kSubItems;     // 2048 points
+constexpr int kSubNodes = 256;                       // a level with an inner node has <= count / bucket nodes
+
+__host__ __device__ __forceinline__ int kd_sub_capacity(int bucket) { return min(kSubMax, kSubNodes * bucket); }
+
+struct SubSeg { int jl, first, count; bool at_level; };
+// local position i of a subtree segment of `count0` points -> the node of local level k containing it
+__device__ __forceinline__ SubSeg sub_locate(int i, int k, int count0, int bucket) {
+  int first = 0, count = count0, jl = 0;
+  for (int l = 0; l < k; ++l) {
+    if (count <= bucket) return SubSeg{jl, first, count, false};
+    const int right = count >> 1, left = count - right;
+    if (i < first + left) { jl = 2 * jl; count = left; }
+    else { jl = 2 * jl + 1; first += left; count = right; }
+  }
+  return SubSeg{jl, first, count, true};
+}
+
+__global__ void __launch_bounds__(kSubThreads)
+kd_subtree_kernel(const double* __restrict__ coord, int64_t cstride, uint32_t* __restrict__ lists, int64_t lstride,
+                  int n, int bucket, int Lg, int levels, const double* __restrict__ bounds_in,
+                  uint8_t* __restrict__ flag, KdNode* __restrict__ nodes, double* __restrict__ ccut,
+                  uint8_t* __restrict__ cdim) {
+  __shared__ uint32_t s_list[3][kSubMax];
+  __shared__ uint32_t s_scan[kSubMax + 1];
+  __shared__ double s_bounds[kSubNodes][6];
+  __shared__ int s_ndim[kSubNodes];
+  __shared__ uint32_t s_warp[kSubThreads / 32];
+  __shared__ int s_any_inner;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int j0 = blockIdx.x;
+  const Seg seg0 = locate_node(j0, Lg, n, bucket);
+  if (!seg0.exists || seg0.count <= bucket) {                // a leaf (or nothing) at level Lg: kd_leaf_kernel's job
+    if (seg0.exists && cdim && Lg < levels && threadIdx.x == 0) cdim[(1 << Lg) - 1 + j0] = 3;
+    return;
+  }
+  const int count0 = seg0.count;
+  for (int d = 0; d < 3; ++d)
+    for (int i = t; i < count0; i += kSubThreads) s_list[d][i] = lists[d * lstride + seg0.first + i];
+  if (t < 6) {
+    if (Lg == 0) {     // root bounds: per-axis min / max of the data (the sorted lists' ends)
+      const int d = t % 3;
+      const uint32_t pid = lists[d * lstride + (t < 3 ? 0 : n - 1)];
+      s_bounds[0][t] = coord[d * cstride + pid];
+    } else {
+      s_bounds[0][t] = bounds_in[(int64_t)j0 * 6 + t];
+    }
+  }
+  __syncthreads();
+  for (int k = 0; Lg + k < levels; ++k) {
+    const int L = Lg + k, nnodes = 1 << k;
+    if (t == 0) s_any_inner = 0;
+    __syncthreads();
+    // ---- nodes of this level (children bounds are formed in registers and stored after the barrier) ----
+    double bl[6], br[6];
+    bool has_children = false;
+    for (int jl = t; jl < nnodes; jl += kSubThreads) {        // > kSubThreads nodes only on all-leaf levels
+      int first = 0, count = count0;
+      bool exists = true;
+      for (int l = k - 1; l >= 0; --l) {
+        if (count <= bucket) { exists = false; break; }
+        const int right = count >> 1, left = count - right;
+        if ((jl >> l) & 1) { first += left; count = right; } else { count = left; }
+      }
+      if (jl < kSubNodes) s_ndim[jl] = 3;
+      if (!exists) continue;
+      const int h = (1 << L) - 1 + ((j0 << k) | jl);
+      if (count <= bucket) {
+        KdNode leaf;
+        leaf.cut = __longlong_as_double(((long long)count << 32) | (long long)(unsigned)(seg0.first + first));
+        leaf.dim = 3; leaf.pad = 0;
+        nodes[blocked_index(h)] = leaf;
+        if (cdim) cdim[h] = 3;
+        continue;
+      }
+      double mn[3], mx[3];
+      for (int d = 0; d < 3; ++d) { mn[d] = s_bounds[jl][d]; mx[d] = s_bounds[jl][3 + d]; }
+      const int dim = argmax3(dsub(mx[0], mn[0]), dsub(mx[1], mn[1]), dsub(mx[2], mn[2]));
+      const int left = count - (count >> 1);
+      const uint32_t pid = s_list[dim][first + left];
+      const double cut = coord[dim * cstride + pid];
+      KdNode nd; nd.cut = cut; nd.dim = dim; nd.pad = 0;
+      nodes[blocked_index(h)] = nd;
+      if (ccut) { ccut[h] = cut; cdim[h] = (uint8_t)dim; }
+      s_ndim[jl] = dim;
+      s_any_inner = 1;
+      for (int d = 0; d < 3; ++d) {
+        bl[d] = mn[d]; bl[3 + d] = (d == dim) ? cut : mx[d];
+        br[d] = (d == dim) ? cut : mn[d]; br[3 + d] = mx[d];
+      }
+      has_children = true;                                     // inner nodes only exist while nnodes <= kSubNodes
+    }
+    __syncthreads();
+    if (!s_any_inner) break;
+    if (has_children && 2 * t + 1 < kSubNodes) {
+      for (int d = 0; d < 6; ++d) { s_bounds[2 * t][d] = bl[d]; s_bounds[2 * t + 1][d] = br[d]; }
+    }
+    // NOTE: with nnodes <= kSubNodes / 2 every inner node is handled by thread jl == t (one node per thread)
+    // ---- side flags + per-item node data ---------------------------------------------------------------
+    int it_first[kSubItems], it_left[kSubItems];
+    bool it_inner[kSubItems];
+#pragma unroll
+    for (int r = 0; r < kSubItems; ++r) {
+      const int i = t * kSubItems + r;
+      it_inner[r] = false; it_first[r] = 0; it_left[r] = 0;
+      if (i < count0) {
+        const SubSeg sg = sub_locate(i, k, count0, bucket);
+        if (sg.at_level && sg.count > bucket) {
+          const int dim = s_ndim[sg.jl];
+          it_inner[r] = true; it_first[r] = sg.first; it_left[r] = sg.count - (sg.count >> 1);
+          flag[s_list[dim][i]] = (i - sg.first >= it_left[r]) ? 1 : 0;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stable partition of the three lists (block scan of the left flags, in place) ------------------------
+    for (int d = 0; d < 3; ++d) {
+      uint32_t pid[kSubItems], isleft[kSubItems], cnt = 0;
+#pragma unroll
+      for (int r = 0; r < kSubItems; ++r) {
+        const int i = t * kSubItems + r;
+        pid[r] = i < count0 ? s_list[d][i] : 0u;
+        isleft[r] = (i < count0 && it_inner[r]) ? (flag[pid[r]] == 0 ? 1u : 0u) : 1u;
+        cnt += isleft[r];
+      }
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      if (lane == 31) s_warp[w] = incl;
+      __syncthreads();
+      uint32_t wb = 0;
+      for (int ww = 0; ww < w; ++ww) wb += s_warp[ww];
+      uint32_t run = wb + incl - cnt;
+#pragma unroll
+      for (int r = 0; r < kSubItems; ++r) { s_scan[t * kSubItems + r] = run; run += isleft[r]; }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kSubItems; ++r) {
+        const int i = t * kSubItems + r;
+        if (i >= count0) continue;
+        int pos = i;
+        if (it_inner[r]) {
+          const int rank_left = (int)(s_scan[i] - s_scan[it_first[r]]);
+          pos = isleft[r] ? it_first[r] + rank_left : it_first[r] + it_left[r] + ((i - it_first[r]) - rank_left);
+        }
+        s_list[d][pos] = pid[r];      // every position is read (into registers) before the barrier above
+      }
+      __syncthreads();
+    }
+  }
+  // the x-ordered list, partitioned down to the leaves, goes back for kd_leaf_kernel
+  for (int i = t; i < count0; i += kSubThreads) lists[seg0.first + i] = s_list[0][i];
+}
+
 // ---- leaves: canonical (ascending original index) order ---------------------------------
 __global__ void kd_leaf_kernel(const uint32_t* __restrict__ list0, int n, int bucket, int levels,
                                KdNode* __restrict__ nodes, uint32_t* __restrict__ leaf_order) {
@@ -343,7 +506,14 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
   if (rc) return rc;
   int cur = 0;
   const int nblk = ceil_div(n, kPartTile);
-  for (int L = 0; L < levels; ++L) {
+  // global passes down to the level whose segments fit one CTA, the rest of every subtree in shared memory
+  int Lg = 0;
+  {
+    const int cap = kd_sub_capacity(bucket);
+    int64_t c = n;
+    while (Lg < levels && c > cap) { c = (c + 1) / 2; ++Lg; }
+  }
+  for (int L = 0; L < Lg; ++L) {
     const int nodes_l = 1 << L;
     kd_node_kernel<<<ceil_div(nodes_l, 128), 128, 0, stream>>>(
         coord, cstride, ws.lists[cur], ls, n, bucket, L, ws.bounds[L & 1], ws.bounds[(L + 1) & 1],
@@ -362,6 +532,9 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
     }
     cur ^= 1;
   }
+  if (Lg < levels)
+    kd_subtree_kernel<<<1 << Lg, kSubThreads, 0, stream>>>(coord, cstride, ws.lists[cur], ls, n, bucket, Lg, levels,
+                                                          ws.bounds[Lg & 1], ws.flag, nodes, ccut, cdim);
   const int total = (1 << (levels + 1)) - 1;
   kd_leaf_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(ws.lists[cur], n, bucket, levels,
                                                           nodes, leaf_order);
