@@ -131,7 +131,8 @@ __device__ __forceinline__ bool cand_less(double d, int id, double wd, int wid) 
 __device__ __forceinline__ void knn_k(const KdNode* __restrict__ nodes, const BucketPoint* __restrict__ bpts,
                                       double qx, double qy, double qz, double* bd, int* bi, int* cnt_out) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  int cnt = 0;
+  int cnt = 0, wpos = 0, worst_id = 0x7fffffff;
+  double worst = inf;                 // (worst, worst_id): the maximum of the held set once kK are held
   StackEntry stack[kMaxStack];
   int sp = 0, idx = 0;
   double rd = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
@@ -145,8 +146,7 @@ __device__ __forceinline__ void knn_k(const KdNode* __restrict__ nodes, const Bu
       const double new_off = dsub(q, nd.cut);
       const int right = new_off > 0.0 ? 1 : 0;
       const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
-      const double worst = cnt < kK ? inf : bd[kK - 1];
-      if (rd_new <= worst && sp < kMaxStack) {
+      if ((cnt < kK || rd_new <= worst) && sp < kMaxStack) {
         StackEntry e;
         e.rd = rd_new;
         e.ox = cd == 0 ? new_off : ox; e.oy = cd == 1 ? new_off : oy; e.oz = cd == 2 ? new_off : oz;
@@ -164,25 +164,38 @@ __device__ __forceinline__ void knn_k(const KdNode* __restrict__ nodes, const Bu
         const double dx = dsub(qx, p.x), dy = dsub(qy, p.y), dz = dsub(qz, p.z);
         const double d = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
         const int id = (int)p.id;
-        if (cnt < kK || cand_less(d, id, bd[kK - 1], bi[kK - 1])) {
-          int pos = cnt < kK ? cnt : kK - 1;
-          while (pos > 0 && cand_less(d, id, bd[pos - 1], bi[pos - 1])) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
-          bd[pos] = d; bi[pos] = id;
-          if (cnt < kK) ++cnt;
+        // the held set is UNSORTED with its maximum tracked (worst, wpos): a candidate costs one compare,
+        // an accepted one a 20-entry rescan — no shifting of a sorted list through local memory
+        if (cnt < kK) {
+          bd[cnt] = d; bi[cnt] = id; ++cnt;
+          if (cnt == kK) {
+            worst = bd[0]; worst_id = bi[0]; wpos = 0;
+            for (int j = 1; j < kK; ++j) if (cand_less(worst, worst_id, bd[j], bi[j])) { worst = bd[j]; worst_id = bi[j]; wpos = j; }
+          }
+        } else if (cand_less(d, id, worst, worst_id)) {
+          bd[wpos] = d; bi[wpos] = id;
+          worst = bd[0]; worst_id = bi[0]; wpos = 0;
+          for (int j = 1; j < kK; ++j) if (cand_less(worst, worst_id, bd[j], bi[j])) { worst = bd[j]; worst_id = bi[j]; wpos = j; }
         }
       }
     }
     bool found = false;
     while (sp > 0) {
       const StackEntry e = stack[--sp];
-      if (cnt < kK || e.rd <= bd[kK - 1]) { idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz; found = true; break; }
+      if (cnt < kK || e.rd <= worst) { idx = e.idx; rd = e.rd; ox = e.ox; oy = e.oy; oz = e.oz; found = true; break; }
     }
     if (!found) break;
+  }
+  for (int a = 1; a < cnt; ++a) {     // ascending (d, id): the order the covariance sums are formed in
+    const double d = bd[a]; const int id = bi[a];
+    int b = a - 1;
+    while (b >= 0 && cand_less(d, id, bd[b], bi[b])) { bd[b + 1] = bd[b]; bi[b + 1] = bi[b]; --b; }
+    bd[b + 1] = d; bi[b + 1] = id;
   }
   *cnt_out = cnt;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 gicp_knn20_cov_kernel(const float* __restrict__ cloud, int n, const KdNode* __restrict__ nodes,
                       const BucketPoint* __restrict__ bpts, double eps, double* __restrict__ covs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,8 +299,11 @@ constexpr int kCostSums = 13;
 
 __global__ void __launch_bounds__(256)
 gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict__ tgt, GicpCostParams P,
-                 const int32_t* __restrict__ match, const double* __restrict__ maha, double* __restrict__ partials) {
+                 const int32_t* __restrict__ match, const double* __restrict__ maha, double* __restrict__ partials,
+                 double* __restrict__ sums, uint32_t* __restrict__ ticket, double* __restrict__ host_sums,
+                 volatile long long* __restrict__ host_flag, long long seq) {
   __shared__ double red[8][kCostSums];
+  __shared__ bool is_last;
   double acc[kCostSums];
 #pragma unroll
   for (int k = 0; k < kCostSums; ++k) acc[k] = 0.0;
@@ -324,17 +340,27 @@ gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict_
     for (int ww = 0; ww < 8; ++ww) v += red[ww][threadIdx.x];
     partials[(int64_t)blockIdx.x * kCostSums + threadIdx.x] = v;
   }
-}
-
-__global__ void __launch_bounds__(512)
-gicp_reduce_kernel(const double* __restrict__ partials, int nblocks, int width, double* __restrict__ out) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = w; k < width; k += 16) {
+  // The block that finishes last reduces the partial sums (fixed order: the same tree whichever block
+  // it is) and hands the 13 results to the host through mapped pinned memory: one launch and no copy per
+  // BFGS evaluation (31 per alignment) instead of two launches, a copy and a stream synchronisation.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nblocks = (int)gridDim.x;
+  for (int k = w; k < kCostSums; k += 8) {
     double v = 0.0;
-    for (int b = lane; b < nblocks; b += 32) v += partials[(int64_t)b * width + k];
+    for (int b = lane; b < nblocks; b += 32) v += *reinterpret_cast<volatile const double*>(partials + (int64_t)b * kCostSums + k);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[k] = v;
+    if (lane == 0) { sums[k] = v; if (host_sums) host_sums[k] = v; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ticket = 0;                                   // ready for the next evaluation
+    if (host_flag) { __threadfence_system(); *host_flag = seq; }
   }
 }
 
@@ -397,7 +423,7 @@ int approx_voxel_grid_emit(int n, int n_runs, void* ws_base, float* out, const u
 
 int gicp_covariances(const float* cloud, int n, const KdNode* nodes, const BucketPoint* bpts, double eps,
                      double* covs, cudaStream_t stream) {
-  gicp_knn20_cov_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(cloud, n, nodes, bpts, eps, covs);
+  gicp_knn20_cov_kernel<<<ceil_div(n, 64), 64, 0, stream>>>(cloud, n, nodes, bpts, eps, covs);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -415,10 +441,11 @@ int gicp_correspond(const float* src, int ns, const float* tgt, const GicpIterPa
 int gicp_cost_blocks(int ns) { return ceil_div(ns, 256); }
 
 int gicp_cost(const float* src, int ns, const float* tgt, const GicpCostParams& P, const int32_t* match,
-              const double* maha, double* partials, double* sums, cudaStream_t stream) {
+              const double* maha, double* partials, double* sums, uint32_t* ticket, double* host_sums_dev,
+              long long* host_flag_dev, long long seq, cudaStream_t stream) {
   const int nb = gicp_cost_blocks(ns);
-  gicp_cost_kernel<<<nb, 256, 0, stream>>>(src, ns, tgt, P, match, maha, partials);
-  gicp_reduce_kernel<<<1, 512, 0, stream>>>(partials, nb, kCostSums, sums);
+  gicp_cost_kernel<<<nb, 256, 0, stream>>>(src, ns, tgt, P, match, maha, partials, sums, ticket, host_sums_dev,
+                                          host_flag_dev, seq);
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

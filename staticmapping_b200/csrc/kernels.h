@@ -219,8 +219,11 @@ int gicp_correspond(const float* src, int ns, const float* tgt, const GicpIterPa
                     const BucketPoint* bpts, const double* cov_s, const double* cov_t, int32_t* match,
                     double* maha, uint32_t* count, cudaStream_t stream);
 int gicp_cost_blocks(int ns);
+// ticket: a zeroed u32; host_sums_dev / host_flag_dev: device views of mapped pinned host memory (13 doubles and a
+// sequence word the kernel sets to `seq` after the sums), or null
 int gicp_cost(const float* src, int ns, const float* tgt, const GicpCostParams& P, const int32_t* match,
-              const double* maha, double* partials, double* sums, cudaStream_t stream);
+              const double* maha, double* partials, double* sums, uint32_t* ticket, double* host_sums_dev,
+              long long* host_flag_dev, long long seq, cudaStream_t stream);
 
 // ---- normals.cu ------------------------------------------------------------------------
 int normals_scratch_blocks(int n);

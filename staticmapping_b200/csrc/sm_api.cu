@@ -227,7 +227,9 @@ struct sm_handle {
   // NDT
   ndt::Options ndt;
   DevBuf src_f32, tgt_f32, ndt_ws, tgt_soa;
-  double* host_sums = nullptr;     // pinned, 64 doubles
+  double* host_sums = nullptr;     // pinned + mapped, 64 doubles; word 60 doubles as the GICP evaluation flag
+  double* host_sums_dev = nullptr; // its device view
+  long long gicp_seq = 0;
   // NdtWithGicp
   struct { float voxel_resolution = 0.2f; bool using_voxel_filter = true; bool use_ndt = true; } ng;   // ndt_gicp.h:71-75
   DevBuf src_filt, tgt_filt, approx_ws, src_soa, nodes2, leaf_order2, bpts2, cov_s, cov_t, maha, match, gicp_partials, counter;
@@ -855,6 +857,10 @@ int gicp_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, c
   H_RC(h->gicp_partials.reserve((size_t)(gicp_cost_blocks(ns) + 1) * 13 * sizeof(double) + 256));
   H_RC(h->counter.reserve(64));
   double* sums_dev = (double*)h->gicp_partials.p + (size_t)gicp_cost_blocks(ns) * 13;
+  uint32_t* ticket_dev = (uint32_t*)h->counter.p + 8;
+  H_CUDA(cudaMemsetAsync(ticket_dev, 0, sizeof(uint32_t), h->stream));
+  *reinterpret_cast<volatile long long*>(h->host_sums + 60) = 0;
+  h->gicp_seq = 0;
   if (o.k_correspondences <= nt)   // :61-65: otherwise PCL_ERROR and the covariances stay unset
     H_RC(gicp_covariances(tgt, nt, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p, o.gicp_epsilon,
                           (double*)h->cov_t.p, h->stream));
@@ -896,10 +902,19 @@ int gicp_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, c
       GicpCostParams CP;
       for (int i = 0; i < 16; ++i) { CP.T[i] = guess[i]; CP.base[i] = guess[i]; }
       gicp::apply_state(CP.T, xx);
+      // the kernel's last block writes the 13 sums and then the sequence word into mapped pinned memory
+      volatile long long* flag = reinterpret_cast<volatile long long*>(h->host_sums + 60);
+      const long long seq = ++h->gicp_seq;
       if (gicp_cost(src, ns, tgt, CP, (const int32_t*)h->match.p, (const double*)h->maha.p,
-                    (double*)h->gicp_partials.p, sums_dev, h->stream) != 0) return -1;
-      if (cudaMemcpyAsync(h->host_sums, sums_dev, 13 * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-          cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+                    (double*)h->gicp_partials.p, sums_dev, ticket_dev, h->host_sums_dev,
+                    reinterpret_cast<long long*>(h->host_sums_dev + 60), seq, h->stream) != 0) return -1;
+      for (long spins = 0; *flag != seq; ++spins) {
+        if ((spins & 0xfff) == 0xfff && cudaStreamQuery(h->stream) != cudaErrorNotReady) {
+          if (*flag == seq) break;
+          if (cudaStreamSynchronize(h->stream) != cudaSuccess || *flag != seq) return -1;   // the kernel failed
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
       const double* S = h->host_sums;
       if (f) *f = S[0] / (double)m;
       if (g) {
@@ -1037,7 +1052,8 @@ int sm_create(int type, int device, sm_handle** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost((void**)&h->host_state, sizeof(IcpState)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->host_sums, 64 * sizeof(double)) != cudaSuccess ||
+      cudaHostAlloc((void**)&h->host_sums, 64 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&h->host_sums_dev, h->host_sums, 0) != cudaSuccess ||
       cudaMallocHost((void**)&h->host_guess, 16 * sizeof(double)) != cudaSuccess) {
     delete h;
     return SM_ERR_CUDA;
