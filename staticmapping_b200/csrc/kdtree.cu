@@ -440,14 +440,24 @@ __global__ void kd_compact_buckets_kernel(const double* __restrict__ coord, int6
   if (pid) pid[e] = id;
 }
 
+// keys32: the coordinates are exactly representable as float (clouds that entered as float): the float
+// bit pattern orders them like the double one and the sort needs 4 byte passes instead of 8
 __global__ void kd_keys_kernel(const double* __restrict__ coord, int64_t cstride, int n,
                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                               int64_t lstride) {
+                               int64_t lstride, int keys32) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    keys[d * lstride + i] = sortable_key(coord[d * cstride + i]);
+    const double v = coord[d * cstride + i];
+    uint64_t key;
+    if (keys32) {
+      const uint32_t u = __float_as_uint((float)v);
+      key = (u >> 31) ? (uint32_t)~u : (u | 0x80000000u);
+    } else {
+      key = sortable_key(v);
+    }
+    keys[d * lstride + i] = key;
     vals[d * lstride + i] = (uint32_t)i;
   }
 }
@@ -495,14 +505,15 @@ void KdWorkspace::carve(void* base, int n, int bucket) {
 // coord: SoA [3][cstride] doubles (already centred).  Writes nodes (heap layout,
 // 2^(levels+1)-1 entries) and leaf_order[n] (point ids in bucket order).
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
-             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut, uint8_t* cdim) {
+             KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut, uint8_t* cdim,
+             bool coords_are_float) {
   if (n <= 0) return -1;
   const int levels = kd_num_levels(n, bucket);
   const int64_t ls = ws.lstride;
   kd_keys_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(coord, cstride, n, ws.keys[0],
-                                                       ws.lists[0], ls);
+                                                       ws.lists[0], ls, coords_are_float ? 1 : 0);
   int rc = radix_sort_pairs_u64(ws.keys[0], ws.lists[0], ws.keys[1], ws.lists[1], n, 3, ls,
-                                ws.scratch, stream);
+                                ws.scratch, stream, coords_are_float ? 4 : 8);
   if (rc) return rc;
   int cur = 0;
   const int nblk = ceil_div(n, kPartTile);

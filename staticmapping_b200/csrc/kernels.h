@@ -32,9 +32,10 @@ struct KdWorkspace {
   void carve(void* base, int n, int bucket);
 };
 // ccut / cdim (optional): the compact search layout's node arrays, see KdCompact
+// coords_are_float: every coordinate is exactly a float (clouds uploaded as float): 32-bit sort keys
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
              KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut = nullptr,
-             uint8_t* cdim = nullptr);
+             uint8_t* cdim = nullptr, bool coords_are_float = false);
 
 // Compact search layout of the same tree, shaped for a shared-memory resident traversal:
 //   cut[h], dim[h]  heap order (children of h: 2h+1, 2h+2) for the levels above the deepest

@@ -696,7 +696,8 @@ int build_tree_f32(sm_handle* h, const float* pts, int n, DevBuf& soa, DevBuf& n
   KdWorkspace kws;
   kws.carve(h->kdws.p, n, 8);
   H_RC(ndt_float_to_soa(pts, n, (double*)soa.p, stride, h->stream));
-  H_RC(kd_build((const double*)soa.p, stride, n, 8, kws, (KdNode*)nodes.p, (uint32_t*)order.p, h->stream));
+  H_RC(kd_build((const double*)soa.p, stride, n, 8, kws, (KdNode*)nodes.p, (uint32_t*)order.p, h->stream,
+                nullptr, nullptr, true));        // the cloud entered as float: 32-bit sort keys
   H_RC(kd_fill_buckets((const double*)soa.p, stride, nullptr, 0, (const uint32_t*)order.p, n,
                        (BucketPoint*)bpts.p, nullptr, h->stream));
   return 0;
