@@ -198,8 +198,11 @@ __device__ __forceinline__ void knn_k(const KdNode* __restrict__ nodes, const Bu
 __global__ void __launch_bounds__(64)
 gicp_knn20_cov_kernel(const float* __restrict__ cloud, int n, const KdNode* __restrict__ nodes,
                       const BucketPoint* __restrict__ bpts, double eps, double* __restrict__ covs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  // queries in the tree's own leaf order: the lanes of a warp are neighbours in space, walk the same
+  // nodes and scan the same buckets (the cloud's input order is the voxel filter's eviction order)
+  const int i = (int)bpts[t].id;
   double bd[kK]; int bi[kK]; int cnt;
   knn_k(nodes, bpts, (double)cloud[3 * (int64_t)i], (double)cloud[3 * (int64_t)i + 1], (double)cloud[3 * (int64_t)i + 2],
         bd, bi, &cnt);

@@ -223,8 +223,8 @@ kd_part_scatter_kernel(const uint32_t* __restrict__ lists, uint32_t* __restrict_
 // passes stop at level 6 (segments of <= 1 669 points) and 64 CTAs do levels 6..13: 56 launches become 25.
 // The tree is the same one (same medians, same tie rule, same implicit bounds): it is checked through the
 // bit-exact k-NN tests and the CalculateNormals leaf counts.
-constexpr int kSubThreads = 256;
-constexpr int kSubItems = 8;
+constexpr int kSubThreads = 512;
+constexpr int kSubItems = 4;
 constexpr int kSubMax = kSubThreads * kSubItems;     // 2048 points
 constexpr int kSubNodes = 256;                       // a level with an inner node has <= count / bucket nodes
 
