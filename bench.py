@@ -438,7 +438,15 @@ def main():
     ms_dev_total = float(np.median(win_dev))
     ms_e2e_total = float(np.median(win_e2e))
     gpu_launches = per_align_launches * B * args.steps
-    allgather_ms = float(np.median(gather_ms)) if gather_ms else 0.0
+    allgather_incl_wait_ms = float(np.median(gather_ms)) if gather_ms else 0.0
+    allgather_ms = 0.0
+    if world > 1:                     # the collective alone (ranks aligned by a barrier first): 17 doubles per pair
+        rec = torch.zeros((B, parallel.POSE_RECORD), dtype=torch.float64, device=dev)
+        outl = [torch.empty_like(rec) for _ in range(world)]
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); dist.all_gather(outl, rec); e1.record(); e1.synchronize()
+        allgather_ms = e0.elapsed_time(e1)
 
     # ---- latency: one alignment in flight, L2 flushed before each -----------------------------
     for m in matchers:
@@ -536,6 +544,7 @@ def main():
                     "in_flight": 1, "icp_iterations_per_s": ITERATIONS / (iter_ms * 1e-3)},
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
         "allgather_ms": allgather_ms,
+        "allgather_incl_rank_skew_ms": allgather_incl_wait_ms,   # as it happened inside the timed windows (waits for the slowest rank)
     }
     if world > 1:
         # clocks were sampled on local rank 0 only (one nvidia-smi, started before warm-up)
