@@ -334,7 +334,7 @@ int icp_prologue(const IcpBuffers& b, const IcpParams& p, const double* guess_de
   center_kernel<<<ceil_div(nt, 256), 256, 0, stream>>>(b.tgt_raw, b.tgt, b.tstride, nt,
                                                       b.mean_partials, nparts, b.state);
   nvtxRangePushA("BuildKdTree");                 // icp_fast.cc:465
-  int rc = kd_build(b.tgt, b.tstride, nt, 8, ws, b.nodes, b.leaf_order, stream, b.ccut, b.cdim);
+  int rc = kd_build(b.tgt, b.tstride, nt, 8, ws, b.nodes, b.leaf_order, stream, b.ccut, b.cdim, false, b.cnode);
   if (rc) { nvtxRangePop(); return rc; }
   rc = kd_compact_buckets(b.tgt, b.tstride, b.nrm, b.tstride, b.leaf_order, nt, 8, p.tree_levels, b.cpb, b.cpn,
                           nullptr, stream);

@@ -57,13 +57,18 @@ __device__ __forceinline__ int argmax3(double ex, double ey, double ez) {
   return mi;
 }
 
+// {cut, dim} of one node as the search kernel loads it (KdCompact::node)
+__device__ __forceinline__ double2 packed_node(double cut, int dim) {
+  return make_double2(cut, __longlong_as_double((long long)dim));
+}
+
 // ---- per level: node kernel -----------------------------------------------------------
 __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride,
                                const uint32_t* __restrict__ lists, int64_t lstride, int n,
                                int bucket, int L, const double* __restrict__ bounds_in,
                                double* __restrict__ bounds_out, int* __restrict__ level_dim,
                                KdNode* __restrict__ nodes, double* __restrict__ ccut,
-                               uint8_t* __restrict__ cdim) {
+                               uint8_t* __restrict__ cdim, double2* __restrict__ cnode) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (1 << L)) return;
   const Seg s = locate_node(j, L, n, bucket);
@@ -76,6 +81,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
     nodes[blocked_index(h)] = leaf;
     level_dim[j] = 3;
     if (cdim) cdim[h] = 3;
+    if (cnode) cnode[h + 1] = packed_node(0.0, 3);
     return;
   }
   double mn[3], mx[3];
@@ -98,6 +104,7 @@ __global__ void kd_node_kernel(const double* __restrict__ coord, int64_t cstride
   nodes[blocked_index(h)] = nd;
   level_dim[j] = dim;
   if (ccut) { ccut[h] = cut; cdim[h] = (uint8_t)dim; }
+  if (cnode) cnode[h + 1] = packed_node(cut, dim);
   double* bl = bounds_out + (int64_t)(2 * j) * 6;
   double* br = bounds_out + (int64_t)(2 * j + 1) * 6;
   for (int d = 0; d < 3; ++d) {
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kSubThreads)
 kd_subtree_kernel(const double* __restrict__ coord, int64_t cstride, uint32_t* __restrict__ lists, int64_t lstride,
                   int n, int bucket, int Lg, int levels, const double* __restrict__ bounds_in,
                   uint8_t* __restrict__ flag, KdNode* __restrict__ nodes, double* __restrict__ ccut,
-                  uint8_t* __restrict__ cdim) {
+                  uint8_t* __restrict__ cdim, double2* __restrict__ cnode) {
   __shared__ uint32_t s_list[3][kSubMax];
   __shared__ uint32_t s_scan[kSubMax + 1];
   __shared__ double s_bounds[kSubNodes][6];
@@ -258,7 +265,10 @@ kd_subtree_kernel(const double* __restrict__ coord, int64_t cstride, uint32_t* _
   const int j0 = blockIdx.x;
   const Seg seg0 = locate_node(j0, Lg, n, bucket);
   if (!seg0.exists || seg0.count <= bucket) {                // a leaf (or nothing) at level Lg: kd_leaf_kernel's job
-    if (seg0.exists && cdim && Lg < levels && threadIdx.x == 0) cdim[(1 << Lg) - 1 + j0] = 3;
+    if (seg0.exists && cdim && Lg < levels && threadIdx.x == 0) {
+      cdim[(1 << Lg) - 1 + j0] = 3;
+      if (cnode) cnode[(1 << Lg) + j0] = packed_node(0.0, 3);
+    }
     return;
   }
   const int count0 = seg0.count;
@@ -298,6 +308,7 @@ kd_subtree_kernel(const double* __restrict__ coord, int64_t cstride, uint32_t* _
         leaf.dim = 3; leaf.pad = 0;
         nodes[blocked_index(h)] = leaf;
         if (cdim) cdim[h] = 3;
+        if (cnode) cnode[h + 1] = packed_node(0.0, 3);
         continue;
       }
       double mn[3], mx[3];
@@ -309,6 +320,7 @@ kd_subtree_kernel(const double* __restrict__ coord, int64_t cstride, uint32_t* _
       KdNode nd; nd.cut = cut; nd.dim = dim; nd.pad = 0;
       nodes[blocked_index(h)] = nd;
       if (ccut) { ccut[h] = cut; cdim[h] = (uint8_t)dim; }
+      if (cnode) cnode[h + 1] = packed_node(cut, dim);
       s_ndim[jl] = dim;
       s_any_inner = 1;
       for (int d = 0; d < 3; ++d) {
@@ -506,7 +518,7 @@ void KdWorkspace::carve(void* base, int n, int bucket) {
 // 2^(levels+1)-1 entries) and leaf_order[n] (point ids in bucket order).
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
              KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut, uint8_t* cdim,
-             bool coords_are_float) {
+             bool coords_are_float, double2* cnode) {
   if (n <= 0) return -1;
   const int levels = kd_num_levels(n, bucket);
   const int64_t ls = ws.lstride;
@@ -528,7 +540,7 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
     const int nodes_l = 1 << L;
     kd_node_kernel<<<ceil_div(nodes_l, 128), 128, 0, stream>>>(
         coord, cstride, ws.lists[cur], ls, n, bucket, L, ws.bounds[L & 1], ws.bounds[(L + 1) & 1],
-        ws.level_dim, nodes, ccut, cdim);
+        ws.level_dim, nodes, ccut, cdim, cnode);
     kd_flag_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(ws.lists[cur], ls, n, bucket, L,
                                                         ws.level_dim, ws.flag);
     kd_part_count_kernel<<<dim3(nblk, 3), kPartThreads, 0, stream>>>(
@@ -545,7 +557,7 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
   }
   if (Lg < levels)
     kd_subtree_kernel<<<1 << Lg, kSubThreads, 0, stream>>>(coord, cstride, ws.lists[cur], ls, n, bucket, Lg, levels,
-                                                          ws.bounds[Lg & 1], ws.flag, nodes, ccut, cdim);
+                                                          ws.bounds[Lg & 1], ws.flag, nodes, ccut, cdim, cnode);
   const int total = (1 << (levels + 1)) - 1;
   kd_leaf_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(ws.lists[cur], n, bucket, levels,
                                                           nodes, leaf_order);

@@ -35,7 +35,7 @@ struct KdWorkspace {
 // coords_are_float: every coordinate is exactly a float (clouds uploaded as float): 32-bit sort keys
 int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspace& ws,
              KdNode* nodes, uint32_t* leaf_order, cudaStream_t stream, double* ccut = nullptr,
-             uint8_t* cdim = nullptr, bool coords_are_float = false);
+             uint8_t* cdim = nullptr, bool coords_are_float = false, double2* cnode = nullptr);
 
 // Compact search layout of the same tree, shaped for a shared-memory resident traversal:
 //   cut[h], dim[h]  heap order (children of h: 2h+1, 2h+2) for the levels above the deepest
@@ -49,6 +49,8 @@ int kd_build(const double* coord, int64_t cstride, int n, int bucket, KdWorkspac
 struct KdCompact {
   const double* cut;
   const uint8_t* dim;
+  const double2* node;    // {cut, dim as a 64-bit integer} of heap node h at slot h + 1, 2^levels slots: the
+                          // search reads the levels below the shared-memory ones with one 16-byte load per node
   const double* pb;
   const BucketNormal* pn;
   const int32_t* pid;
@@ -106,6 +108,7 @@ struct IcpBuffers {
   uint32_t* leaf_order;
   double* ccut;           // writable views of kc.cut / kc.dim / kc.pb / kc.pn (filled by the prologue)
   uint8_t* cdim;
+  double2* cnode;
   double* cpb;
   BucketNormal* cpn;
   KdCompact kc;

@@ -34,6 +34,12 @@ namespace dev {
 #ifndef SMB_KNN_SMEM_LEVELS
 #define SMB_KNN_SMEM_LEVELS 11
 #endif
+#ifndef SMB_KNN_LDG256
+#define SMB_KNN_LDG256 1
+#endif
+#ifndef SMB_KNN_PAIR_PREFETCH
+#define SMB_KNN_PAIR_PREFETCH 0
+#endif
 constexpr int kKnnCtaThreads = SMB_KNN_THREADS;        // threads (= traversal slots) per CTA
 constexpr int kKnnSmemLevels = SMB_KNN_SMEM_LEVELS;    // tree levels staged in shared memory: 2^11 * 9 B = 18 KB
 constexpr int kKnnCtasPerSm = 1024 / kKnnCtaThreads;   // 64 registers per thread -> 1024 threads per SM
@@ -44,6 +50,7 @@ struct SmemTree {
   int n_smem;               // heap indices < n_smem are resident in shared memory
   const double* g_cut;      // global (all nodes)
   const uint8_t* g_dim;
+  const double2* g_node;    // global, packed {cut, dim} of heap node h at slot h + 1 (one 16-byte load per node)
   const double* pb;         // padded buckets
   int levels;
   double* sq;               // this thread's query: sq[d * kKnnCtaThreads] (shared memory, d = 0..2)
@@ -110,7 +117,7 @@ __device__ __forceinline__ SmemTree stage_tree(const KdCompact& t, unsigned char
   *bar_out = bar;
   SmemTree st;
   st.s_cut = s_cut; st.s_dim = s_dim; st.n_smem = slots;
-  st.g_cut = t.cut; st.g_dim = t.dim; st.pb = t.pb; st.levels = t.levels;
+  st.g_cut = t.cut; st.g_dim = t.dim; st.g_node = t.node; st.pb = t.pb; st.levels = t.levels;
   st.sq = *extra_out + 16 + threadIdx.x;
   st.so = st.sq + 3 * kKnnCtaThreads;
   return st;
@@ -128,22 +135,50 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const void* p) {
   return v;
 }
 
-// One padded bucket: 12 back-to-back 16-byte loads, 8 squared distances in the reference's
+// A node of the levels below the staged ones: cut and dimension in ONE 16-byte load (two dependent
+// loads of two arrays before).
+__device__ __forceinline__ void ldg_node(const double2* __restrict__ g_node, int h, double& cut, int& dim) {
+  const double2 v = ldg_nc_f64x2(g_node + h + 1);
+  cut = v.x;
+  dim = (int)__double_as_longlong(v.y);
+}
+
+struct Double4 { double a, b, c, d; };
+__device__ __forceinline__ Double4 ldg_nc_f64x4(const void* p) {      // LDG.E.256 (sm_100), 32-byte aligned
+  Double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+
+// One padded bucket: 6 back-to-back 32-byte loads, 8 squared distances in the reference's
 // operation order, then a tournament on the bit patterns in which the lower index wins ties
 // (libnabo walks the bucket in order and replaces the head on a strict '<').  Padding entries
 // are +inf: their distance is +inf or NaN, never below the head.
 __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int bucket, double qx, double qy,
                                             double qz, double& head, int& best) {
   const char* base = reinterpret_cast<const char*>(pb + (int64_t)bucket * 24);
+  unsigned long long key[8];
+#if SMB_KNN_LDG256
+  Double4 v[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = ldg_nc_f64x4(base + 32 * k);
+#else
   double2 v[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) v[k] = ldg_nc_f64x2(base + 16 * k);
-  unsigned long long key[8];
+#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
+#if SMB_KNN_LDG256
+    const Double4 &vx = v[k >> 2], &vy = v[2 + (k >> 2)], &vz = v[4 + (k >> 2)];
+    const double x = (k & 3) == 0 ? vx.a : (k & 3) == 1 ? vx.b : (k & 3) == 2 ? vx.c : vx.d;
+    const double y = (k & 3) == 0 ? vy.a : (k & 3) == 1 ? vy.b : (k & 3) == 2 ? vy.c : vy.d;
+    const double z = (k & 3) == 0 ? vz.a : (k & 3) == 1 ? vz.b : (k & 3) == 2 ? vz.c : vz.d;
+#else
     const double x = (k & 1) ? v[k >> 1].y : v[k >> 1].x;
     const double y = (k & 1) ? v[4 + (k >> 1)].y : v[4 + (k >> 1)].x;
     const double z = (k & 1) ? v[8 + (k >> 1)].y : v[8 + (k >> 1)].x;
+#endif
     const double dx = dsub(qx, x), dy = dsub(qy, y), dz = dsub(qz, z);
     key[k] = (unsigned long long)__double_as_longlong(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
   }
@@ -186,10 +221,20 @@ __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, doub
   int sp = 0;
   while (true) {
     int l = 31 - __clz(h + 1);
+#if SMB_KNN_PAIR_PREFETCH
+    double cut = 0.0; int cd = 3;
+    if (l < t.levels) ldg_node(t.g_node, h, cut, cd);
+#endif
     while (l < t.levels) {
-      const int cd = __ldg(t.g_dim + h);
+#if SMB_KNN_PAIR_PREFETCH
       if (cd == 3) break;
-      const double cut = __ldg(t.g_cut + h);
+      Double4 ch = {0.0, 0.0, 0.0, 0.0};                       // both children, fetched while this node is decided
+      if (l + 1 < t.levels) ch = ldg_nc_f64x4(t.g_node + 2 * (h + 1));
+#else
+      double cut; int cd;
+      ldg_node(t.g_node, h, cut, cd);
+      if (cd == 3) break;
+#endif
       const double q = t.sq[cd * kKnnCtaThreads];
       const double old_off = t.so[cd * kKnnCtaThreads];
       const double new_off = dsub(q, cut);
@@ -204,6 +249,10 @@ __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, doub
       }
       h = 2 * h + 1 + right;
       ++l;
+#if SMB_KNN_PAIR_PREFETCH
+      cut = right ? ch.c : ch.a;
+      cd = (int)__double_as_longlong(right ? ch.d : ch.b);
+#endif
     }
     scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
     bool found = false;
@@ -237,12 +286,28 @@ __device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double q
     ++l;
   }
   if (!kAllSmem && !leaf) {
+#if SMB_KNN_PAIR_PREFETCH
+    double cut = 0.0; int cd = 3;
+    if (l < t.levels) ldg_node(t.g_node, h, cut, cd);
     while (l < t.levels) {
-      const int cd = __ldg(t.g_dim + h);
       if (cd == 3) break;
-      h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > __ldg(t.g_cut + h) ? 1 : 0);
+      Double4 ch = {0.0, 0.0, 0.0, 0.0};
+      if (l + 1 < t.levels) ch = ldg_nc_f64x4(t.g_node + 2 * (h + 1));
+      const int right = t.sq[cd * kKnnCtaThreads] > cut ? 1 : 0;
+      h = 2 * h + 1 + right;
+      ++l;
+      cut = right ? ch.c : ch.a;
+      cd = (int)__double_as_longlong(right ? ch.d : ch.b);
+    }
+#else
+    while (l < t.levels) {
+      double cut; int cd;
+      ldg_node(t.g_node, h, cut, cd);
+      if (cd == 3) break;
+      h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > cut ? 1 : 0);
       ++l;
     }
+#endif
   }
   scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
   // Root frame.  Path node of level a: ((h+1) >> (l-a)) - 1.  rd = 0 and off = 0 along the whole
@@ -261,15 +326,18 @@ __device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double q
 #pragma unroll 2
   for (int a = lsm2; a < ll; ++a) {
     const int n = (hp1 >> (ll - a)) - 1;
-    const double off = dsub(t.sq[__ldg(t.g_dim + n) * kKnnCtaThreads], __ldg(t.g_cut + n));
+    double cut; int cd;
+    ldg_node(t.g_node, n, cut, cd);
+    const double off = dsub(t.sq[cd * kKnnCtaThreads], cut);
     if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
   }
   while (mask != 0u) {
     const int a = 31 - __clz(mask);
     mask &= ~(1u << a);
     const int n = (hp1 >> (ll - a)) - 1;
-    const int cd = __ldg(t.g_dim + n);
-    const double off = dsub(t.sq[cd * kKnnCtaThreads], __ldg(t.g_cut + n));
+    double cut; int cd;
+    ldg_node(t.g_node, n, cut, cd);
+    const double off = dsub(t.sq[cd * kKnnCtaThreads], cut);
     const double rd_new = dmul(off, off);
     if (dmul(rd_new, me2) < head) {
       t.so[0] = 0.0; t.so[kKnnCtaThreads] = 0.0; t.so[2 * kKnnCtaThreads] = 0.0;

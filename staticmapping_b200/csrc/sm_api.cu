@@ -428,7 +428,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->src_sort.reserve((size_t)h->sstride * 24 + radix_sort_scratch_bytes(ns, 1) + 1024));
   H_RC(h->nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   H_RC(h->leaf_order.reserve((size_t)nt * sizeof(uint32_t)));
-  H_RC(h->ccut.reserve(kd_compact_node_slots(levels) * sizeof(double)));
+  H_RC(h->ccut.reserve(kd_compact_node_slots(levels) * (sizeof(double) + sizeof(double2))));   // cut[] then node[]
   H_RC(h->cdim.reserve(kd_compact_node_slots(levels)));
   H_RC(h->cpb.reserve(kd_compact_bucket_entries(levels) * 3 * sizeof(double)));
   H_RC(h->cpn.reserve(kd_compact_bucket_entries(levels) * sizeof(BucketNormal)));
@@ -451,8 +451,9 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.tstride = h->tstride;
   b.nodes = (KdNode*)h->nodes.p; b.leaf_order = (uint32_t*)h->leaf_order.p;
   b.ccut = (double*)h->ccut.p; b.cdim = (uint8_t*)h->cdim.p;
+  b.cnode = reinterpret_cast<double2*>(b.ccut + kd_compact_node_slots(levels));
   b.cpb = (double*)h->cpb.p; b.cpn = (BucketNormal*)h->cpn.p;
-  b.kc.cut = b.ccut; b.kc.dim = b.cdim; b.kc.pb = b.cpb; b.kc.pn = b.cpn; b.kc.pid = nullptr; b.kc.levels = levels;
+  b.kc.cut = b.ccut; b.kc.dim = b.cdim; b.kc.node = b.cnode; b.kc.pb = b.cpb; b.kc.pn = b.cpn; b.kc.pid = nullptr; b.kc.levels = levels;
   b.src_raw = (double*)h->src_raw.p; b.src0 = (double*)h->src0.p; b.sstride = h->sstride;
   b.src_g0 = (double*)h->src_g0.p;
   b.src_keys[0] = (uint64_t*)h->src_sort.p; b.src_keys[1] = b.src_keys[0] + h->sstride;
@@ -1428,7 +1429,7 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_OK(nodes.reserve((size_t)blocked_node_slots(levels) * sizeof(KdNode)));
   K_OK(order.reserve((size_t)nt * sizeof(uint32_t)));
   K_OK(kdws.reserve(KdWorkspace::bytes_needed((int)nt, bucket)));
-  K_OK(ccut.reserve(kd_compact_node_slots(levels) * sizeof(double)));
+  K_OK(ccut.reserve(kd_compact_node_slots(levels) * (sizeof(double) + sizeof(double2))));
   K_OK(cdim.reserve(kd_compact_node_slots(levels)));
   K_OK(cpb.reserve(kd_compact_bucket_entries(levels) * 3 * sizeof(double)));
   K_OK(cpid.reserve(kd_compact_bucket_entries(levels) * sizeof(int32_t)));
@@ -1440,12 +1441,14 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   KdWorkspace ws;
   ws.carve(kdws.p, (int)nt, bucket);
   K_OK(kd_build((const double*)tgt.p, ts, (int)nt, bucket, ws, (KdNode*)nodes.p, (uint32_t*)order.p, s,
-                (double*)ccut.p, (uint8_t*)cdim.p));
+                (double*)ccut.p, (uint8_t*)cdim.p, false,
+                reinterpret_cast<double2*>((double*)ccut.p + kd_compact_node_slots(levels))));
   K_OK(kd_compact_buckets((const double*)tgt.p, ts, nullptr, 0, (const uint32_t*)order.p, (int)nt, bucket, levels,
                           (double*)cpb.p, nullptr, (int32_t*)cpid.p, s));
   if (nq > 0) {
     KdCompact kc;
     kc.cut = (const double*)ccut.p; kc.dim = (const uint8_t*)cdim.p; kc.pb = (const double*)cpb.p;
+    kc.node = reinterpret_cast<const double2*>(kc.cut + kd_compact_node_slots(levels));
     kc.pn = nullptr; kc.pid = (const int32_t*)cpid.p; kc.levels = levels;
     K_CUDA(cudaMemcpyAsync(stage.p, query, (size_t)3 * nq * sizeof(double), cudaMemcpyHostToDevice, s));
     deinterleave3_kernel<<<ceil_div(nq, 256), 256, 0, s>>>((const double*)stage.p, (double*)qry.p, qs, (int)nq);
