@@ -153,6 +153,8 @@ __global__ void gather_source_kernel(const double* __restrict__ in, double* __re
 #ifndef SMB_KNN_MIN_CTAS
 #define SMB_KNN_MIN_CTAS 4
 #endif
+// Phase A, one query per thread (a single alignment in flight: 469 CTAs, all resident at once, the
+// kernel lasts as long as its longest search).
 template <bool kAllSmem>
 __global__ void __launch_bounds__(kKnnCtaThreads, SMB_KNN_MIN_CTAS)
 icp_knn_kernel(IcpBuffers b, IcpParams p, int per_cta) {
@@ -176,6 +178,78 @@ icp_knn_kernel(IcpBuffers b, IcpParams p, int per_cta) {
     if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
     i += kKnnCtaThreads;
     if (i < end) transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+  }
+}
+
+#ifndef SMB_KNN_QPT
+#define SMB_KNN_QPT 4                 // queries per thread and batch of the two-phase kernel (<= kKnnMaxQpt)
+#endif
+// Phase A with several queries per thread (many alignments in flight: queries_per_cta > 256).  Per batch
+// of 256 * QPT queries of a CTA:
+//   (1) every thread transforms its queries (one per pass, consecutive threads = consecutive queries) and
+//       does their ROOT visit in lockstep with its warp: all lanes walk the same number of levels and scan
+//       one bucket each.  A query without far-side candidates is final here (~1/3 of them);
+//   (2) the others are parked as 16-byte items (knn_smem.cuh) and the warp works through its list with
+//       every lane pulling the next item as soon as its query is finished.
+// The one-query-per-thread form of round 1 / early round 2 (knn1_smem, still used by sm_knn1) spends its
+// time in passes in which a few lanes finish long searches: 13 of 32 lanes busy on average.
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kKnnCtaThreads, SMB_KNN_MIN_CTAS)
+icp_knn_batch_kernel(IcpBuffers b, IcpParams p, int per_cta) {
+  extern __shared__ __align__(128) unsigned char knn_smem[];
+  if (b.state->done) return;
+  uint64_t* bar; double* T;
+  const SmemTree tree = stage_tree(b.kc, knn_smem, &bar, &T);
+  if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
+  __syncthreads();
+  const int begin = blockIdx.x * per_cta, end = min(begin + per_cta, p.n_source);
+  const int warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  const int qpt = min(SMB_KNN_QPT, (per_cta + kKnnCtaThreads - 1) / kKnnCtaThreads);
+  const double me2 = p.max_error2;
+  mbar_wait(bar, 0);      // every thread waits: the CTA must not retire while the copy engine writes its smem
+  auto finish = [&](int i, int slot, double d2) {
+    b.slot[i] = slot;
+    b.d2[i] = d2;
+    // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident)
+    if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
+  };
+  for (int base = begin; base < end; base += kKnnCtaThreads * qpt) {
+    const int qb = min(qpt, (begin + per_cta - base) / kKnnCtaThreads);   // per_cta is a multiple of the CTA size
+    int4* items = b.knn_items + base + warp * 32 * qb;      // this warp's list: inside the batch's own index range
+    int count = 0;
+    for (int j = 0; j < qb; ++j) {
+      const int i = base + j * kKnnCtaThreads + threadIdx.x;
+      bool far = false;
+      int4 item = make_int4(0, 0, 0, 0);
+      if (i < end) {
+        double px, py, pz, head;
+        int best, hp1, ll;
+        uint32_t mask;
+        transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
+        knn_root_visit<kAllSmem>(tree, px, py, pz, me2, head, best, hp1, ll, mask);
+        if (mask == 0u) {
+          finish(i, best, head);
+        } else {
+          b.slot[i] = best;
+          b.d2[i] = head;
+          far = true;
+          item = make_int4(i, hp1, ll, (int)mask);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, far);
+      if (far) items[count + __popc(m & lt)] = item;
+      count += __popc(m);
+    }
+    __syncwarp();
+    knn_far_phase(tree, me2, items, count,
+                  [&](int i, double& qx, double& qy, double& qz, double& head, int& best) {
+                    transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], qx, qy, qz);
+                    head = __ldcg(b.d2 + i);
+                    best = __ldcg(b.slot + i);
+                  },
+                  finish);
+    __syncwarp();
   }
 }
 
@@ -305,8 +379,7 @@ int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int
 // of the tree top over more queries.
 static void knn_geometry(int nq, int queries_per_cta, int* grid, int* per_cta) {
   int per = queries_per_cta > 0 ? queries_per_cta : kKnnCtaThreads;
-  per = ((per + 31) / 32) * 32;
-  if (per < 64) per = 64;
+  per = ((per + kKnnCtaThreads - 1) / kKnnCtaThreads) * kKnnCtaThreads;
   *per_cta = per;
   *grid = ceil_div(nq, per);
 }
@@ -363,10 +436,16 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_it
     nvtxRangePushA("Iteration");                 // REGISTER_BLOCK("Iteration"), icp_fast.cc:484
     if (events) cudaEventRecord(events[4 * it + 0], stream);
     nvtxRangePushA("FindClosests");              // icp_fast.cc:169-180
-    if (p.tree_levels <= kKnnSmemLevels)
+    if (per > kKnnCtaThreads) {
+      if (p.tree_levels <= kKnnSmemLevels)
+        icp_knn_batch_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+      else
+        icp_knn_batch_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+    } else if (p.tree_levels <= kKnnSmemLevels) {
       icp_knn_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
-    else
+    } else {
       icp_knn_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(b, p, per);
+    }
     nvtxRangePop();
     if (events) cudaEventRecord(events[4 * it + 1], stream);
     nvtxRangePushA("ErrorElements");             // icp_fast.cc:92-167 (+ the sums of ComputePointToPlane)

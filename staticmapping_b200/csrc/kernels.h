@@ -63,6 +63,7 @@ int kd_compact_buckets(const double* coord, int64_t cstride, const double* nrm, 
                        BucketNormal* pn, int32_t* pid, cudaStream_t stream);
 
 // ---- icp.cu ----------------------------------------------------------------------------
+constexpr int kKnnItemSlack = 4096;   // a warp's item list may extend past the last query of the last batch
 constexpr int kHistBins = 2048;
 
 // Device-resident state of one IcpFast::Align call (one per handle).
@@ -122,6 +123,7 @@ struct IcpBuffers {
   int64_t sstride;
   // per-iteration
   int32_t* slot;          // [n_source] padded bucket entry of the match (kc.pb / kc.pn index)
+  int4* knn_items;        // [n_source + kKnnItemSlack] parked searches of the k-NN kernel's second phase (16 B each)
   double* d2;             // [n_source]
   uint32_t* hist;         // [kHistBins] first-level histogram of dist^2 (phase A)
   uint32_t* hist2;        // [kHistBins] second-level histogram inside the quantile bin (phase B)

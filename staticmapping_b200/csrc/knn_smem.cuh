@@ -37,6 +37,17 @@ namespace dev {
 #ifndef SMB_KNN_LDG256
 #define SMB_KNN_LDG256 1
 #endif
+#ifndef SMB_KNN_HALF_SCAN
+#define SMB_KNN_HALF_SCAN 1
+#endif
+#ifndef SMB_KNN_Q_FROM_SMEM
+#define SMB_KNN_Q_FROM_SMEM 0
+#endif
+#if SMB_KNN_Q_FROM_SMEM      // the query of a bucket scan re-read from its shared-memory column (frees six registers)
+#define SMB_KNN_Q(t, reg, d) ((t).sq[(d) * kKnnCtaThreads])
+#else
+#define SMB_KNN_Q(t, reg, d) (reg)
+#endif
 #ifndef SMB_KNN_PAIR_PREFETCH
 #define SMB_KNN_PAIR_PREFETCH 0
 #endif
@@ -150,13 +161,35 @@ __device__ __forceinline__ Double4 ldg_nc_f64x4(const void* p) {      // LDG.E.2
   return v;
 }
 
-// One padded bucket: 6 back-to-back 32-byte loads, 8 squared distances in the reference's
-// operation order, then a tournament on the bit patterns in which the lower index wins ties
-// (libnabo walks the bucket in order and replaces the head on a strict '<').  Padding entries
-// are +inf: their distance is +inf or NaN, never below the head.
+// One padded bucket: 6 32-byte loads, 8 squared distances in the reference's operation order, then
+// a tournament on the bit patterns in which the lower index wins ties (libnabo walks the bucket in
+// order and replaces the head on a strict '<').  Padding entries are +inf: their distance is +inf
+// or NaN, never below the head.  SMB_KNN_HALF_SCAN: four points at a time (half the registers).
+__device__ __forceinline__ unsigned long long dist_key(double qx, double qy, double qz, double x, double y, double z) {
+  const double dx = dsub(qx, x), dy = dsub(qy, y), dz = dsub(qz, z);
+  return (unsigned long long)__double_as_longlong(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
+}
+
 __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int bucket, double qx, double qy,
                                             double qz, double& head, int& best) {
   const char* base = reinterpret_cast<const char*>(pb + (int64_t)bucket * 24);
+#if SMB_KNN_HALF_SCAN
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const Double4 vx = ldg_nc_f64x4(base + 32 * half), vy = ldg_nc_f64x4(base + 64 + 32 * half),
+                  vz = ldg_nc_f64x4(base + 128 + 32 * half);
+    unsigned long long k0 = dist_key(qx, qy, qz, vx.a, vy.a, vz.a), k1 = dist_key(qx, qy, qz, vx.b, vy.b, vz.b);
+    unsigned long long k2 = dist_key(qx, qy, qz, vx.c, vy.c, vz.c), k3 = dist_key(qx, qy, qz, vx.d, vy.d, vz.d);
+    int a0 = 0, a2 = 2;
+    if (k1 < k0) { k0 = k1; a0 = 1; }
+    if (k3 < k2) { k2 = k3; a2 = 3; }
+    if (k2 < k0) { k0 = k2; a0 = a2; }
+    if (k0 < (unsigned long long)__double_as_longlong(head)) {
+      head = __longlong_as_double((long long)k0);
+      best = bucket * 8 + 4 * half + a0;
+    }
+  }
+#else
   unsigned long long key[8];
 #if SMB_KNN_LDG256
   Double4 v[6];
@@ -179,8 +212,7 @@ __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int b
     const double y = (k & 1) ? v[4 + (k >> 1)].y : v[4 + (k >> 1)].x;
     const double z = (k & 1) ? v[8 + (k >> 1)].y : v[8 + (k >> 1)].x;
 #endif
-    const double dx = dsub(qx, x), dy = dsub(qy, y), dz = dsub(qz, z);
-    key[k] = (unsigned long long)__double_as_longlong(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
+    key[k] = dist_key(qx, qy, qz, x, y, z);
   }
   int arg[8];
 #pragma unroll
@@ -198,9 +230,11 @@ __device__ __forceinline__ void scan_bucket(const double* __restrict__ pb, int b
     head = __longlong_as_double((long long)key[0]);
     best = bucket * 8 + arg[0];
   }
+#endif
 }
 
 constexpr int kKnnMaxStack = 32;
+constexpr int kKnnMaxLevels = 24;        // sm_api rejects deeper trees
 
 // The coordinate of the query / the recursion's off[] along a node's cut dimension are read from
 // per-thread shared-memory columns indexed by that dimension (one LDS instead of a three-way select
@@ -254,7 +288,7 @@ __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, doub
       cd = (int)__double_as_longlong(right ? ch.d : ch.b);
 #endif
     }
-    scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
+    scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), SMB_KNN_Q(t, qx, 0), SMB_KNN_Q(t, qy, 1), SMB_KNN_Q(t, qz, 2), head, best);
     bool found = false;
     while (sp > 0) {
       const KnnStackEntry& e = stack[--sp];
@@ -269,68 +303,60 @@ __device__ __forceinline__ void visit_subtree(const SmemTree& t, double qx, doub
   }
 }
 
-// best: padded entry index (bucket * 8 + k) or -1; d2: squared distance (+inf if none)
+// First visit of a query: the descent from the root (staged levels from shared memory, the rest one
+// packed record per level), the first bucket, and the mask of the path levels whose far side passes
+// with the head that bucket left.  Path node of level a: ((hp1) >> (ll-a)) - 1.  rd = 0 and off = 0
+// along the whole root path, so rd_new(a) = 0 + (-(0*0) + new_off^2) = new_off^2 exactly.
 template <bool kAllSmem>
-__device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double qy, double qz, double me2,
-                                          int& best_out, double& d2_out) {
-  double head = __longlong_as_double(0x7ff0000000000000ll);
-  int best = -1;
+__device__ __forceinline__ void knn_root_visit(const SmemTree& t, double qx, double qy, double qz, double me2,
+                                               double& head, int& best, int& hp1_out, int& ll_out, uint32_t& mask_out) {
+  head = __longlong_as_double(0x7ff0000000000000ll);
+  best = -1;
   t.sq[0] = qx; t.sq[kKnnCtaThreads] = qy; t.sq[2 * kKnnCtaThreads] = qz;
   const int lsm = kAllSmem ? t.levels : min(t.levels, kKnnSmemLevels);    // levels staged in shared memory
+  // lb[a]: the squared distance to the cutting plane of path level a, rounded DOWN to float while the
+  // descent has the node in hand.  RN(lb * me2) <= RN(off^2 * me2), so "lb * me2 < head" holds whenever the
+  // exact test does: the mask below is a superset of the levels that pass, and every level of it is
+  // re-tested exactly (node re-read) at the moment the recursion would test it.  The array lives in local
+  // memory; all lanes of a warp store / load the same level together (one 128-byte line per access).
+  float lb[kKnnMaxLevels];
   int h = 0, l = 0;
   bool leaf = false;
   while (l < lsm) {
     const int cd = t.s_dim[h];
     if (cd == 3) { leaf = true; break; }
-    h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > t.s_cut[h] ? 1 : 0);
+    const double q = t.sq[cd * kKnnCtaThreads], off = dsub(q, t.s_cut[h]);
+    lb[l] = __double2float_rd(dmul(off, off));
+    h = 2 * h + 1 + (off > 0.0 ? 1 : 0);              // == (q > cut) for IEEE doubles
     ++l;
   }
   if (!kAllSmem && !leaf) {
-#if SMB_KNN_PAIR_PREFETCH
-    double cut = 0.0; int cd = 3;
-    if (l < t.levels) ldg_node(t.g_node, h, cut, cd);
-    while (l < t.levels) {
-      if (cd == 3) break;
-      Double4 ch = {0.0, 0.0, 0.0, 0.0};
-      if (l + 1 < t.levels) ch = ldg_nc_f64x4(t.g_node + 2 * (h + 1));
-      const int right = t.sq[cd * kKnnCtaThreads] > cut ? 1 : 0;
-      h = 2 * h + 1 + right;
-      ++l;
-      cut = right ? ch.c : ch.a;
-      cd = (int)__double_as_longlong(right ? ch.d : ch.b);
-    }
-#else
     while (l < t.levels) {
       double cut; int cd;
       ldg_node(t.g_node, h, cut, cd);
       if (cd == 3) break;
-      h = 2 * h + 1 + (t.sq[cd * kKnnCtaThreads] > cut ? 1 : 0);
+      const double q = t.sq[cd * kKnnCtaThreads], off = dsub(q, cut);
+      lb[l] = __double2float_rd(dmul(off, off));
+      h = 2 * h + 1 + (off > 0.0 ? 1 : 0);
       ++l;
     }
-#endif
   }
   scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
-  // Root frame.  Path node of level a: ((h+1) >> (l-a)) - 1.  rd = 0 and off = 0 along the whole
-  // root path, so rd_new(a) = 0 + (-(0*0) + new_off^2) = new_off^2 exactly.  First a mask of the
-  // levels that pass with the head of the first bucket (independent iterations), then those levels
-  // deepest first, each re-tested with the head of that moment.
   const int hp1 = h + 1, ll = l;
   uint32_t mask = 0u;
-  const int lsm2 = min(ll, lsm);
-#pragma unroll 2
-  for (int a = 0; a < lsm2; ++a) {
-    const int n = (hp1 >> (ll - a)) - 1;
-    const double off = dsub(t.sq[t.s_dim[n] * kKnnCtaThreads], t.s_cut[n]);
-    if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
-  }
-#pragma unroll 2
-  for (int a = lsm2; a < ll; ++a) {
-    const int n = (hp1 >> (ll - a)) - 1;
-    double cut; int cd;
-    ldg_node(t.g_node, n, cut, cd);
-    const double off = dsub(t.sq[cd * kKnnCtaThreads], cut);
-    if (dmul(dmul(off, off), me2) < head) mask |= 1u << a;
-  }
+#pragma unroll 4
+  for (int a = 0; a < ll; ++a)
+    if (dmul((double)lb[a], me2) < head) mask |= 1u << a;
+  hp1_out = hp1; ll_out = ll; mask_out = mask;
+}
+
+// best: padded entry index (bucket * 8 + k) or -1; d2: squared distance (+inf if none)
+template <bool kAllSmem>
+__device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double qy, double qz, double me2,
+                                          int& best_out, double& d2_out) {
+  double head; int best, hp1, ll; uint32_t mask;
+  knn_root_visit<kAllSmem>(t, qx, qy, qz, me2, head, best, hp1, ll, mask);
+  // the levels of the mask deepest first, each re-tested with the head of that moment
   while (mask != 0u) {
     const int a = 31 - __clz(mask);
     mask &= ~(1u << a);
@@ -348,6 +374,100 @@ __device__ __forceinline__ void knn1_smem(const SmemTree& t, double qx, double q
   }
   best_out = best;
   d2_out = head;
+}
+
+// ---- far visits of a batch of queries, one WARP working through a list ---------------------------
+// A query whose root visit left far-side candidates (knn_root_visit's mask != 0) is parked as a
+// KnnItem; the lanes of the warp then pull items from the list.  Every pass of the loop below is ONE
+// bucket visit per busy lane — the next subtree of the lane's query (a nested far child popped from its
+// stack, else the next root-path level of the mask, both re-tested with the head of that moment exactly
+// as recurseKnn tests them), the descent into it with far children pushed, the bucket — and a lane
+// whose query is finished takes the next item in the same pass.  The per-query visit order is the
+// recursion's; only WHICH lane runs a query and when is different, so results are bit-identical.
+// Static one-query-per-lane scheduling leaves 13 of 32 lanes busy (the visit count per query is 1..29,
+// mean 2.9); here the bucket scans and descents of a pass run with most lanes busy.
+struct KnnItem { int i, hp1, ll; uint32_t mask; };      // 16 bytes
+
+template <typename LoadQuery, typename StoreResult>
+__device__ __forceinline__ void knn_far_phase(const SmemTree& t, double me2, const int4* __restrict__ items,
+                                              int n_items, LoadQuery load_query, StoreResult store_result) {
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  KnnStackEntry stack[kKnnMaxStack];
+  int sp = 0, next = 0;
+  bool have = false;
+  int qi = 0, hp1 = 1, ll = 0, best = -1;
+  uint32_t mask = 0u;
+  double head = 0.0, qx = 0.0, qy = 0.0, qz = 0.0;
+  while (true) {
+    const unsigned need = __ballot_sync(0xffffffffu, !have);
+    if (!have) {
+      const int idx = next + __popc(need & lt);
+      if (idx < n_items) {
+        const int4 it = __ldcg(items + idx);
+        qi = it.x; hp1 = it.y; ll = it.z; mask = (uint32_t)it.w;
+        load_query(qi, qx, qy, qz, head, best);
+        t.sq[0] = qx; t.sq[kKnnCtaThreads] = qy; t.sq[2 * kKnnCtaThreads] = qz;
+        sp = 0;
+        have = true;
+      }
+    }
+    next += __popc(need);
+    if (!__any_sync(0xffffffffu, have)) break;
+    bool go = false;
+    int h = 0;
+    double rd = 0.0;
+    if (have) {
+      while (sp > 0) {                                 // nested far children first (the recursion is inside them)
+        const KnnStackEntry& e = stack[--sp];
+        if (dmul(e.rd, me2) < head) {
+          h = e.h; rd = e.rd;
+          t.so[0] = e.o[0]; t.so[kKnnCtaThreads] = e.o[1]; t.so[2 * kKnnCtaThreads] = e.o[2];
+          go = true;
+          break;
+        }
+      }
+      while (!go && mask != 0u) {                      // then the root path, deepest level first
+        const int a = 31 - __clz(mask);
+        mask &= ~(1u << a);
+        const int n = (hp1 >> (ll - a)) - 1;
+        double cut; int cd;
+        ldg_node(t.g_node, n, cut, cd);
+        const double off = dsub(t.sq[cd * kKnnCtaThreads], cut);
+        const double rd_new = dmul(off, off);
+        if (dmul(rd_new, me2) < head) {
+          t.so[0] = 0.0; t.so[kKnnCtaThreads] = 0.0; t.so[2 * kKnnCtaThreads] = 0.0;
+          t.so[cd * kKnnCtaThreads] = off;
+          h = ((hp1 >> (ll - a - 1)) ^ 1) - 1;         // sibling of the path node of level a + 1
+          rd = rd_new;
+          go = true;
+        }
+      }
+      if (!go) { store_result(qi, best, head); have = false; }
+    }
+    if (go) {
+      int l = 31 - __clz(h + 1);
+      while (l < t.levels) {
+        double cut; int cd;
+        ldg_node(t.g_node, h, cut, cd);
+        if (cd == 3) break;
+        const double q = t.sq[cd * kKnnCtaThreads];
+        const double old_off = t.so[cd * kKnnCtaThreads];
+        const double new_off = dsub(q, cut);
+        const double rd_new = dadd(rd, dadd(-dmul(old_off, old_off), dmul(new_off, new_off)));
+        const int right = q > cut ? 1 : 0;
+        if (dmul(rd_new, me2) < head && sp < kKnnMaxStack) {
+          KnnStackEntry& e = stack[sp++];
+          e.rd = rd_new;
+          e.o[0] = t.so[0]; e.o[1] = t.so[kKnnCtaThreads]; e.o[2] = t.so[2 * kKnnCtaThreads];
+          e.o[cd] = new_off;
+          e.h = 2 * h + 2 - right;
+        }
+        h = 2 * h + 1 + right;
+        ++l;
+      }
+      scan_bucket(t.pb, (h + 1 - (1 << l)) << (t.levels - l), qx, qy, qz, head, best);
+    }
+  }
 }
 
 }  // namespace dev

@@ -432,7 +432,8 @@ int icp_begin(sm_handle* h, const double* guess) {
   H_RC(h->cdim.reserve(kd_compact_node_slots(levels)));
   H_RC(h->cpb.reserve(kd_compact_bucket_entries(levels) * 3 * sizeof(double)));
   H_RC(h->cpn.reserve(kd_compact_bucket_entries(levels) * sizeof(BucketNormal)));
-  H_RC(h->slot.reserve((size_t)ns * sizeof(int32_t) + 64));
+  const size_t slot_bytes = (((size_t)ns * sizeof(int32_t) + 64 + 255) / 256) * 256;
+  H_RC(h->slot.reserve(slot_bytes + ((size_t)ns + kKnnItemSlack) * sizeof(int4)));
   H_RC(h->d2.reserve((size_t)ns * sizeof(double)));
   H_RC(h->hist.reserve((2 * kHistBins + 64) * sizeof(uint32_t) + 32 * sizeof(double)));
   H_RC(h->cand_idx.reserve((size_t)nb * 512 * 8 * sizeof(double)));   // cand_terms
@@ -460,6 +461,7 @@ int icp_begin(sm_handle* h, const double* guess) {
   b.src_vals[0] = (uint32_t*)(b.src_keys[1] + h->sstride); b.src_vals[1] = b.src_vals[0] + h->sstride;
   b.src_scratch = b.src_vals[1] + h->sstride;
   b.slot = (int32_t*)h->slot.p;
+  b.knn_items = reinterpret_cast<int4*>((char*)h->slot.p + slot_bytes);
   b.d2 = (double*)h->d2.p; b.hist = (uint32_t*)h->hist.p;
   b.hist2 = b.hist + kHistBins;
   b.sums = (double*)(b.hist + 2 * kHistBins + 64);
