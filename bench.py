@@ -52,9 +52,9 @@ ITERATIONS = 30
 BYTES_PER_POINT_ITER = 64           # whole iteration
 BYTES_KNN_PER_POINT = 40            # of which the k-NN kernel: 16 src + 16 matched + 8 write
 # dram__bytes_read + dram__bytes_write of ONE launch of icp_knn_kernel from the committed
-# `ncu --set full` capture (profiles/r02_ncu_full_icp_knn_accum_finish.txt; ncu flushes the caches
+# `ncu --set full` capture (profiles/r02_ncu_full_icp_knn_final.txt; ncu flushes the caches
 # before the launch, so this is the cold figure; the steady state of an alignment is lower)
-NCU_TRAFFIC_BYTES = 6_284_288
+NCU_TRAFFIC_BYTES = 6_438_400
 KNN_KERNEL = "icp_knn_kernel"
 METRIC = "scan-pair alignments/sec (120k->500k pts, 30 ICP iters)"
 UNIT = "alignments/s"

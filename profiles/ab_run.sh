@@ -1,4 +1,4 @@
-# parity of the product build, then profiles/ab_lib.sh over A/B builds
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_gpu_icp.py tests/test_gpu_full_size.py -x -q -m gpu 2>&1 | tail -3
-timeout 400 bash profiles/ab_lib.sh libsm_b200_2p4.so libsm_b200.so
+bash profiles/ncu_run.sh
+timeout 400 bash profiles/ab_pipelines.sh "16 2" "24 2" "32 2" "24 3"
+SM_B200_KNN_QPC=768 timeout 100 bash profiles/ab_pipelines.sh "16 2"

@@ -18,7 +18,13 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread",
-        "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max"]
+        "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 
 
 def launches(path):
