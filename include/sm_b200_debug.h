@@ -6,7 +6,11 @@
  *     minimum-norm branch, SVD fallback = SolvePossiblyUnderdeterminedLinearSystem, icp_fast.cc:204-254),
  *     run on the device exactly as icp_finish_kernel calls it;
  *   - the BFGS minimiser of the GICP stage (csrc/gicp_host.h: PCL's port of GSL vector_bfgs2 with the
- *     Fletcher line search, parameters of gicp_omp_impl.hpp:218-224), run on a caller-supplied function. */
+ *     Fletcher line search, parameters of gicp_omp_impl.hpp:218-224), run on a caller-supplied function.
+ * And one launch shape that is otherwise only reachable through whole alignments:
+ *   - sm_knn1 with the scheduling the ICP iteration uses when many alignments are in flight
+ *     (queries_per_cta > 256: lockstep root visits, then the lanes of a warp pull parked searches), so the
+ *     index sets and squared distances of that path are compared with the oracle's directly. */
 #ifndef SM_B200_DEBUG_H_
 #define SM_B200_DEBUG_H_
 
@@ -26,6 +30,12 @@ typedef int (*sm_debug_fdf)(const double* x_6, double* f, double* g_6, void* use
  * 2 no progress, -1 error. */
 int sm_debug_bfgs_minimize(sm_debug_fdf fn, void* user, double* x_6_inout, double grad_tol,
                            int32_t max_iterations, int32_t* iterations, int32_t* evaluations, int32_t* status);
+
+/* sm_knn1 (include/sm_b200.h) with `queries_per_cta` queries per 256-thread CTA (rounded up to a multiple of
+ * 256; 0 = sm_knn1's own one query per thread). */
+int sm_debug_knn1_batched(int device, const double* target_3xn, int64_t n_target, const double* query_3xn,
+                          int64_t n_query, double epsilon, int bucket_size, int32_t queries_per_cta,
+                          int32_t* ids, double* dists2);
 
 #ifdef __cplusplus
 }

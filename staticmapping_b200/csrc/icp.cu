@@ -181,18 +181,10 @@ icp_knn_kernel(IcpBuffers b, IcpParams p, int per_cta) {
   }
 }
 
-#ifndef SMB_KNN_QPT
-#define SMB_KNN_QPT 4                 // queries per thread and batch of the two-phase kernel (<= kKnnMaxQpt)
-#endif
-// Phase A with several queries per thread (many alignments in flight: queries_per_cta > 256).  Per batch
-// of 256 * QPT queries of a CTA:
-//   (1) every thread transforms its queries (one per pass, consecutive threads = consecutive queries) and
-//       does their ROOT visit in lockstep with its warp: all lanes walk the same number of levels and scan
-//       one bucket each.  A query without far-side candidates is final here (~1/3 of them);
-//   (2) the others are parked as 16-byte items (knn_smem.cuh) and the warp works through its list with
-//       every lane pulling the next item as soon as its query is finished.
-// The one-query-per-thread form of round 1 / early round 2 (knn1_smem, still used by sm_knn1) spends its
-// time in passes in which a few lanes finish long searches: 13 of 32 lanes busy on average.
+// Phase A with several queries per thread (many alignments in flight: queries_per_cta > 256): lockstep root
+// visits, then the lanes of every warp pull the parked searches of their batch (knn_batch_cta, knn_smem.cuh).
+// The one-query-per-thread form spends its time in passes in which a few lanes finish long searches
+// (11.7 of 32 lanes busy on average, 18.0 here).
 template <bool kAllSmem>
 __global__ void __launch_bounds__(kKnnCtaThreads, SMB_KNN_MIN_CTAS)
 icp_knn_batch_kernel(IcpBuffers b, IcpParams p, int per_cta) {
@@ -203,54 +195,20 @@ icp_knn_batch_kernel(IcpBuffers b, IcpParams p, int per_cta) {
   if (threadIdx.x < 16) T[threadIdx.x] = b.state->T_iter[threadIdx.x];
   __syncthreads();
   const int begin = blockIdx.x * per_cta, end = min(begin + per_cta, p.n_source);
-  const int warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-  const int qpt = min(SMB_KNN_QPT, (per_cta + kKnnCtaThreads - 1) / kKnnCtaThreads);
-  const double me2 = p.max_error2;
   mbar_wait(bar, 0);      // every thread waits: the CTA must not retire while the copy engine writes its smem
-  auto finish = [&](int i, int slot, double d2) {
-    b.slot[i] = slot;
-    b.d2[i] = d2;
-    // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident)
-    if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
-  };
-  for (int base = begin; base < end; base += kKnnCtaThreads * qpt) {
-    const int qb = min(qpt, (begin + per_cta - base) / kKnnCtaThreads);   // per_cta is a multiple of the CTA size
-    int4* items = b.knn_items + base + warp * 32 * qb;      // this warp's list: inside the batch's own index range
-    int count = 0;
-    for (int j = 0; j < qb; ++j) {
-      const int i = base + j * kKnnCtaThreads + threadIdx.x;
-      bool far = false;
-      int4 item = make_int4(0, 0, 0, 0);
-      if (i < end) {
-        double px, py, pz, head;
-        int best, hp1, ll;
-        uint32_t mask;
-        transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], px, py, pz);
-        knn_root_visit<kAllSmem>(tree, px, py, pz, me2, head, best, hp1, ll, mask);
-        if (mask == 0u) {
-          finish(i, best, head);
-        } else {
-          b.slot[i] = best;
-          b.d2[i] = head;
-          far = true;
-          item = make_int4(i, hp1, ll, (int)mask);
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, far);
-      if (far) items[count + __popc(m & lt)] = item;
-      count += __popc(m);
-    }
-    __syncwarp();
-    knn_far_phase(tree, me2, items, count,
-                  [&](int i, double& qx, double& qy, double& qz, double& head, int& best) {
-                    transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], qx, qy, qz);
-                    head = __ldcg(b.d2 + i);
-                    best = __ldcg(b.slot + i);
-                  },
-                  finish);
-    __syncwarp();
-  }
+  knn_batch_cta<kAllSmem>(
+      tree, begin, end, per_cta, p.max_error2, b.knn_items,
+      [&](int i, double& x, double& y, double& z) {
+        transform_point(T, b.src0[i], b.src0[b.sstride + i], b.src0[2 * b.sstride + i], x, y, z);
+      },
+      [&](int i, int best, double head) { b.slot[i] = best; b.d2[i] = head; },
+      [&](int i, double& head, int& best) { head = __ldcg(b.d2 + i); best = __ldcg(b.slot + i); },
+      [&](int i, int slot, double d2) {
+        b.slot[i] = slot;
+        b.d2[i] = d2;
+        // fire-and-forget reduction straight into the 2048-bin global histogram (L2-resident)
+        if (finite_d2(d2)) atomicAdd(&b.hist[dist_bin(d2)], 1u);
+      });
 }
 
 // -------------------------------------------------------------------------------- phase B
@@ -359,6 +317,27 @@ knn_query_kernel(KdCompact kc, const double* __restrict__ query, int64_t qstride
   }
 }
 
+
+// the same search with the batch scheduling of icp_knn_batch_kernel (sm_debug_knn1_batched: parity tests of
+// the warp-pulled far visits against the oracle's index sets); ids[] / d2[] double as the parking arrays
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kKnnCtaThreads, SMB_KNN_MIN_CTAS)
+knn_query_batch_kernel(KdCompact kc, const double* __restrict__ query, int64_t qstride, int nq,
+                       double max_error2, int per_cta, int32_t* __restrict__ ids, double* __restrict__ d2,
+                       int4* __restrict__ items) {
+  extern __shared__ __align__(128) unsigned char knn_smem[];
+  uint64_t* bar; double* extra;
+  const SmemTree tree = stage_tree(kc, knn_smem, &bar, &extra);
+  const int begin = blockIdx.x * per_cta, end = min(begin + per_cta, nq);
+  mbar_wait(bar, 0);
+  knn_batch_cta<kAllSmem>(
+      tree, begin, end, per_cta, max_error2, items,
+      [&](int i, double& x, double& y, double& z) { x = query[i]; y = query[qstride + i]; z = query[2 * qstride + i]; },
+      [&](int i, int best, double head) { ids[i] = best; d2[i] = head; },
+      [&](int i, double& head, int& best) { head = __ldcg(d2 + i); best = __ldcg(ids + i); },
+      [&](int i, int slot, double d) { ids[i] = slot >= 0 ? kc.pid[slot] : -1; d2[i] = d; });
+}
+
 }  // namespace
 
 int icp_accum_blocks(int n_source) { return ceil_div(n_source, kAccTile); }
@@ -385,15 +364,21 @@ static void knn_geometry(int nq, int queries_per_cta, int* grid, int* per_cta) {
 }
 
 int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
-              int32_t* ids, double* d2, cudaStream_t stream) {
+              int32_t* ids, double* d2, cudaStream_t stream, int queries_per_cta, int4* items) {
   if (nq <= 0) return 0;
   int grid, per;
-  knn_geometry(nq, 0, &grid, &per);
+  knn_geometry(nq, queries_per_cta, &grid, &per);
   const size_t smem = knn_smem_bytes(kc.levels);
-  if (kc.levels <= kKnnSmemLevels)
+  const bool all = kc.levels <= kKnnSmemLevels;
+  if (per > kKnnCtaThreads) {
+    if (!items) return -1;
+    if (all) knn_query_batch_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2, items);
+    else knn_query_batch_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2, items);
+  } else if (all) {
     knn_query_kernel<true><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
-  else
+  } else {
     knn_query_kernel<false><<<grid, kKnnCtaThreads, smem, stream>>>(kc, query, qstride, nq, max_error2, per, ids, d2);
+  }
   SMB_CUDA_OK(cudaGetLastError());
   return 0;
 }

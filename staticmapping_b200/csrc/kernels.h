@@ -146,7 +146,7 @@ int icp_enqueue_iterations(const IcpBuffers& b, const IcpParams& p, int start_it
 void icp_finish_launch(const IcpBuffers& b, const IcpParams& p, int nblocks_b, cudaStream_t stream);
 // stand-alone k-NN over an already built tree (compact layout incl. pid): ids = original indices
 int knn_query(const KdCompact& kc, const double* query, int64_t qstride, int nq, double max_error2,
-              int32_t* ids, double* d2, cudaStream_t stream);
+              int32_t* ids, double* d2, cudaStream_t stream, int queries_per_cta = 0, int4* items = nullptr);
 int kd_fill_buckets(const double* coord, int64_t cstride, const double* nrm, int64_t nstride,
                     const uint32_t* leaf_order, int n, BucketPoint* bpts, BucketNormal* bnrm,
                     cudaStream_t stream);

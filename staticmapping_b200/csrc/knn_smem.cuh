@@ -470,6 +470,58 @@ __device__ __forceinline__ void knn_far_phase(const SmemTree& t, double me2, con
   }
 }
 
+// One CTA's range [begin, end) in batches of 256 * qpt queries (per_cta is a multiple of the CTA size):
+//   (1) every thread loads its queries (one per pass, consecutive threads = consecutive queries) and does
+//       their root visits in lockstep with its warp.  A query without far-side candidates is final here;
+//   (2) the others are parked (park: head and best of the moment; a 16-byte item in the warp's slice of
+//       items_all, which lies inside the batch's own index range) and the warp works through its list
+//       (knn_far_phase).
+// load_q(i, x, y, z), park(i, best, head), unpark(i, head&, best&), finish(i, best, head).
+constexpr int kKnnMaxQpt = 4;
+template <bool kAllSmem, typename LoadQ, typename Park, typename Unpark, typename Finish>
+__device__ __forceinline__ void knn_batch_cta(const SmemTree& tree, int begin, int end, int per_cta, double me2,
+                                              int4* __restrict__ items_all, LoadQ load_q, Park park,
+                                              Unpark unpark, Finish finish) {
+  const int warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  const int qpt = min(kKnnMaxQpt, per_cta / kKnnCtaThreads);
+  for (int base = begin; base < end; base += kKnnCtaThreads * qpt) {
+    const int qb = min(qpt, (begin + per_cta - base) / kKnnCtaThreads);
+    int4* items = items_all + base + warp * 32 * qb;
+    int count = 0;
+    for (int j = 0; j < qb; ++j) {
+      const int i = base + j * kKnnCtaThreads + threadIdx.x;
+      bool far = false;
+      int4 item = make_int4(0, 0, 0, 0);
+      if (i < end) {
+        double px, py, pz, head;
+        int best, hp1, ll;
+        uint32_t mask;
+        load_q(i, px, py, pz);
+        knn_root_visit<kAllSmem>(tree, px, py, pz, me2, head, best, hp1, ll, mask);
+        if (mask == 0u) {
+          finish(i, best, head);
+        } else {
+          park(i, best, head);
+          far = true;
+          item = make_int4(i, hp1, ll, (int)mask);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, far);
+      if (far) items[count + __popc(m & lt)] = item;
+      count += __popc(m);
+    }
+    __syncwarp();
+    knn_far_phase(tree, me2, items, count,
+                  [&](int i, double& qx, double& qy, double& qz, double& head, int& best) {
+                    load_q(i, qx, qy, qz);
+                    unpark(i, head, best);
+                  },
+                  finish);
+    __syncwarp();
+  }
+}
+
 }  // namespace dev
 }  // namespace smb
 

@@ -1404,8 +1404,24 @@ int sm_calculate_normals(int device, const double* points, int64_t n, double* ou
   return SM_OK;
 }
 
+static int knn1_impl(int device, const double* target, int64_t nt, const double* query, int64_t nq,
+                     double epsilon, int bucket, int queries_per_cta, int32_t* ids, double* d2);
+
 int sm_knn1(int device, const double* target, int64_t nt, const double* query, int64_t nq,
             double epsilon, int bucket, int32_t* ids, double* d2) {
+  return knn1_impl(device, target, nt, query, nq, epsilon, bucket, 0, ids, d2);
+}
+
+// test hook (include/sm_b200_debug.h): the same search with the launch shape and warp-level scheduling the
+// ICP iteration uses with many alignments in flight
+int sm_debug_knn1_batched(int device, const double* target, int64_t nt, const double* query, int64_t nq,
+                          double epsilon, int bucket, int32_t queries_per_cta, int32_t* ids, double* d2) {
+  if (queries_per_cta < 0 || queries_per_cta > (1 << 20)) return SM_ERR_BAD_ARGUMENT;
+  return knn1_impl(device, target, nt, query, nq, epsilon, bucket, queries_per_cta, ids, d2);
+}
+
+static int knn1_impl(int device, const double* target, int64_t nt, const double* query, int64_t nq,
+                     double epsilon, int bucket, int queries_per_cta, int32_t* ids, double* d2) {
   // buckets hold at most 8 points (one padded bucket = x[8] y[8] z[8]); libnabo's default is 8
   if (!target || !query || nt <= 0 || nt > (1 << 30) || nq < 0 || nq > (1 << 30) || bucket < 2 || bucket > 8 ||
       !(epsilon >= 0.0))
@@ -1417,10 +1433,10 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   const int64_t ts = pad64(nt), qs = pad64(nq > 0 ? nq : 1);
   const int levels = kd_num_levels((int)nt, bucket);
   if (levels > 24) return SM_ERR_BAD_ARGUMENT;
-  DevBuf stage, tgt, qry, nodes, order, kdws, ids_d, d2_d, ccut, cdim, cpb, cpid;
+  DevBuf stage, tgt, qry, nodes, order, kdws, ids_d, d2_d, ccut, cdim, cpb, cpid, items;
   int rc = 0;
   auto cleanup = [&]() {
-    DevBuf* bufs[] = {&stage, &tgt, &qry, &nodes, &order, &kdws, &ids_d, &d2_d, &ccut, &cdim, &cpb, &cpid};
+    DevBuf* bufs[] = {&stage, &tgt, &qry, &nodes, &order, &kdws, &ids_d, &d2_d, &ccut, &cdim, &cpb, &cpid, &items};
     for (DevBuf* b : bufs) b->release();
   };
 #define K_OK(expr) do { if ((rc = (expr)) != 0) { cleanup(); return rc < 0 ? rc : SM_ERR_CUDA; } } while (0)
@@ -1437,6 +1453,7 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
   K_OK(cpid.reserve(kd_compact_bucket_entries(levels) * sizeof(int32_t)));
   K_OK(ids_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(int32_t)));
   K_OK(d2_d.reserve((size_t)(nq > 0 ? nq : 1) * sizeof(double)));
+  K_OK(items.reserve(((size_t)nq + kKnnItemSlack) * sizeof(int4)));
   K_CUDA(cudaMemcpyAsync(stage.p, target, (size_t)3 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
   deinterleave3_kernel<<<ceil_div(nt, 256), 256, 0, s>>>((const double*)stage.p, (double*)tgt.p, ts, (int)nt);
   K_CUDA(cudaStreamSynchronize(s));
@@ -1455,7 +1472,7 @@ int sm_knn1(int device, const double* target, int64_t nt, const double* query, i
     K_CUDA(cudaMemcpyAsync(stage.p, query, (size_t)3 * nq * sizeof(double), cudaMemcpyHostToDevice, s));
     deinterleave3_kernel<<<ceil_div(nq, 256), 256, 0, s>>>((const double*)stage.p, (double*)qry.p, qs, (int)nq);
     K_OK(knn_query(kc, (const double*)qry.p, qs, (int)nq, (1.0 + epsilon) * (1.0 + epsilon), (int32_t*)ids_d.p,
-                   (double*)d2_d.p, s));
+                   (double*)d2_d.p, s, queries_per_cta, (int4*)items.p));
     K_CUDA(cudaMemcpyAsync(ids, ids_d.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     K_CUDA(cudaMemcpyAsync(d2, d2_d.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, s));
   }

@@ -412,15 +412,20 @@ def _ptr(a):
     return a.ctypes.data
 
 
-def knn1(target, query, epsilon=3.16, bucket_size=8, device=0):
-    """libnabo-compatible 1-NN on the GPU (NNS::create + knn, icp_fast.cc:466-467,177-178)."""
+def knn1(target, query, epsilon=3.16, bucket_size=8, device=0, queries_per_cta=0):
+    """libnabo-compatible 1-NN on the GPU (NNS::create + knn, icp_fast.cc:466-467,177-178).
+    queries_per_cta > 0: the test hook sm_debug_knn1_batched (the launch shape of batched alignments)."""
     lib = _lib.lib()
     t = np.ascontiguousarray(np.asarray(target, dtype=np.float64))
     q = np.ascontiguousarray(np.asarray(query, dtype=np.float64))
     ids = np.empty(q.shape[0], dtype=np.int32)
     d2 = np.empty(q.shape[0], dtype=np.float64)
-    rc = lib.sm_knn1(device, t.ctypes.data, t.shape[0], q.ctypes.data, q.shape[0], float(epsilon),
-                     int(bucket_size), ids.ctypes.data, d2.ctypes.data)
+    if queries_per_cta:
+        rc = lib.sm_debug_knn1_batched(device, t.ctypes.data, t.shape[0], q.ctypes.data, q.shape[0], float(epsilon),
+                                       int(bucket_size), int(queries_per_cta), ids.ctypes.data, d2.ctypes.data)
+    else:
+        rc = lib.sm_knn1(device, t.ctypes.data, t.shape[0], q.ctypes.data, q.shape[0], float(epsilon),
+                         int(bucket_size), ids.ctypes.data, d2.ctypes.data)
     if rc == -20:
         raise RuntimeError("staticmapping_b200: no CUDA device (no CPU fallback)")
     if rc != 0:
