@@ -57,25 +57,6 @@ def test_config2_knn_on_real_clouds_bit_exact(pair0):
         assert np.array_equal(d2_g, d2_o)
 
 
-def test_config2_batched_search_full_size(pair0):
-    # the launch shape bench.py uses with many alignments in flight (1 024 queries per CTA: lockstep root
-    # visits + warp-pulled far visits): the same index sets, and an alignment bit-identical to the default one
-    src, sub, P = pair0
-    tp, tn = O.calculate_normals(sub)
-    ids_o, d2_o = O.knn1(tp, src, epsilon=3.16)
-    ids_g, d2_g = smb.knn1(tp, src, epsilon=3.16, queries_per_cta=1024)
-    assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
-    res = []
-    for qpc in (0, 1024):
-        m = smb.IcpFast()
-        m.InitWithXml({"max_iteration": 30, "disable_convergence_check": 1, "knn_queries_per_cta": qpc})
-        m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tp, tn))
-        ok, r = m.Align(np.eye(4))
-        assert ok
-        res.append((r.copy(), m.GetFitnessScore()))
-    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
-
-
 def test_config3_ndt_full_size(pair0):
     src, sub, P = pair0
     s32, t32 = src.astype(np.float32), sub.astype(np.float32)

@@ -24,51 +24,6 @@ def test_knn_index_sets_bit_exact(nt, nq, eps):
     assert np.array_equal(d2_g, d2_o)          # bit-exact squared distances
 
 
-@pytest.mark.parametrize("qpc", [512, 768, 1024, 4096])
-@pytest.mark.parametrize("eps", [0.0, 3.16])
-@pytest.mark.parametrize("nt,nq", [(9, 100), (1000, 5000), (106784, 120000)])
-def test_knn_batched_schedule_bit_exact(nt, nq, eps, qpc):
-    # the launch shape of batched alignments: lockstep root visits, then the lanes of a warp pull the parked
-    # searches (eps = 0 parks nearly every query and makes the far visits long)
-    rng = np.random.default_rng(nt * 11 + nq)
-    T = rng.normal(size=(nt, 3)) * np.array([20.0, 10.0, 2.0])
-    Q = rng.normal(size=(nq, 3)) * np.array([22.0, 11.0, 2.5])
-    ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
-    ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, queries_per_cta=qpc)
-    assert np.array_equal(ids_g, ids_o)
-    assert np.array_equal(d2_g, d2_o)
-
-
-def test_knn_batched_schedule_lidar_scene_and_ties():
-    src, sub, _ = scenes.lidar_pair(pair=0)
-    ids_o, d2_o = O.knn1(sub, src, epsilon=3.16)
-    ids_g, d2_g = smb.knn1(sub, src, epsilon=3.16, queries_per_cta=1024)
-    assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
-    rng = np.random.default_rng(5)
-    base = rng.normal(size=(500, 3))
-    T = np.concatenate([base, base, base[:100]])        # duplicates: ties resolved by visit order
-    Q = np.concatenate([base[:300], rng.normal(size=(700, 3))])
-    for eps in (0.0, 3.16):
-        ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
-        ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, queries_per_cta=512)
-        assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
-
-
-@pytest.mark.parametrize("qpc", [512, 1024, 2048])
-def test_align_with_batched_search_is_bit_identical(qpc):
-    src, sub, _ = scenes.lidar_pair(pair=1)
-    tgt = smb.CalculateNormals(sub)
-    results = []
-    for q in (0, qpc):
-        m = smb.IcpFast(0)
-        m.InitWithXml({"knn_queries_per_cta": q})
-        m.SetInputSource(smb.EigenCloud(src)); m.SetInputTarget(smb.EigenCloud(tgt.points, tgt.normals))
-        ok, res = m.Align(np.eye(4))
-        results.append((ok, res.copy(), m.GetFitnessScore(), m.GetAlignInfo()["iterations"]))
-    assert results[0][0] == results[1][0] and results[0][3] == results[1][3]
-    assert np.array_equal(results[0][1], results[1][1]) and results[0][2] == results[1][2]
-
-
 @pytest.mark.parametrize("bucket", [2, 3, 4, 5, 7])
 def test_knn_other_bucket_sizes(bucket):
     # libnabo's bucketSize parameter; one padded bucket of the compact layout holds up to 8 points
