@@ -381,6 +381,83 @@ inline void mulpt_f(const float* T, const float* p, float* out) {   // (T * [p;1
   for (int r = 0; r < 3; ++r) out[r] = ((T[r] * p[0] + T[r + 4] * p[1]) + T[r + 8] * p[2]) + T[r + 12] * 1.0f;
 }
 
+// The per-point part of one outer iteration (gicp_omp_impl.hpp:419-463): query = transformation_ * (guess * p),
+// exact 1-NN in the target, gate on the squared float distance, M_i = (R C1 R^T + C2)^-1 with
+// R = rot(transformation_ * guess) formed in double.  Correspondences come out in ascending source index.
+void GicpCorrespond(const float* src, int64_t ns, const float* tgt, int64_t nt, const float* guess,
+                    const float* transformation, const std::vector<double>& cov_s, const std::vector<double>& cov_t,
+                    double dist_threshold, std::vector<float>* query_io, std::vector<int32_t>* nn_io,
+                    std::vector<double>* maha_io, std::vector<int>* si_out, std::vector<int>* ti_out) {
+  std::vector<float>& query = *query_io;
+  std::vector<int32_t>& nn = *nn_io;
+  std::vector<double>& maha = *maha_io;
+  std::vector<int>& si = *si_out;
+  std::vector<int>& ti = *ti_out;
+  si.clear(); ti.clear();
+  double TR[16];   // transform_R = transformation_ * guess in double (:423-427)
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += (double)transformation[i + 4 * k] * (double)guess[k + 4 * j];
+      TR[i + 4 * j] = s;
+    }
+  double R[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = TR[r + 4 * c];
+  for (int64_t i = 0; i < ns; ++i) {   // query = transformation_ * (guess * p) (:437-439)
+    float q1[3];
+    mulpt_f(guess, src + 3 * i, q1);
+    mulpt_f(transformation, q1, &query[(size_t)(3 * i)]);
+  }
+  ExactNn1Float(tgt, nt, query.data(), ns, nn.data());
+  for (int64_t i = 0; i < ns; ++i) {
+    const int j = nn[(size_t)i];
+    if (j < 0) continue;
+    const float d = ndt_dist2f(query[(size_t)(3 * i)], query[(size_t)(3 * i + 1)], query[(size_t)(3 * i + 2)], tgt + 3 * (int64_t)j);
+    if ((double)d < dist_threshold) {   // :448
+      const double* C1 = &cov_s[(size_t)(9 * i)];
+      const double* C2 = &cov_t[(size_t)(9 * (int64_t)j)];
+      double M[9], tmp[9];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+        M[r * 3 + c] = (R[r * 3] * C1[c] + R[r * 3 + 1] * C1[3 + c]) + R[r * 3 + 2] * C1[6 + c];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+        tmp[r * 3 + c] = ((M[r * 3] * R[c * 3] + M[r * 3 + 1] * R[c * 3 + 1]) + M[r * 3 + 2] * R[c * 3 + 2]) + C2[r * 3 + c];
+      inverse3_cofactor(tmp, &maha[(size_t)(9 * i)]);
+      si.push_back((int)i); ti.push_back(j);
+    }
+  }
+}
+
+// OptimizationFunctorWithIndices::fdf / operator() / df (gicp_omp_impl.hpp:255-377) at state x over the
+// correspondences (si, ti): f = mean res^T M res, g = [2/m sum M res ; <dR/dangle, 2/m sum (base p) (M res)^T>].
+void GicpCost(const float* src, const float* tgt, const float* base, const std::vector<double>& maha,
+              const std::vector<int>& si, const std::vector<int>& ti, const double* xx, double* f, double* g) {
+  const int m = (int)si.size();
+  float T[16];
+  for (int i = 0; i < 16; ++i) T[i] = base[i];
+  GicpApplyState(T, xx);
+  double fs = 0.0, gt[3] = {0, 0, 0}, Rm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < m; ++c) {
+    const float* ps = src + 3 * (int64_t)si[(size_t)c];
+    const float* pt = tgt + 3 * (int64_t)ti[(size_t)c];
+    float pp[3], pb[3];
+    mulpt_f(T, ps, pp);
+    const double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
+    const double* M = &maha[(size_t)(9 * (int64_t)si[(size_t)c])];
+    double temp[3];
+    for (int r = 0; r < 3; ++r) temp[r] = (M[r * 3] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
+    fs += (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
+    for (int r = 0; r < 3; ++r) gt[r] += temp[r];
+    mulpt_f(base, ps, pb);
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Rm[r * 3 + cc] += (double)pb[r] * temp[cc];
+  }
+  if (f) *f = fs / (double)m;
+  if (g) {
+    for (int r = 0; r < 3; ++r) g[r] = gt[r] * (2.0 / m);
+    for (int q = 0; q < 9; ++q) Rm[q] *= 2.0 / m;
+    GicpRDerivative(xx, Rm, g);
+  }
+}
+
 // GeneralizedIterativeClosestPoint::computeTransformation (gicp_omp_impl.hpp:381-514)
 int GicpAlign(const float* src, int64_t ns, const float* tgt, int64_t nt, const float* guess /*col-major*/,
               const GicpOptions& o, float* final_T, int* iterations, int* bfgs_evals) {
@@ -397,38 +474,8 @@ int GicpAlign(const float* src, int64_t ns, const float* tgt, int64_t nt, const 
   int nr_iterations = 0, evals = 0;
   bool converged = false;
   while (!converged) {
-    double TR[16];   // transform_R = transformation_ * guess in double (:423-427)
-    for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 4; ++j) {
-        double s = 0.0;
-        for (int k = 0; k < 4; ++k) s += (double)transformation[i + 4 * k] * (double)guess[k + 4 * j];
-        TR[i + 4 * j] = s;
-      }
-    double R[9];
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = TR[r + 4 * c];
-    for (int64_t i = 0; i < ns; ++i) {   // query = transformation_ * (guess * p) (:437-439)
-      float q1[3];
-      mulpt_f(guess, src + 3 * i, q1);
-      mulpt_f(transformation, q1, &query[(size_t)(3 * i)]);
-    }
-    ExactNn1Float(tgt, nt, query.data(), ns, nn.data());
     std::vector<int> si, ti;
-    for (int64_t i = 0; i < ns; ++i) {
-      const int j = nn[(size_t)i];
-      if (j < 0) continue;
-      const float d = ndt_dist2f(query[(size_t)(3 * i)], query[(size_t)(3 * i + 1)], query[(size_t)(3 * i + 2)], tgt + 3 * (int64_t)j);
-      if ((double)d < dist_threshold) {   // :448
-        const double* C1 = &cov_s[(size_t)(9 * i)];
-        const double* C2 = &cov_t[(size_t)(9 * (int64_t)j)];
-        double M[9], tmp[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
-          M[r * 3 + c] = (R[r * 3] * C1[c] + R[r * 3 + 1] * C1[3 + c]) + R[r * 3 + 2] * C1[6 + c];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
-          tmp[r * 3 + c] = ((M[r * 3] * R[c * 3] + M[r * 3 + 1] * R[c * 3 + 1]) + M[r * 3 + 2] * R[c * 3 + 2]) + C2[r * 3 + c];
-        inverse3_cofactor(tmp, &maha[(size_t)(9 * i)]);
-        si.push_back((int)i); ti.push_back(j);
-      }
-    }
+    GicpCorrespond(src, ns, tgt, nt, guess, transformation, cov_s, cov_t, dist_threshold, &query, &nn, &maha, &si, &ti);
     for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
     const int m = (int)si.size();
     if (m < 4) break;   // NotEnoughPointsException -> caught, loop ends (:470-492)
@@ -440,30 +487,7 @@ int GicpAlign(const float* src, int64_t ns, const float* tgt, int64_t nt, const 
     bfgs::Minimizer mz;
     mz.fdf = [&](const double* xx, double* f, double* g) {   // fdf / operator() / df (:255-377)
       ++evals;
-      float T[16];
-      for (int i = 0; i < 16; ++i) T[i] = base[i];
-      GicpApplyState(T, xx);
-      double fs = 0.0, gt[3] = {0, 0, 0}, Rm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < m; ++c) {
-        const float* ps = src + 3 * (int64_t)si[(size_t)c];
-        const float* pt = tgt + 3 * (int64_t)ti[(size_t)c];
-        float pp[3], pb[3];
-        mulpt_f(T, ps, pp);
-        const double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
-        const double* M = &maha[(size_t)(9 * (int64_t)si[(size_t)c])];
-        double temp[3];
-        for (int r = 0; r < 3; ++r) temp[r] = (M[r * 3] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
-        fs += (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
-        for (int r = 0; r < 3; ++r) gt[r] += temp[r];
-        mulpt_f(base, ps, pb);
-        for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Rm[r * 3 + cc] += (double)pb[r] * temp[cc];
-      }
-      if (f) *f = fs / (double)m;
-      if (g) {
-        for (int r = 0; r < 3; ++r) g[r] = gt[r] * (2.0 / m);
-        for (int q = 0; q < 9; ++q) Rm[q] *= 2.0 / m;
-        GicpRDerivative(xx, Rm, g);
-      }
+      GicpCost(src, tgt, base, maha, si, ti, xx, f, g);
     };
     mz.par = bfgs::Params();   // sigma 0.01, rho 0.01, tau1 9, tau2 0.05, tau3 0.5, order 3 (:218-224)
     mz.init(x);
@@ -545,6 +569,29 @@ int sm_oracle_gicp_covariances(const float* pts, int64_t n, int k, double eps, d
 }
 
 // NdtWithGicp::Align (ndt_gicp.cc:55-112).  Returns 1 / 0 like the reference's bool.
+// Test hook for tests/test_oracle_vs_python_restatement.py: the correspondence step and one cost / gradient
+// evaluation of GICP for given transformation_ (col-major float 4x4), guess = base_transformation_ and state x.
+// maha_out: ns x 9 (row-major, identity where no correspondence), si / ti: capacity ns; returns m.
+int64_t sm_oracle_gicp_cost(const float* src, int64_t ns, const float* tgt, int64_t nt, const float* guess,
+                            const float* transformation, const double* x, double* f, double* g6, double* maha_out,
+                            int32_t* si_out, int32_t* ti_out) {
+  GicpOptions o;
+  std::vector<double> cov_t, cov_s;
+  GicpCovariances(tgt, nt, o.k_correspondences, o.gicp_epsilon, &cov_t);
+  GicpCovariances(src, ns, o.k_correspondences, o.gicp_epsilon, &cov_s);
+  std::vector<double> maha((size_t)(9 * ns));
+  for (int64_t i = 0; i < ns; ++i) for (int q = 0; q < 9; ++q) maha[(size_t)(9 * i + q)] = (q % 4 == 0) ? 1.0 : 0.0;
+  std::vector<float> query((size_t)(3 * ns));
+  std::vector<int32_t> nn((size_t)ns);
+  std::vector<int> si, ti;
+  GicpCorrespond(src, ns, tgt, nt, guess, transformation, cov_s, cov_t, o.corr_dist_threshold * o.corr_dist_threshold,
+                 &query, &nn, &maha, &si, &ti);
+  if (!si.empty()) GicpCost(src, tgt, guess, maha, si, ti, x, f, g6);
+  for (size_t q = 0; q < maha.size(); ++q) maha_out[q] = maha[q];
+  for (size_t c = 0; c < si.size(); ++c) { si_out[c] = si[c]; ti_out[c] = ti[c]; }
+  return (int64_t)si.size();
+}
+
 int sm_oracle_ndt_gicp_align(const float* source, int64_t ns, const float* target, int64_t nt,
                              const double* guess, const sm_oracle_ndt_gicp_options* opt, double* result,
                              double* final_score, sm_oracle_ndt_gicp_info* info) {

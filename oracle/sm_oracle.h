@@ -115,6 +115,10 @@ typedef struct sm_oracle_ndt_gicp_info {
 } sm_oracle_ndt_gicp_info;
 int64_t sm_oracle_approx_voxel_grid(const float* pts, int64_t n, float leaf, float* out, int64_t capacity);
 int sm_oracle_gicp_covariances(const float* pts, int64_t n, int k, double eps, double* cov_out);
+/* test hook: GICP's correspondence step + one cost / gradient evaluation (gicp_omp_impl.hpp:419-463,255-377) */
+int64_t sm_oracle_gicp_cost(const float* src, int64_t ns, const float* tgt, int64_t nt, const float* guess,
+                            const float* transformation, const double* x, double* f, double* g6, double* maha_out,
+                            int32_t* si_out, int32_t* ti_out);
 int sm_oracle_ndt_gicp_align(const float* source, int64_t ns, const float* target, int64_t nt,
                              const double* guess, const sm_oracle_ndt_gicp_options* opt, double* result,
                              double* final_score, sm_oracle_ndt_gicp_info* info);

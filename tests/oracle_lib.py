@@ -78,6 +78,8 @@ def lib():
         _lib.sm_oracle_gicp_covariances.argtypes = [fp, i64, C.c_int, C.c_double, dp]
         _lib.sm_oracle_ndt_gicp_align.argtypes = [fp, i64, fp, i64, dp, C.POINTER(NdtGicpOptions), dp, dp,
                                                   C.POINTER(NdtGicpInfo)]
+        _lib.sm_oracle_gicp_cost.restype = C.c_int64
+        _lib.sm_oracle_gicp_cost.argtypes = [fp, i64, fp, i64, fp, fp, dp, dp, dp, dp, ip, ip]
     return _lib
 
 
@@ -93,6 +95,20 @@ def gicp_covariances(points, k=20, eps=1e-3):
     cov = np.zeros((p.shape[0], 9))
     lib().sm_oracle_gicp_covariances(_f(p), p.shape[0], k, eps, _d(cov))
     return cov.reshape(-1, 3, 3)
+
+
+def gicp_cost(source, target, guess, transformation, x):
+    """GICP correspondence step for (guess, transformation_) and one cost / gradient evaluation at state x
+    (test hook sm_oracle_gicp_cost) -> dict(f, g, maha (ns,3,3), si, ti)."""
+    s, t = _fcloud(source), _fcloud(target)
+    g_cm = np.ascontiguousarray(np.asarray(guess, dtype=np.float32).T).ravel()
+    t_cm = np.ascontiguousarray(np.asarray(transformation, dtype=np.float32).T).ravel()
+    xx = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    f = C.c_double(); g = np.zeros(6); maha = np.zeros((s.shape[0], 9))
+    si = np.zeros(s.shape[0], np.int32); ti = np.zeros(s.shape[0], np.int32)
+    m = lib().sm_oracle_gicp_cost(_f(s), s.shape[0], _f(t), t.shape[0], _f(g_cm), _f(t_cm), _d(xx), C.byref(f), _d(g),
+                                  _d(maha), _i(si), _i(ti))
+    return {"f": f.value, "g": g, "maha": maha.reshape(-1, 3, 3), "si": si[:m].copy(), "ti": ti[:m].copy()}
 
 
 def ndt_gicp_align(source, target, guess=None, voxel_resolution=0.2, using_voxel_filter=True, use_ndt=True):

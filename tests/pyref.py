@@ -400,7 +400,7 @@ class NdtGrid:
         return pi[o], li[o]
 
 
-def _ndt_angle_derivatives(p):
+def _ndt_angle_derivatives(p, dt=F32):
     def cs(a):
         return (1.0, 0.0) if abs(a) < 10e-5 else (math.cos(a), math.sin(a))
     cx, sx = cs(p[3]); cy, sy = cs(p[4]); cz, sz = cs(p[5])
@@ -412,7 +412,7 @@ def _ndt_angle_derivatives(p):
         [-cx * cy * cz, cx * cy * sz, -cx * sy],
         [-cy * sz, -cy * cz, 0.0],
         [cx * cz - sx * sy * sz, -cx * sz - sx * sy * cz, 0.0],
-        [sx * cz + cx * sy * sz, cx * sy * cz - sx * sz, 0.0]]).astype(F32)
+        [sx * cz + cx * sy * sz, cx * sy * cz - sx * sz, 0.0]]).astype(dt)
     h_ang = np.array([
         [-cx * sz - sx * sy * cz, -cx * cz + sx * sy * sz, sx * cy],          # a2
         [-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, -cx * cy],         # a3
@@ -428,49 +428,53 @@ def _ndt_angle_derivatives(p):
         [cx * cy * sz, cx * cy * cz, 0.0],                                    # e3
         [-cy * cz, cy * sz, 0.0],                                             # f1
         [-cx * sz - sx * sy * cz, -cx * cz + sx * sy * sz, 0.0],              # f2
-        [-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, 0.0]]).astype(F32)  # f3
+        [-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, 0.0]]).astype(dt)   # f3
     return j_ang, h_ang
 
 
-def ndt_derivatives(grid, source_f32, trans_f32, p, outlier_ratio=0.55):
-    """computeDerivatives(score_gradient, hessian, trans_cloud, p, true) -> (score, g[6], H[6,6], mean neighbours)."""
+def ndt_derivatives(grid, source_f32, trans_f32, p, outlier_ratio=0.55, f64=False):
+    """computeDerivatives(score_gradient, hessian, trans_cloud, p, true) -> (score, g[6], H[6,6], mean neighbours).
+    f64 = False: pclomp (Matrix<float, 4, 6> point math, registrators/pclomp/ndt_omp_impl.hpp);
+    f64 = True : stock pcl::NormalDistributionsTransform (the same formulas in double, pcl/registration/impl/ndt.hpp),
+                 the matcher NdtWithGicp drives (registrators/ndt_gicp.cc:44-47,82-88)."""
+    dt = np.float64 if f64 else F32
     d1, d2, _ = ndt_gauss_constants(outlier_ratio, grid.resolution)
-    j_ang, h_ang = _ndt_angle_derivatives(p)
+    j_ang, h_ang = _ndt_angle_derivatives(p, dt)
     pi, li = grid.radius_search(trans_f32)
     m = pi.size
     x = source_f32[pi].astype(np.float64)                    # Eigen::Vector3d x(x_pt.x, ...)
-    x4 = x.astype(F32)                                        # Vector4f x4(x[0], x[1], x[2], 0)
-    xj = x4 @ j_ang.T                                         # (m, 8) float
-    PG = np.zeros((m, 3, 6), dtype=F32)                       # rows 0..2 of the 4x6 (row 3 is zero)
+    x4 = x.astype(dt)                                         # pclomp: Vector4f x4(x[0], x[1], x[2], 0)
+    xj = x4 @ j_ang.T                                         # (m, 8)
+    PG = np.zeros((m, 3, 6), dtype=dt)                        # rows 0..2 of the 4x6 (row 3 is zero)
     PG[:, 0, 0] = PG[:, 1, 1] = PG[:, 2, 2] = 1.0
     PG[:, 1, 3] = xj[:, 0]; PG[:, 2, 3] = xj[:, 1]
     PG[:, 0, 4] = xj[:, 2]; PG[:, 1, 4] = xj[:, 3]; PG[:, 2, 4] = xj[:, 4]
     PG[:, 0, 5] = xj[:, 5]; PG[:, 1, 5] = xj[:, 6]; PG[:, 2, 5] = xj[:, 7]
     xh = x4 @ h_ang.T                                         # (m, 15)
-    z = np.zeros(m, dtype=F32)
+    z = np.zeros(m, dtype=dt)
     a = np.stack([z, xh[:, 0], xh[:, 1]], axis=1); b = np.stack([z, xh[:, 2], xh[:, 3]], axis=1)
     c = np.stack([z, xh[:, 4], xh[:, 5]], axis=1); d = xh[:, 6:9]; e = xh[:, 9:12]; f = xh[:, 12:15]
-    PH = np.zeros((m, 6, 3, 6), dtype=F32)                    # block i (rows 4i..4i+2), column j
+    PH = np.zeros((m, 6, 3, 6), dtype=dt)                     # block i (rows 4i..4i+2 / 3i..3i+2), column j
     PH[:, 3, :, 3] = a; PH[:, 4, :, 3] = b; PH[:, 5, :, 3] = c
     PH[:, 3, :, 4] = b; PH[:, 4, :, 4] = d; PH[:, 5, :, 4] = e
     PH[:, 3, :, 5] = c; PH[:, 4, :, 5] = e; PH[:, 5, :, 5] = f
-    xt = (trans_f32[pi].astype(np.float64) - grid.mean[li]).astype(F32)      # x_trans (double) -> x_trans4 (float)
-    ci = grid.icov[li].astype(F32)                                           # c_inv.cast<float>()
-    gd2 = F32(d2)
-    xc = np.einsum("mi,mij->mj", xt, ci)                                     # x_trans4 * c_inv4
+    xt = (trans_f32[pi].astype(np.float64) - grid.mean[li]).astype(dt)       # x_trans (double) [-> x_trans4 (float)]
+    ci = grid.icov[li].astype(dt)                                            # c_inv [.cast<float>()]
+    gd2 = dt(d2)
+    xc = np.einsum("mi,mij->mj", xt, ci)                                     # x_trans * c_inv
     q = np.einsum("mj,mj->m", xt, xc)
     with np.errstate(over="ignore", invalid="ignore"):
-        e_x = np.exp(-gd2 * q * F32(0.5)).astype(F32)
-    score_inc = (-d1 * e_x.astype(np.float64)).astype(F32)                   # float score_inc = -gauss_d1_ * e_x_cov_x
+        e_x = np.exp(-gd2 * q * dt(0.5)).astype(dt)
+    score_inc = (-d1 * e_x.astype(np.float64)).astype(dt)                    # pclomp: float score_inc = -gauss_d1_ * e
     e_x = gd2 * e_x
     valid = ~((e_x > 1) | (e_x < 0) | np.isnan(e_x))
-    e_x = (e_x.astype(np.float64) * d1).astype(F32)                          # e_x_cov_x *= gauss_d1_ (float *= double)
-    cg = np.einsum("mij,mjk->mik", ci, PG)                                   # c_inv4 * point_gradient4
+    e_x = (e_x.astype(np.float64) * d1).astype(dt)                           # e_x_cov_x *= gauss_d1_
+    cg = np.einsum("mij,mjk->mik", ci, PG)                                   # c_inv * point_gradient
     xcg = np.einsum("mi,mik->mk", xt, cg)                                    # (m, 6)
     g_pair = (e_x[:, None] * xcg).astype(np.float64)
-    gg = np.einsum("mri,mrj->mij", PG, cg)                                   # point_gradient4^T * c_inv4_x_point_gradient4
-    xh_ij = np.einsum("mr,mirj->mij", xc, PH)                                # x_trans4_x_c_inv4 * point_hessian block i
-    # hessian(i, j) += e * (-d2 * xcg(i) * xcg(j) + xh(i)(j) + gg(j, i)): a double += of a float expression
+    gg = np.einsum("mri,mrj->mij", PG, cg)                                   # point_gradient^T * c_inv * point_gradient
+    xh_ij = np.einsum("mr,mirj->mij", xc, PH)                                # x_trans^T c_inv * point_hessian block i
+    # hessian(i, j) += e * (-d2 * xcg(i) * xcg(j) + xh(i)(j) + gg(j, i))
     h_pair = (e_x[:, None, None] * (-gd2 * xcg[:, :, None] * xcg[:, None, :] + xh_ij
                                     + np.transpose(gg, (0, 2, 1)))).astype(np.float64)
     v = valid.astype(np.float64)
@@ -513,8 +517,9 @@ def _euler_angles_012_f32(R):
 
 
 def ndt_align(source_f32, target_f32, guess=None, resolution=1.0, step_size=0.1, outlier_ratio=0.55,
-              transformation_epsilon=0.1, max_iterations=35):
-    """Ndt::Align: pclomp computeTransformation + pcl::Registration::getFitnessScore."""
+              transformation_epsilon=0.1, max_iterations=35, f64=False):
+    """Ndt::Align: pclomp computeTransformation + pcl::Registration::getFitnessScore.  f64 = True with
+    transformation_epsilon = 0.01: the stock PCL NDT stage of NdtWithGicp::Align (ndt_gicp.cc:44-47,82-88)."""
     from scipy.spatial import cKDTree
     src = np.ascontiguousarray(source_f32, dtype=F32)
     tgt = np.ascontiguousarray(target_f32, dtype=F32)
@@ -527,7 +532,7 @@ def ndt_align(source_f32, target_f32, guess=None, resolution=1.0, step_size=0.1,
         output = _transform_cloud_f32(g4, output)
     rot = _euler_angles_012_f32(final[:3, :3])
     p = np.array([final[0, 3], final[1, 3], final[2, 3], rot[0], rot[1], rot[2]], dtype=np.float64)
-    score, grad, hess, nbar = ndt_derivatives(grid, src, output, p, outlier_ratio)
+    score, grad, hess, nbar = ndt_derivatives(grid, src, output, p, outlier_ratio, f64)
     nr_iterations, converged, evaluations, nb_sum = 0, False, 1, nbar
     while not converged:
         delta_p = np.linalg.lstsq(hess, -grad, rcond=None)[0]        # JacobiSVD(hessian).solve(-score_gradient)
@@ -552,7 +557,7 @@ def ndt_align(source_f32, target_f32, guess=None, resolution=1.0, step_size=0.1,
             x_t = p + delta_p * a_t
             final = _ndt_pose_matrix_f32(x_t)
             output = _transform_cloud_f32(final, src)
-            score, grad, hess, nbar = ndt_derivatives(grid, src, output, x_t, outlier_ratio)
+            score, grad, hess, nbar = ndt_derivatives(grid, src, output, x_t, outlier_ratio, f64)
             evaluations += 1
             nb_sum += nbar
             delta_p = delta_p * a_t
@@ -568,3 +573,87 @@ def ndt_align(source_f32, target_f32, guess=None, resolution=1.0, step_size=0.1,
     return {"result": final.astype(np.float64), "iterations": nr_iterations, "evaluations": evaluations,
             "fitness": fitness, "trans_probability": trans_probability,
             "mean_neighbors": nb_sum / evaluations}          # a diagnostic of this repo (mean over the evaluations)
+
+
+# ------------------------------------------------------------------------------------ GICP pieces
+# registrators/pclomp/gicp_omp_impl.hpp (the in-tree statement of the stock PCL GICP that NdtWithGicp runs):
+# :59-131 computeCovariances, :419-463 correspondences + Mahalanobis matrices, :255-377 cost / gradient,
+# :133-183 computeRDerivative, :516-527 applyState.
+def gicp_covariances(cloud_f32, k=20, eps=1e-3):
+    from scipy.spatial import cKDTree
+    c = np.ascontiguousarray(cloud_f32, dtype=F32)
+    _, nn = cKDTree(c.astype(np.float64)).query(c.astype(np.float64), k=k)
+    out = np.zeros((c.shape[0], 3, 3))
+    for i in range(c.shape[0]):
+        pts = c[nn[i]]
+        mean = pts.astype(np.float64).sum(axis=0) / k
+        prod = (pts[:, :, None] * pts[:, None, :]).astype(np.float64)       # float products, double sums
+        cov = prod.sum(axis=0) / k - np.outer(mean, mean)
+        w, V = np.linalg.eigh(cov)                                           # ascending: column 0 = smallest
+        out[i] = np.outer(V[:, 2], V[:, 2]) + np.outer(V[:, 1], V[:, 1]) + eps * np.outer(V[:, 0], V[:, 0])
+    return out
+
+
+def _rot_zyx_f32(x3, x4, x5):
+    cx, sx = np.cos(F32(x3)), np.sin(F32(x3)); cy, sy = np.cos(F32(x4)), np.sin(F32(x4))
+    cz, sz = np.cos(F32(x5)), np.sin(F32(x5))
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]], dtype=F32)
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]], dtype=F32)
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]], dtype=F32)
+    return (rz @ ry) @ rx
+
+
+def gicp_apply_state(T_f32, x):
+    """applyState: t.R = Rz(x5) Ry(x4) Rx(x3) * t.R ; t.t += x[0:3]   (all float)."""
+    T = np.array(T_f32, dtype=F32)
+    T[:3, :3] = _rot_zyx_f32(x[3], x[4], x[5]) @ T[:3, :3]
+    T[:3, 3] += np.asarray(x[:3]).astype(F32)
+    return T
+
+
+def gicp_correspond(src_f32, tgt_f32, guess_f32, transformation_f32, cov_s, cov_t, corr_dist=5.0):
+    """-> (source indices, target indices, M_i for every source point (identity without a correspondence))."""
+    from scipy.spatial import cKDTree
+    src = np.ascontiguousarray(src_f32, dtype=F32); tgt = np.ascontiguousarray(tgt_f32, dtype=F32)
+    G = np.asarray(guess_f32, dtype=F32); Tm = np.asarray(transformation_f32, dtype=F32)
+    R = (Tm.astype(np.float64) @ G.astype(np.float64))[:3, :3]             # transform_R formed in double
+    query = _transform_cloud_f32(Tm, _transform_cloud_f32(G, src))
+    _, nn = cKDTree(tgt.astype(np.float64)).query(query.astype(np.float64))
+    d = query - tgt[nn]
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]        # float squared distance
+    ok = d2.astype(np.float64) < corr_dist * corr_dist
+    M = np.tile(np.eye(3), (src.shape[0], 1, 1))
+    si = np.flatnonzero(ok)
+    ti = nn[si]
+    M[si] = np.linalg.inv(R @ cov_s[si] @ R.T + cov_t[ti])
+    return si, ti, M
+
+
+def gicp_cost(src_f32, tgt_f32, base_f32, M, si, ti, x):
+    """(f, g[6]) of OptimizationFunctorWithIndices at state x."""
+    src = np.ascontiguousarray(src_f32, dtype=F32); tgt = np.ascontiguousarray(tgt_f32, dtype=F32)
+    base = np.asarray(base_f32, dtype=F32)
+    T = gicp_apply_state(base, x)
+    pp = _transform_cloud_f32(T, src[si])
+    res = (pp - tgt[ti]).astype(np.float64)                                  # float subtraction, then double
+    temp = np.einsum("mij,mj->mi", M[si], res)
+    m = si.size
+    f = float(np.einsum("mi,mi->", res, temp)) / m
+    g = np.zeros(6)
+    g[:3] = temp.sum(axis=0) * (2.0 / m)
+    pb = _transform_cloud_f32(base, src[si]).astype(np.float64)
+    Rm = (pb.T @ temp) * (2.0 / m)
+    phi, theta, psi = x[3], x[4], x[5]
+    cphi, sphi, cth, sth, cpsi, spsi = math.cos(phi), math.sin(phi), math.cos(theta), math.sin(theta), math.cos(psi), math.sin(psi)
+    # d(Rz(psi) Ry(theta) Rx(phi)) / d angle, written out from the rotation itself (not from the table in the source)
+    def rot(ph, th, ps):
+        cx, sx, cy, sy, cz, sz = math.cos(ph), math.sin(ph), math.cos(th), math.sin(th), math.cos(ps), math.sin(ps)
+        return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]]) @ np.array([[cy, 0, sy], [0, 1.0, 0], [-sy, 0, cy]])
+                @ np.array([[1.0, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    h = 1e-6
+    for k, dv in enumerate(np.eye(3)):
+        dR = (rot(phi + h * dv[0], theta + h * dv[1], psi + h * dv[2])
+              - rot(phi - h * dv[0], theta - h * dv[1], psi - h * dv[2])) / (2 * h)
+        # matricesInnerProd(dR, Rm) = sum_ij dR(j,i) Rm(i,j) = tr(dR Rm) = sum_k temp_k^T dR (base p_k): df/dangle
+        g[3 + k] = float(np.sum(dR * Rm.T))
+    return f, g

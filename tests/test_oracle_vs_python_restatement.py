@@ -206,3 +206,55 @@ def test_ndt_align_with_a_rotated_guess():
     assert p["iterations"] == o["iterations"]
     dt, dr = scenes.se3_error(o["result"], p["result"])
     assert dt < 1e-4 and dr < 1e-4, (dt, dr)
+
+
+# ---------------------------------------------------------------------------------- NdtWithGicp pieces
+def _gicp_scene():
+    src, sub, P = scenes.lidar_pair(pair=1)
+    s = O.approx_voxel_grid(src.astype(np.float32), 0.2)
+    t = O.approx_voxel_grid(sub.astype(np.float32), 0.2)
+    return s[::2].copy(), t[::3].copy(), P
+
+
+def test_stock_pcl_ndt_stage_of_ndt_gicp():
+    # NdtWithGicp's first stage: stock pcl::NormalDistributionsTransform (double point math), transformation
+    # epsilon 0.01 (ndt_gicp.cc:44-47) -> steps clamped to [0.005, 0.1]; then the fitness gate (:84, :92)
+    s, t, _ = _gicp_scene()
+    o = O.ndt_gicp_align(s, t, using_voxel_filter=False, use_ndt=True)
+    p = pyref.ndt_align(s, t, transformation_epsilon=0.01, f64=True)
+    assert p["iterations"] == o["ndt_iterations"]
+    assert abs(p["fitness"] - o["ndt_score"]) <= 1e-5 * o["ndt_score"]
+
+
+def test_gicp_covariances_correspondences_and_mahalanobis():
+    s, t, _ = _gicp_scene()
+    cs, ct = pyref.gicp_covariances(s), pyref.gicp_covariances(t)
+    assert np.allclose(cs, O.gicp_covariances(s), rtol=0, atol=1e-7)        # eigh vs Jacobi on near-planar patches
+    guess = synth.se3_from_rpy_t(0.01, -0.005, 0.02, (0.2, -0.1, 0.03)).astype(np.float32)
+    tr = synth.se3_from_rpy_t(-0.002, 0.003, -0.004, (0.02, 0.01, -0.01)).astype(np.float32)
+    x = np.array([0.03, -0.02, 0.01, 0.004, -0.006, 0.008])
+    o = O.gicp_cost(s, t, guess, tr, x)
+    si, ti, M = pyref.gicp_correspond(s, t, guess, tr, cs, ct)
+    assert np.array_equal(si, o["si"]) and np.array_equal(ti, o["ti"])
+    assert 0.9 * s.shape[0] < si.size <= s.shape[0]
+    scale = np.abs(o["maha"]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(M - o["maha"]) <= 1e-6 * scale)
+    f, g = pyref.gicp_cost(s, t, guess, M, si, ti, x)
+    assert abs(f - o["f"]) <= 1e-6 * abs(o["f"])
+    assert np.all(np.abs(g - o["g"]) <= 1e-5 * np.abs(o["g"]).max())
+
+
+def test_gicp_gradient_is_the_derivative_of_the_cost():
+    # the analytic gradient (translation part 2/m sum M res, rotation part through computeRDerivative's tables)
+    # against central differences of the oracle's own cost; the float pose matrix of applyState limits the step
+    s, t, _ = _gicp_scene()
+    guess = np.eye(4, dtype=np.float32)
+    tr = np.eye(4, dtype=np.float32)
+    x = np.array([0.05, -0.04, 0.02, 0.01, -0.012, 0.015])
+    o = O.gicp_cost(s, t, guess, tr, x)
+    h = 2e-3
+    for k in range(6):
+        xp = x.copy(); xp[k] += h
+        xm = x.copy(); xm[k] -= h
+        fd = (O.gicp_cost(s, t, guess, tr, xp)["f"] - O.gicp_cost(s, t, guess, tr, xm)["f"]) / (2 * h)
+        assert abs(fd - o["g"][k]) <= 2e-3 * max(np.abs(o["g"]).max(), abs(fd)), (k, fd, o["g"][k])
