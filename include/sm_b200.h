@@ -68,11 +68,13 @@ int sm_destroy(sm_handle* h);
  * every <param> for type 5; the engine itself accepts the pclomp setters hard-coded by the
  * reference: resolution (1.0), step_size (0.1), outlier_ratio (0.55),
  * transformation_epsilon (0.1), max_iterations (35).
- * SM_TYPE_ICP_PM is NOT a parity implementation of registrator::IcpUsingPointMatcher: libpointmatcher 1.3.1 is
- * an external float library whose RandomSampling filter draws from std::rand and whose surface-normal filter
- * uses eigenvector normals; neither can be restated or pinned from the reference tree.  Type 1 is a
- * deterministic matcher with the same module chain whose results are checked only
- * against a composition of this repository's own oracle pieces.
+ * SM_TYPE_ICP_PM is NOT a bit-level parity implementation of registrator::IcpUsingPointMatcher: libpointmatcher
+ * 1.3.1 is an external float library whose RandomSampling filter draws from the process-global std::rand stream
+ * (two Align calls on the same clouds give poses ~0.5 mm apart: the reference's result is not a function of its
+ * inputs) and whose surface-normal filter uses eigenvector normals.  Type 1 is a deterministic matcher with the
+ * same module chain: bit-checked against a composition of this repository's oracle
+ * pieces, and shown to lie within the literal chain's own call-to-call variation by a restatement of
+ * libpointmatcher's filters (tests/pyref.py icp_pm_literal, tests/test_oracle_vs_python_restatement.py).
  * SM_TYPE_ICP_PM (stand-in for IcpUsingPointMatcher's default libpointmatcher chain,
  * icp_pointmatcher.cc:166-247; float clouds through the _f32 setters) registers no option in the
  * reference either; the engine accepts the IcpFast names (max_iteration defaults to 150, :214)

@@ -657,3 +657,111 @@ def gicp_cost(src_f32, tgt_f32, base_f32, M, si, ti, x):
         # matricesInnerProd(dR, Rm) = sum_ij dR(j,i) Rm(i,j) = tr(dR Rm) = sum_k temp_k^T dR (base p_k): df/dangle
         g[3 + k] = float(np.sum(dR * Rm.T))
     return f, g
+
+
+# ------------------------------------------------------------------------------------ IcpUsingPointMatcher
+# The reference's type-1 matcher is libpointmatcher 1.3.1 (external, `PointMatcher<float>`) driven by the default
+# chain of registrators/icp_pointmatcher.cc:166-247; its Align() and score pass are :95-148.  libpointmatcher is
+# not in the reference tree; the modules are restated from the published sources of that release:
+#   RandomSamplingDataPointsFilter (prob 0.9):   keep point i iff (float)rand() / (float)RAND_MAX < prob
+#   SamplingSurfaceNormalDataPointsFilter (knn 7, samplingMethod 1): the recursion the reference author ported as
+#       CalculateNormals (cloud_types.cc:73-144), but the normal is the eigenvector of the smallest eigenvalue of
+#       the box's covariance, and the kept point is the box mean
+#   KDTreeMatcher (knn 1, epsilon 3.16), TrimmedDistOutlierFilter (0.7), PointToPlaneErrorMinimizer,
+#   CounterTransformationChecker (150), DifferentialTransformationChecker (0.001 rad, 0.01 m, smoothLength 4):
+#       the chain icp_fast.cc restates in double.
+# `rand()` is glibc's TYPE_3 additive feedback generator (r[i] = r[i-3] + r[i-31], 310 outputs discarded,
+# result >> 1), default seed 1 — a process-global stream, so only the FIRST Align of a process is reproducible.
+class GlibcRand:
+    RAND_MAX = 2147483647
+
+    def __init__(self, seed=1):
+        r = [0] * 34
+        r[0] = seed if seed != 0 else 1
+        for i in range(1, 31):
+            hi, lo = divmod(r[i - 1], 127773)          # 16807 * r mod (2^31 - 1) without overflow, as glibc does
+            word = 16807 * lo - 2836 * hi
+            if word < 0:
+                word += 2147483647
+            r[i] = word
+        for i in range(31, 34):
+            r[i] = r[i - 31]
+        self.r = r
+        for _ in range(310):
+            self._next()
+
+    def _next(self):
+        v = (self.r[-31] + self.r[-3]) & 0xFFFFFFFF
+        self.r.append(v)
+        if len(self.r) > 64:
+            del self.r[:len(self.r) - 34]
+        return v
+
+    def rand(self):
+        return self._next() >> 1
+
+
+def pm_random_sampling_mask(n, prob=0.9, rng=None):
+    rng = rng or GlibcRand(1)
+    p = F32(prob)
+    denom = F32(GlibcRand.RAND_MAX)                      # (float)RAND_MAX = 2147483648.0f
+    return np.array([F32(rng.rand()) / denom < p for _ in range(n)], dtype=bool)
+
+
+def pm_sampling_surface_normal(points_f32, knn=7):
+    """-> (means (M,3) f32, normals (M,3) f32) in ascending order of the box's smallest member index."""
+    pts = np.ascontiguousarray(points_f32, dtype=F32)
+    rows = [tuple(float(x) for x in p) for p in pts]
+    kept = []
+
+    def fuse(idx):
+        d = pts[sorted(idx)].T                                       # 3 x count, float
+        mean = d.sum(axis=1, dtype=F32) / F32(d.shape[1])
+        nn = d - mean[:, None]
+        c = (nn @ nn.T).astype(F32)
+        if np.linalg.matrix_rank(c.astype(np.float64), tol=float(np.finfo(F32).eps) * 3 * np.abs(c).max()) + 1 < 3:
+            return
+        w, v = np.linalg.eigh(c)                                      # EigenSolver on a symmetric matrix: real spectrum
+        kept.append((min(idx), mean, v[:, int(np.argmin(w))]))
+
+    def build(idx, min_values, max_values):
+        if len(idx) <= knn:
+            fuse(idx)
+            return
+        cut_dim = _arg_max([max_values[r] - min_values[r] for r in range(3)])
+        left, right = _median_split(rows, idx, cut_dim)
+        cut_val = rows[right[0]][cut_dim]
+        left_max = list(max_values); left_max[cut_dim] = cut_val
+        right_min = list(min_values); right_min[cut_dim] = cut_val
+        build(left, min_values, left_max)
+        build(right, right_min, max_values)
+
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 10000))
+    build(list(range(len(rows))), [float(x) for x in pts.min(axis=0)], [float(x) for x in pts.max(axis=0)])
+    kept.sort(key=lambda t: t[0])
+    return (np.array([k[1] for k in kept], dtype=F32).reshape(-1, 3),
+            np.array([k[2] for k in kept], dtype=F32).reshape(-1, 3))
+
+
+def icp_pm_literal(source_f32, target_f32, guess=None, rng=None, knn_full=None):
+    """IcpUsingPointMatcher::Align with the literal data filters; the iteration itself in double (the float
+    arithmetic of PointMatcher<float> is NOT reproduced: its effect is at the 1e-5 m level, the filters' at 1e-3 m).
+    knn_full(target, query) -> (ids, d2) is used for the score pass over the unfiltered clouds (defaults to PyNabo)."""
+    src = np.ascontiguousarray(source_f32, dtype=F32)
+    tgt = np.ascontiguousarray(target_f32, dtype=F32)
+    keep = pm_random_sampling_mask(src.shape[0], 0.9, rng)
+    tp, tn = pm_sampling_surface_normal(tgt, 7)
+    out = icp_fast_align(src[keep].astype(np.float64), tp.astype(np.float64), tn.astype(np.float64), guess,
+                         max_iteration=150)
+    out["n_source"], out["n_target"] = int(keep.sum()), int(tp.shape[0])
+    # score pass (icp_pointmatcher.cc:101-148): unfiltered reading moved by the result, matched against the
+    # unfiltered reference, trimmed at 0.7, exp(-mean distance); Align() is false below 0.6
+    moved = _apply_transform(out["result"], src.astype(np.float64))
+    t64 = tgt.astype(np.float64)
+    ids, d2 = (knn_full(t64, moved) if knn_full else PyNabo(t64).knn1(moved, 3.16))
+    limit = _quantile_limit(d2, 0.7)
+    kept = d2[(d2 != INF) & (d2 <= limit)]
+    out["icp_score"] = out["score"]
+    out["score"] = math.exp(-float(np.sqrt(kept).sum()) / kept.size)
+    out["ok"] = out["score"] >= 0.6
+    return out
