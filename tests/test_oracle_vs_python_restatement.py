@@ -305,3 +305,20 @@ def test_type1_stand_in_lies_within_the_reference_chains_own_call_to_call_variat
         gt_t, gt_r = scenes.se3_error(GT, c["result"])
         assert gt_t < 5e-3 and gt_r < 1e-3                           # both are noise-limited at the millimetre level
     assert 4300 < calls[0]["n_source"] < 4700 and calls[0]["n_target"] == st["n_target"] == 1024
+
+
+def test_align_full_size_benchmark_pair_30_iterations():
+    # BASELINE configs[1] (120 000 -> 106 784 points, 30 fixed iterations): everything of IcpFast::Align except the
+    # search restated in numpy; the search (pinned bit-exact above) is borrowed from the oracle to keep this quick
+    src, sub, P = scenes.full_size_pair(0)
+    tp, tn = O.calculate_normals(sub)
+    kn = lambda t, q: O.knn1(t, q, epsilon=3.16)      # noqa: E731
+    tr = []
+    p = pyref.icp_fast_align(src, tp, tn, max_iteration=30, disable_convergence_check=True, knn=kn, trace=tr)
+    o = O.icp_fast_align(src, tp, tn, max_iteration=30, disable_convergence_check=True, trace=True)
+    assert p["iterations"] == o["iterations"] == 30
+    assert [a["kept"] for a in tr] == [b["kept"] for b in o["trace"]] and tr[0]["kept"] == 84_000
+    assert tr[0]["limit"] == o["trace"][0]["limit"]
+    dt, dr = scenes.se3_error(o["result"], p["result"])
+    assert dt < 1e-9 and dr < 1e-9, (dt, dr)
+    assert abs(p["score"] - o["score"]) < 1e-12
