@@ -9,7 +9,9 @@
  * registrators/ (README.md:203-206; builder/data/test/test_cloud_types.cc:158 is an
  * empty stub) and cannot be compiled in this image (Eigen, PCL, libnabo, glog, Boost
  * absent), so this restatement is checked only against analytic known-answer scenes,
- * brute force and scipy's cKDTree (tests/test_oracle_*.py).  The one row that does have reference
+ * brute force and scipy's cKDTree (tests/test_oracle_*.py) and against a second, independent
+ * restatement of the same reference algorithms in Python / numpy (tests/pyref.py,
+ * tests/test_oracle_vs_python_restatement.py).  The one row that does have reference
  * golden values is the voxel filter (pre_processors/test/test_filter_voxel_grid.cc), which the
  * restatement reproduces (tests/test_oracle_voxel_filter.py).
  *
