@@ -461,7 +461,9 @@ __global__ void kd_keys_kernel(const double* __restrict__ coord, int64_t cstride
   if (i >= n) return;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double v = coord[d * cstride + i];
+    // + 0.0 turns -0.0 into +0.0 (every other value is unchanged): the reference's comparator, and the oracle's
+    // total order (coordinate, index), treat the two zeros as EQUAL coordinates, the bit-pattern key would not
+    const double v = dadd(coord[d * cstride + i], 0.0);
     uint64_t key;
     if (keys32) {
       const uint32_t u = __float_as_uint((float)v);

@@ -80,3 +80,22 @@ def test_config2_batched_search_full_size(pair0):
         assert ok
         res.append((r.copy(), m.GetFitnessScore()))
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
+def test_signed_zero_coordinates_split_like_the_oracle():
+    # -0.0 and +0.0 are EQUAL coordinates for the reference's comparator (cloud_types.cc:58-66, libnabo alike) and for
+    # the oracle's total order (coordinate, index); the sort keys of the tree build canonicalise the sign of zero, so
+    # a median that falls inside a group of zeros splits it by index on both sides
+    rng = np.random.default_rng(21)
+    n = 6000
+    x = rng.uniform(-1.0, 1.0, size=n)
+    zero = rng.random(n) < 0.5
+    x[zero] = np.where(rng.random(int(zero.sum())) < 0.5, -0.0, 0.0)
+    T = np.stack([x, rng.normal(size=n) * 0.05, rng.normal(size=n) * 0.05], axis=1)
+    assert np.signbit(T[:, 0][T[:, 0] == 0.0]).any() and (~np.signbit(T[:, 0][T[:, 0] == 0.0])).any()
+    Q = np.stack([rng.uniform(-0.2, 0.2, size=3000), rng.normal(size=3000) * 0.05, rng.normal(size=3000) * 0.05], axis=1)
+    for eps in (0.0, 3.16):
+        ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
+        for qpc in (0, 1024):
+            ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, queries_per_cta=qpc)
+            assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
