@@ -1,5 +1,5 @@
 /* sm_b200_debug.h — TEST HOOKS of libsm_b200.so.  Not part of the drop-in boundary (include/sm_b200.h):
- * nothing in the reference binds these.  They let tests/ drive two pieces of product code that have no
+ * nothing in the reference binds these.  They let tests/ drive three pieces of product code that have no
  * entry point of their own against INDEPENDENT implementations (numpy / scipy), so that a transcription
  * error shared by the product and the oracle cannot pass unnoticed:
  *   - the 6x6 solver of the ICP iteration (csrc/linalg_dev.cuh: pivoted-QR rank test, LLT, rank-reduced
@@ -7,6 +7,8 @@
  *     run on the device exactly as icp_finish_kernel calls it;
  *   - the BFGS minimiser of the GICP stage (csrc/gicp_host.h: PCL's port of GSL vector_bfgs2 with the
  *     Fletcher line search, parameters of gicp_omp_impl.hpp:218-224), run on a caller-supplied function.
+ *   - the host-side scalar pieces of the NDT Newton loop (csrc/ndt_host.h: 6x6 Jacobi SVD solve, pose <-> 6-vector
+ *     with Eigen's eulerAngles(0,1,2), Gauss constants), run on the host without a GPU.
  * And one launch shape that is otherwise only reachable through whole alignments:
  *   - sm_knn1 with the scheduling the ICP iteration uses when many alignments are in flight
  *     (queries_per_cta > 256: lockstep root visits, then the lanes of a warp pull parked searches), so the
@@ -36,6 +38,17 @@ int sm_debug_bfgs_minimize(sm_debug_fdf fn, void* user, double* x_6_inout, doubl
 int sm_debug_knn1_batched(int device, const double* target_3xn, int64_t n_target, const double* query_3xn,
                           int64_t n_query, double epsilon, int bucket_size, int32_t queries_per_cta,
                           int32_t* ids, double* dists2);
+
+/* The host-side scalar pieces of registrator::Ndt's Newton loop (csrc/ndt_host.h), runnable without a GPU, so that
+ * product code is compared with numpy directly (tests/test_independent_checks.py):
+ *   op 0: JacobiSVD(H).solve(b), ndt_omp_impl.hpp:127-129     in = H[36] row-major, b[6]       out = x[6]
+ *   op 1: Translation * AngleAxis(X) * AngleAxis(Y) * AngleAxis(Z) in float, :146-149 / :797-800
+ *                                                              in = p[6]                        out = T[16] col-major
+ *   op 2: translation + rotation().eulerAngles(0, 1, 2) in float, :103-111
+ *                                                              in = T[16] col-major             out = p[6]
+ *   op 3: Gauss constants d1, d2, :86-93                       in = {outlier_ratio, resolution} out = {d1, d2}
+ * Returns 0, or SM_ERR_BAD_ARGUMENT for an unknown op / null pointer. */
+int sm_debug_ndt_host(int32_t op, const double* in, double* out);
 
 #ifdef __cplusplus
 }

@@ -1316,6 +1316,34 @@ int sm_debug_solve6(int device, const double* A, const double* b, double* x, int
   return rc;
 }
 
+// test hook (include/sm_b200_debug.h): the scalar host pieces of the NDT Newton loop, no GPU involved
+int sm_debug_ndt_host(int32_t op, const double* in, double* out) {
+  if (!in || !out) return SM_ERR_BAD_ARGUMENT;
+  switch (op) {
+    case 0: ndt::svd_solve6(in, in + 36, out); return SM_OK;
+    case 1: {
+      float T[16];
+      ndt::transform_from_p(in, T);
+      for (int i = 0; i < 16; ++i) out[i] = (double)T[i];
+      return SM_OK;
+    }
+    case 2: {
+      float T[16];
+      for (int i = 0; i < 16; ++i) T[i] = (float)in[i];
+      ndt::p_from_transform(T, out);
+      return SM_OK;
+    }
+    case 3: {
+      ndt::Options o;
+      o.outlier_ratio = in[0];
+      o.resolution = (float)in[1];
+      ndt::gauss_constants(o, &out[0], &out[1]);
+      return SM_OK;
+    }
+    default: return SM_ERR_BAD_ARGUMENT;
+  }
+}
+
 int sm_debug_bfgs_minimize(sm_debug_fdf fn, void* user, double* x, double grad_tol, int32_t max_iterations,
                            int32_t* iterations, int32_t* evaluations, int32_t* status) {
   if (!fn || !x || !iterations || !evaluations || !status) return SM_ERR_BAD_ARGUMENT;

@@ -183,3 +183,59 @@ def test_bfgs_with_the_gicp_stopping_rule_stops_early_like_the_reference():
     x, it, ev, st = _run_product_bfgs(fun, np.zeros(6), grad_tol=1e-2, max_iter=20)
     assert st == 0 and it <= 20
     assert np.linalg.norm(fun(x)[1]) < 1e-2
+
+
+# ---------------------------------------------------------------------------------- NDT host pieces (no GPU)
+def _ndt_host(op, vec, nout):
+    lib = _lib.lib()
+    a = np.ascontiguousarray(np.asarray(vec, dtype=np.float64))
+    out = np.zeros(nout)
+    assert lib.sm_debug_ndt_host(op, a.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_ndt_newton_step_svd_solve_against_numpy(seed):
+    # JacobiSVD(hessian).solve(-gradient), ndt_omp_impl.hpp:127-129: indefinite symmetric Hessians are the normal case
+    rng = np.random.default_rng(seed)
+    M = rng.normal(size=(6, 6)); H = (M + M.T) * 50.0
+    g = rng.normal(size=6) * 10.0
+    x = _ndt_host(0, np.concatenate([H.ravel(), -g]), 6)
+    assert np.allclose(x, np.linalg.solve(H, -g), rtol=1e-9, atol=1e-12)
+    # rank-deficient: the minimum-norm least-squares solution, like Eigen's JacobiSVD::solve
+    B = rng.normal(size=(4, 6)); Hs = B.T @ B
+    xs = _ndt_host(0, np.concatenate([Hs.ravel(), g]), 6)
+    assert np.allclose(xs, np.linalg.lstsq(Hs, g, rcond=None)[0], rtol=1e-7, atol=1e-10)
+
+
+def test_ndt_pose_vector_to_matrix_and_back_against_scipy():
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        p = np.concatenate([rng.normal(size=3) * 3.0, rng.uniform(-0.6, 0.6, size=3)])
+        T = _ndt_host(1, p, 16).reshape(4, 4).T
+        R = Rotation.from_euler("XYZ", p[3:]).as_matrix()          # intrinsic x-y'-z'' = Rx * Ry * Rz
+        assert np.allclose(T[:3, :3], R, atol=3e-7) and np.allclose(T[:3, 3], p[:3].astype(np.float32), atol=0)
+        assert np.array_equal(T[3], [0, 0, 0, 1])
+        # eulerAngles(0, 1, 2) inverts it; Eigen 3.3 keeps the FIRST angle in [0, pi], so a negative roll comes back
+        # as the equivalent triple (roll + pi, pi - pitch, yaw + pi): compare as rotations, and literally when roll >= 0
+        q = _ndt_host(2, T.T.ravel(), 6)
+        assert np.allclose(q[:3], T[:3, 3], atol=0)
+        assert np.allclose(Rotation.from_euler("XYZ", q[3:]).as_matrix(), R, atol=1e-6)
+        assert -1e-7 <= q[3] <= np.pi + 1e-6
+        if p[3] > 1e-3:
+            assert np.allclose(q[3:], p[3:], atol=5e-6)
+
+
+def test_ndt_euler_angles_of_a_small_negative_roll_take_the_other_branch():
+    # the well-known consequence of Eigen 3.3's range convention, which the reference inherits (ndt_omp_impl.hpp:109)
+    from scipy.spatial.transform import Rotation
+    T = np.eye(4); T[:3, :3] = Rotation.from_euler("XYZ", [-0.01, 0.02, 0.03]).as_matrix()
+    q = _ndt_host(2, T.T.ravel(), 6)
+    assert abs(q[3] - (np.pi - 0.01)) < 1e-5 and abs(abs(q[4]) - (np.pi - 0.02)) < 1e-5
+    assert np.allclose(Rotation.from_euler("XYZ", q[3:]).as_matrix(), T[:3, :3], atol=1e-6)
+
+
+def test_ndt_gauss_constants_known_answer():
+    d = _ndt_host(3, [0.55, 1.0], 2)
+    assert abs(d[0] + 2.217225) < 1e-6 and abs(d[1] - 0.433123) < 1e-6
