@@ -25,6 +25,9 @@ extern "C" {
 /* A: row-major 6x6 (symmetric in the ICP use), b: 6.  path: 0 LLT, 1 rank-reduced min-norm, 2 SVD. */
 int sm_debug_solve6(int device, const double* A_36, const double* b_6, double* x_6, int32_t* path);
 
+/* the same routine compiled for the host (no GPU needed): the source both builds share is csrc/linalg_dev.cuh */
+int sm_debug_solve6_host(const double* A_36, const double* b_6, double* x_6, int32_t* path);
+
 /* f and/or g may be NULL (value-only / gradient-only evaluations of the line search); return < 0 to abort. */
 typedef int (*sm_debug_fdf)(const double* x_6, double* f, double* g_6, void* user);
 /* Runs the GICP inner loop (gicp_omp_impl.hpp:225-240): set, then iterate + test_gradient(grad_tol) until

@@ -22,7 +22,7 @@ struct PivQR {
   int nonzero_pivots;
   double maxpivot;
 
-  __device__ void compute(const double* A) {
+  __host__ __device__ void compute(const double* A) {
     const double precision = kEps * (double)N;
     for (int i = 0; i < N * N; ++i) { R[i] = A[i]; Qt[i] = 0.0; }
     for (int i = 0; i < N; ++i) { Qt[i * N + i] = 1.0; perm[i] = i; }
@@ -80,7 +80,7 @@ struct PivQR {
       }
     }
   }
-  __device__ int rank() const {
+  __host__ __device__ int rank() const {
     const double thr = fabs(maxpivot) * (kEps * (double)N);
     int rk = 0;
     for (int i = 0; i < nonzero_pivots; ++i) rk += (fabs(R[i * N + i]) > thr) ? 1 : 0;
@@ -89,7 +89,7 @@ struct PivQR {
 };
 
 // Cholesky solve, n <= 6
-__device__ inline void llt_solve(const double* A, const double* b, double* x, int n) {
+__host__ __device__ inline void llt_solve(const double* A, const double* b, double* x, int n) {
   double L[36];
   for (int i = 0; i < n * n; ++i) L[i] = 0.0;
   for (int k = 0; k < n; ++k) {
@@ -117,7 +117,7 @@ __device__ inline void llt_solve(const double* A, const double* b, double* x, in
 }
 
 // symmetric Jacobi eigen-decomposition, n <= 6 (V columns = eigenvectors)
-__device__ inline void jacobi_eig_sym(const double* Ain, int n, double* w, double* V) {
+__host__ __device__ inline void jacobi_eig_sym(const double* Ain, int n, double* w, double* V) {
   double A[36];
   for (int i = 0; i < n * n; ++i) { A[i] = Ain[i]; V[i] = 0.0; }
   for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
@@ -150,7 +150,7 @@ __device__ inline void jacobi_eig_sym(const double* Ain, int n, double* w, doubl
   for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
 
-__device__ inline void sym_svd_solve(const double* A, const double* b, double* x, int n) {
+__host__ __device__ inline void sym_svd_solve(const double* A, const double* b, double* x, int n) {
   double w[6], V[36];
   jacobi_eig_sym(A, n, w, V);
   double svmax = 0.0;
@@ -167,7 +167,7 @@ __device__ inline void sym_svd_solve(const double* A, const double* b, double* x
 }
 
 // icp_fast.cc:204-254.  path: 0 LLT, 1 rank-reduced min-norm, 2 SVD fallback.
-__device__ inline int solve_possibly_underdetermined(const double* A, const double* b, double* x) {
+__host__ __device__ inline int solve_possibly_underdetermined(const double* A, const double* b, double* x) {
   PivQR<6> qr;
   qr.compute(A);
   const int rank = qr.rank();
@@ -208,7 +208,7 @@ __device__ inline int solve_possibly_underdetermined(const double* A, const doub
 }
 
 // 3x3 inverse via partial-pivot LU (dynamic MatrixXd::inverse path, cloud_types.cc:93)
-__device__ inline void lu_inverse3(const double* M, double* inv) {
+__host__ __device__ inline void lu_inverse3(const double* M, double* inv) {
   double lu[9];
   int piv[3] = {0, 1, 2};
   for (int i = 0; i < 9; ++i) lu[i] = M[i];
@@ -242,7 +242,7 @@ __device__ inline void lu_inverse3(const double* M, double* inv) {
   }
 }
 
-__device__ inline void angle_axis_to_rotation(double angle, const double* axis, double* R) {
+__host__ __device__ inline void angle_axis_to_rotation(double angle, const double* axis, double* R) {
   double s, c;
   sincos(angle, &s, &c);
   const double sa0 = s * axis[0], sa1 = s * axis[1], sa2 = s * axis[2];
@@ -254,7 +254,7 @@ __device__ inline void angle_axis_to_rotation(double angle, const double* axis, 
   R[0] = ca0 * axis[0] + c; R[4] = ca1 * axis[1] + c; R[8] = ca2 * axis[2] + c;
 }
 
-__device__ inline void rotation_to_quaternion(const double* m, double* q) {
+__host__ __device__ inline void rotation_to_quaternion(const double* m, double* q) {
   double t = m[0] + m[4] + m[8];
   if (t > 0.0) {
     t = sqrt(t + 1.0);
@@ -273,7 +273,7 @@ __device__ inline void rotation_to_quaternion(const double* m, double* q) {
   }
 }
 
-__device__ inline double quaternion_angular_distance(const double* a, const double* b) {
+__host__ __device__ inline double quaternion_angular_distance(const double* a, const double* b) {
   const double bw = b[0], bx = -b[1], by = -b[2], bz = -b[3];
   const double w = a[0] * bw - a[1] * bx - a[2] * by - a[3] * bz;
   const double x = a[0] * bx + a[1] * bw + a[2] * bz - a[3] * by;
@@ -283,7 +283,7 @@ __device__ inline double quaternion_angular_distance(const double* a, const doub
 }
 
 // column-major 4x4 product, k-order accumulation
-__device__ inline void mul4(const double* A, const double* B, double* C) {
+__host__ __device__ inline void mul4(const double* A, const double* B, double* C) {
   double out[16];
   for (int j = 0; j < 4; ++j)
     for (int i = 0; i < 4; ++i) {

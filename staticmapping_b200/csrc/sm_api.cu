@@ -1316,6 +1316,14 @@ int sm_debug_solve6(int device, const double* A, const double* b, double* x, int
   return rc;
 }
 
+// test hook: csrc/linalg_dev.cuh's solver (the code icp_finish_kernel runs when its Cholesky certificate is not
+// conclusive) compiled for the HOST, so the product's transcription is checked against numpy without a GPU
+int sm_debug_solve6_host(const double* A, const double* b, double* x, int32_t* path) {
+  if (!A || !b || !x || !path) return SM_ERR_BAD_ARGUMENT;
+  *path = la::solve_possibly_underdetermined(A, b, x);
+  return SM_OK;
+}
+
 // test hook (include/sm_b200_debug.h): the scalar host pieces of the NDT Newton loop, no GPU involved
 int sm_debug_ndt_host(int32_t op, const double* in, double* out) {
   if (!in || !out) return SM_ERR_BAD_ARGUMENT;

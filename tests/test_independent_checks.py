@@ -50,6 +50,31 @@ def test_oracle_solve6_against_numpy(rank, seed):
     _check_solution(A, b, x, path, rank)
 
 
+@pytest.mark.parametrize("rank", [6, 5, 4, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_product_solve6_compiled_for_the_host_against_numpy(rank, seed):
+    # csrc/linalg_dev.cuh is __host__ __device__: the very source icp_finish_kernel runs, without a GPU
+    A, b = _normal_matrix(rank, 10 * rank + seed, scale=[1.0, 30.0, 0.05][seed])
+    lib = _lib.lib()
+    Ac = np.ascontiguousarray(A); bc = np.ascontiguousarray(b)
+    x = np.zeros(6); path = C.c_int32(-1)
+    assert lib.sm_debug_solve6_host(Ac.ctypes.data, bc.ctypes.data, x.ctypes.data, C.byref(path)) == 0
+    _check_solution(A, b, x, path.value, rank)
+    xo, po = O.solve6(A, b)
+    assert po == path.value and np.allclose(x, xo, rtol=1e-9, atol=1e-12)
+
+
+def test_product_solve6_host_nan_input_gives_zero_like_the_oracle():
+    A, b = _normal_matrix(6, 3)
+    A[2, 3] = A[3, 2] = np.nan
+    lib = _lib.lib()
+    x = np.ones(6); path = C.c_int32(-1)
+    assert lib.sm_debug_solve6_host(np.ascontiguousarray(A).ctypes.data, np.ascontiguousarray(b).ctypes.data,
+                                    x.ctypes.data, C.byref(path)) == 0
+    xo, po = O.solve6(A, b)
+    assert np.array_equal(np.nan_to_num(x, nan=-1.0), np.nan_to_num(xo, nan=-1.0)) and po == path.value
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("rank", [6, 5, 4, 3])
 @pytest.mark.parametrize("seed", [0, 1, 2])
