@@ -53,6 +53,13 @@ int sm_debug_knn1_batched(int device, const double* target_3xn, int64_t n_target
  * Returns 0, or SM_ERR_BAD_ARGUMENT for an unknown op / null pointer. */
 int sm_debug_ndt_host(int32_t op, const double* in, double* out);
 
+/* One (point, voxel) term of computeDerivatives (ndt_omp_impl.hpp:397-438 + :483-535; f64_math = 1: the stock PCL
+ * double form NdtWithGicp uses): csrc/ndt.cu's update_derivatives compiled for the host, evaluation tables built by
+ * csrc/ndt_host.h for the pose vector p.  out43 = {score increment, gradient term[6], Hessian term[36] row-major}. */
+int sm_debug_ndt_term(const double* p_6, double outlier_ratio, float resolution, int32_t f64_math,
+                      const float* x_orig_3, const float* x_trans_3, const double* voxel_mean_3,
+                      const double* voxel_icov_9, double* out43);
+
 #ifdef __cplusplus
 }
 #endif

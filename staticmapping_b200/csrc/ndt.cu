@@ -328,7 +328,7 @@ __device__ __forceinline__ float dist2f(float qx, float qy, float qz, const floa
 
 // one (point, voxel) term: computePointDerivatives (float overload, ndt_omp_impl.hpp:397-438)
 // + updateDerivatives (:483-535); operation order as written out in oracle/ndt_math.h
-__device__ __forceinline__ double update_derivatives(const NdtEvalParams& P, const float* x_orig,
+__host__ __device__ __forceinline__ double update_derivatives(const NdtEvalParams& P, const float* x_orig,
                                                      const float* x_trans_f, const NdtLeaf& leaf,
                                                      double* grad_pt, double* hess_pt) {
   float xj[8], xh[15];
@@ -389,7 +389,7 @@ __device__ __forceinline__ double update_derivatives(const NdtEvalParams& P, con
 // the same term with double Eigen matrices: stock pcl::NormalDistributionsTransform
 // (computePointDerivatives / updateDerivatives of PCL's ndt.hpp; the in-tree double overloads
 // ndt_omp_impl.hpp:441-481 and updateHessian :596-629 are that code).  Used by NdtWithGicp.
-__device__ __forceinline__ double update_derivatives_f64(const NdtEvalParams& P, const float* x_orig,
+__host__ __device__ __forceinline__ double update_derivatives_f64(const NdtEvalParams& P, const float* x_orig,
                                                          const float* x_trans_f, const NdtLeaf& leaf,
                                                          double* grad_pt, double* hess_pt) {
   const double x[3] = {(double)x_orig[0], (double)x_orig[1], (double)x_orig[2]};
@@ -569,6 +569,19 @@ ndt_fitness_kernel(const float* __restrict__ src, int n, NdtEvalParams P, const 
 }
 
 }  // namespace
+
+// Host build of the per-(point, voxel) term (test hook sm_debug_ndt_term): out[0] = score increment,
+// out[1..6] = gradient term, out[7..42] = Hessian term (row-major) of ONE neighbour voxel.
+void ndt_debug_term_host(const NdtEvalParams& P, const float* x_orig, const float* x_trans, const double* mean,
+                         const double* icov, double* out43) {
+  NdtLeaf leaf;
+  for (int d = 0; d < 3; ++d) { leaf.mean[d] = mean[d]; leaf.centroid[d] = (float)mean[d]; }
+  for (int q = 0; q < 9; ++q) leaf.icov[q] = icov[q];
+  leaf.nr_points = 6; leaf.searchable = 1; leaf.pad = 0;
+  for (int q = 0; q < 43; ++q) out43[q] = 0.0;
+  out43[0] = P.f64_math ? update_derivatives_f64(P, x_orig, x_trans, leaf, out43 + 1, out43 + 7)
+                        : update_derivatives(P, x_orig, x_trans, leaf, out43 + 1, out43 + 7);
+}
 
 int ndt_blocks(int n) { return ceil_div(n, kNdtThreads); }
 

@@ -1324,6 +1324,26 @@ int sm_debug_solve6_host(const double* A, const double* b, double* x, int32_t* p
   return SM_OK;
 }
 
+// test hook: the per-(point, voxel) derivative term of ndt.cu (update_derivatives / update_derivatives_f64, the
+// functions ndt_derivatives_kernel calls) compiled for the HOST, with the evaluation parameters built by the
+// product's own host code (ndt_host.h) for pose vector p — no GPU involved
+int sm_debug_ndt_term(const double* p6, double outlier_ratio, float resolution, int32_t f64_math, const float* x_orig,
+                      const float* x_trans, const double* mean3, const double* icov9, double* out43) {
+  if (!p6 || !x_orig || !x_trans || !mean3 || !icov9 || !out43) return SM_ERR_BAD_ARGUMENT;
+  ndt::Options o;
+  o.outlier_ratio = outlier_ratio;
+  o.resolution = resolution;
+  NdtEvalParams P;
+  memset(&P, 0, sizeof(P));
+  ndt::gauss_constants(o, &P.gauss_d1, &P.gauss_d2);
+  ndt::angle_tables(p6, &P);
+  ndt::transform_from_p(p6, P.T);
+  P.radius = resolution;
+  P.f64_math = f64_math ? 1 : 0;
+  ndt_debug_term_host(P, x_orig, x_trans, mean3, icov9, out43);
+  return SM_OK;
+}
+
 // test hook (include/sm_b200_debug.h): the scalar host pieces of the NDT Newton loop, no GPU involved
 int sm_debug_ndt_host(int32_t op, const double* in, double* out) {
   if (!in || !out) return SM_ERR_BAD_ARGUMENT;

@@ -264,3 +264,38 @@ def test_ndt_euler_angles_of_a_small_negative_roll_take_the_other_branch():
 def test_ndt_gauss_constants_known_answer():
     d = _ndt_host(3, [0.55, 1.0], 2)
     assert abs(d[0] + 2.217225) < 1e-6 and abs(d[1] - 0.433123) < 1e-6
+
+
+@pytest.mark.parametrize("f64", [0, 1])
+def test_ndt_derivative_terms_of_the_product_against_the_numpy_restatement(f64):
+    """csrc/ndt.cu's update_derivatives / update_derivatives_f64 — the functions ndt_derivatives_kernel calls —
+    compiled for the host and summed over the (point, voxel) pairs of a lidar scene, against tests/pyref.py's
+    independent numpy statement of computeDerivatives (and through it against the oracle): product code, no GPU."""
+    import pyref
+    import scenes
+    src, sub, _ = scenes.lidar_pair(pair=2)
+    s32 = src[::4].astype(np.float32); t32 = sub.astype(np.float32)
+    p = np.array([0.2, -0.15, 0.05, 0.01, -0.008, 0.03])
+    grid = pyref.NdtGrid(t32)
+    T = _ndt_host(1, p, 16).reshape(4, 4).T.astype(np.float32)            # the product's own pose matrix
+    assert np.allclose(T, pyref._ndt_pose_matrix_f32(p), rtol=0, atol=1.2e-7)   # AngleAxis products vs numpy: 1 float ulp
+    trans = pyref._transform_cloud_f32(T, s32)
+    pi, li = grid.radius_search(trans)
+    lib = _lib.lib()
+    acc = np.zeros(43)
+    out = np.zeros(43)
+    pp = np.ascontiguousarray(p)
+    for a, b in zip(pi, li):
+        xo = np.ascontiguousarray(s32[a]); xt = np.ascontiguousarray(trans[a])
+        mean = np.ascontiguousarray(grid.mean[b]); icov = np.ascontiguousarray(grid.icov[b].ravel())
+        assert lib.sm_debug_ndt_term(pp.ctypes.data, 0.55, 1.0, f64, xo.ctypes.data, xt.ctypes.data,
+                                     mean.ctypes.data, icov.ctypes.data, out.ctypes.data) == 0
+        acc += out
+    score, g, H, _ = pyref.ndt_derivatives(grid, s32, trans, p, f64=bool(f64))
+    tol = 1e-9 if f64 else 3e-5
+    assert abs(acc[0] - score) <= tol * abs(score)
+    assert np.all(np.abs(acc[1:7] - g) <= tol * np.abs(g).max())
+    assert np.all(np.abs(acc[7:].reshape(6, 6) - H) <= 2 * tol * np.abs(H).max())
+    if not f64:
+        so, go, Ho, _ = O.ndt_derivatives(s32, t32, p)
+        assert abs(acc[0] - so) <= 1e-6 * abs(so) and np.all(np.abs(acc[1:7] - go) <= 1e-6 * np.abs(go).max())
