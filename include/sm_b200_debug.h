@@ -53,6 +53,16 @@ int sm_debug_knn1_batched(int device, const double* target_3xn, int64_t n_target
  * Returns 0, or SM_ERR_BAD_ARGUMENT for an unknown op / null pointer. */
 int sm_debug_ndt_host(int32_t op, const double* in, double* out);
 
+/* The ICP iteration's per-match arithmetic and pose-update helpers compiled for the host (csrc/icp_dev.cuh,
+ * csrc/linalg_dev.cuh; ErrorElements + ComputePointToPlane, icp_fast.cc:268-313, CheckConvergence :377-405):
+ *   op 0: in = n records {p[3], q[3], normal[3], d2}  out = 29 sums: upper triangle of A = sum F F^T (21, row by row),
+ *         sum F (n . (p - q)) (6), sum sqrt(d2), count;  F = [p x normal; normal]
+ *   op 1: in = {angle, axis[3]}        out = R[9] row-major   (Eigen::AngleAxis::toRotationMatrix)
+ *   op 2: in = R[9] row-major          out = {w, x, y, z}     (Eigen::Quaterniond(Matrix3d))
+ *   op 3: in = two quaternions {w,x,y,z}  out[0] = angularDistance
+ *   op 4: in = two column-major 4x4    out = their product */
+int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out);
+
 /* One (point, voxel) term of computeDerivatives (ndt_omp_impl.hpp:397-438 + :483-535; f64_math = 1: the stock PCL
  * double form NdtWithGicp uses): csrc/ndt.cu's update_derivatives compiled for the host, evaluation tables built by
  * csrc/ndt_host.h for the pose vector p.  out43 = {score increment, gradient term[6], Hessian term[36] row-major}. */

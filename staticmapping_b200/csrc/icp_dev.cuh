@@ -264,7 +264,7 @@ __device__ __forceinline__ BinSel select_bin(const uint32_t* __restrict__ ghist,
 
 // contribution of one match to the normal equations (icp_fast.cc:268-302), in two halves so
 // that phase B can park the terms of a quantile-bin member for phase C
-__device__ __forceinline__ void match_terms(double px, double py, double pz, const BucketPoint& q,
+__host__ __device__ __forceinline__ void match_terms(double px, double py, double pz, const BucketPoint& q,
                                             const BucketNormal& n, double* F, double& dot) {
   F[0] = py * n.z - pz * n.y;
   F[1] = pz * n.x - px * n.z;
@@ -272,7 +272,7 @@ __device__ __forceinline__ void match_terms(double px, double py, double pz, con
   F[3] = n.x; F[4] = n.y; F[5] = n.z;
   dot = (px - q.x) * n.x + (py - q.y) * n.y + (pz - q.z) * n.z;
 }
-__device__ __forceinline__ void add_terms(double* acc, const double* F, double dot, double d2) {
+__host__ __device__ __forceinline__ void add_terms(double* acc, const double* F, double dot, double d2) {
   int k = 0;
 #pragma unroll
   for (int r = 0; r < 6; ++r)

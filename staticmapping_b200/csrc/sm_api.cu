@@ -1324,6 +1324,32 @@ int sm_debug_solve6_host(const double* A, const double* b, double* x, int32_t* p
   return SM_OK;
 }
 
+// test hook: the per-match contribution to the point-to-plane normal equations (icp_dev.cuh match_terms /
+// add_terms, the functions icp_accum_kernel and icp_finish_kernel call) and the pose-update helpers of
+// linalg_dev.cuh, compiled for the HOST
+int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out) {
+  if (!in || !out || n < 0) return SM_ERR_BAD_ARGUMENT;
+  switch (op) {
+    case 0: {   // in = n records {p[3], q[3], normal[3], d2}; out = the 29 sums, matches added in order
+      for (int k = 0; k < dev::kNumSums; ++k) out[k] = 0.0;
+      for (int64_t i = 0; i < n; ++i) {
+        const double* r = in + 10 * i;
+        BucketPoint q; q.x = r[3]; q.y = r[4]; q.z = r[5];
+        BucketNormal nn; nn.x = r[6]; nn.y = r[7]; nn.z = r[8];
+        double F[6], dot;
+        dev::match_terms(r[0], r[1], r[2], q, nn, F, dot);
+        dev::add_terms(out, F, dot, r[9]);
+      }
+      return SM_OK;
+    }
+    case 1: la::angle_axis_to_rotation(in[0], in + 1, out); return SM_OK;          // out = R[9] row-major
+    case 2: la::rotation_to_quaternion(in, out); return SM_OK;                     // in = R[9], out = {w, x, y, z}
+    case 3: out[0] = la::quaternion_angular_distance(in, in + 4); return SM_OK;    // in = two quaternions
+    case 4: la::mul4(in, in + 16, out); return SM_OK;                              // column-major 4x4 product
+    default: return SM_ERR_BAD_ARGUMENT;
+  }
+}
+
 // test hook: the per-(point, voxel) derivative term of ndt.cu (update_derivatives / update_derivatives_f64, the
 // functions ndt_derivatives_kernel calls) compiled for the HOST, with the evaluation parameters built by the
 // product's own host code (ndt_host.h) for pose vector p — no GPU involved

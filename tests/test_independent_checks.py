@@ -299,3 +299,64 @@ def test_ndt_derivative_terms_of_the_product_against_the_numpy_restatement(f64):
     if not f64:
         so, go, Ho, _ = O.ndt_derivatives(s32, t32, p)
         assert abs(acc[0] - so) <= 1e-6 * abs(so) and np.all(np.abs(acc[1:7] - go) <= 1e-6 * np.abs(go).max())
+
+
+# ---------------------------------------------------------------------------------- ICP per-match math (no GPU)
+def _icp_host(op, vec, n, nout):
+    lib = _lib.lib()
+    a = np.ascontiguousarray(np.asarray(vec, dtype=np.float64))
+    out = np.zeros(nout)
+    assert lib.sm_debug_icp_host(op, a.ctypes.data, n, out.ctypes.data) == 0
+    return out
+
+
+def test_icp_normal_equation_terms_of_the_product_against_numpy():
+    """icp_dev.cuh match_terms / add_terms (what icp_accum_kernel and icp_finish_kernel add per kept match) on the host:
+    A = sum F F^T with F = [p x n; n], sum F (n . (p - q)), sum sqrt(d2), count (icp_fast.cc:268-302, :518-521)."""
+    import scenes
+    src, tgt, _ = scenes.corner_pair()
+    tp, tn = O.calculate_normals(tgt)
+    mean = tp.sum(axis=0) / tp.shape[0]                      # the iteration runs in the target-mean frame (:457-471)
+    tc, sc = tp - mean, src - mean
+    ids, d2 = O.knn1(tc, sc, epsilon=3.16)
+    keep = d2 <= np.partition(d2, O.quantile_index(d2.size))[O.quantile_index(d2.size)]
+    P, Q, N, D = sc[keep], tc[ids[keep]], tn[ids[keep]], d2[keep]
+    rec = np.concatenate([P, Q, N, D[:, None]], axis=1)
+    s = _icp_host(0, rec.ravel(), rec.shape[0], 29)
+    F = np.concatenate([np.cross(P, N), N], axis=1)
+    A = F.T @ F
+    iu = np.triu_indices(6)
+    assert np.allclose(s[:21], A[iu], rtol=1e-12, atol=1e-12 * np.abs(A).max())
+    assert np.allclose(s[21:27], F.T @ np.einsum("ij,ij->i", P - Q, N), rtol=1e-11, atol=1e-12 * np.abs(A).max())
+    assert abs(s[27] - np.sqrt(D).sum()) <= 1e-12 * np.sqrt(D).sum() and s[28] == rec.shape[0]
+    # and the solve of those sums is the oracle's first iteration: x = A^-1 (-b) -> T_iter of the trace
+    Afull = np.zeros((6, 6)); Afull[iu] = s[:21]; Afull = Afull + Afull.T - np.diag(np.diag(Afull))
+    x = np.linalg.solve(Afull, -s[21:27])
+    o = O.icp_fast_align(src, tp, tn, max_iteration=1, trace=True)
+    assert np.allclose(o["trace"][0]["T_iter"][:3, 3], x[3:], rtol=0, atol=1e-12)
+
+
+def test_icp_pose_update_helpers_of_the_product_against_scipy():
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    for _ in range(100):
+        w = rng.normal(size=3) * rng.choice([1e-4, 0.05, 2.0])
+        ang = np.linalg.norm(w)
+        R = _icp_host(1, np.concatenate([[ang], w / ang]), 0, 9).reshape(3, 3)        # AngleAxis(|w|, w / |w|)
+        Rs = Rotation.from_rotvec(w)
+        assert np.allclose(R, Rs.as_matrix(), atol=1e-14)
+        q = _icp_host(2, R.ravel(), 0, 4)                                              # Quaterniond(Matrix3d): {w, x, y, z}
+        qs = Rs.as_quat()[[3, 0, 1, 2]]
+        assert np.allclose(q, qs if q @ qs > 0 else -qs, atol=1e-13) and abs(np.linalg.norm(q) - 1) < 1e-14
+        R2 = Rotation.from_rotvec(rng.normal(size=3) * 0.3)
+        q2 = _icp_host(2, R2.as_matrix().ravel(), 0, 4)
+        d = _icp_host(3, np.concatenate([q, q2]), 0, 1)[0]
+        assert abs(d - (Rs.inv() * R2).magnitude()) < 1e-12                            # angularDistance
+    A, B = rng.normal(size=(4, 4)), rng.normal(size=(4, 4))
+    C_ = _icp_host(4, np.concatenate([A.T.ravel(), B.T.ravel()]), 0, 16).reshape(4, 4).T
+    assert np.allclose(C_, A @ B, atol=1e-14)
+    # trace <= 0 branches of the matrix -> quaternion conversion (rotations by ~pi about each axis)
+    for axis in np.eye(3):
+        Rm = Rotation.from_rotvec(axis * 3.1).as_matrix()
+        q = _icp_host(2, Rm.ravel(), 0, 4)
+        assert np.allclose(Rotation.from_quat(q[[1, 2, 3, 0]]).as_matrix(), Rm, atol=1e-14)
