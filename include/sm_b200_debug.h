@@ -63,6 +63,10 @@ int sm_debug_ndt_host(int32_t op, const double* in, double* out);
  *   op 4: in = two column-major 4x4    out = their product */
 int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out);
 
+/* sm_motion_compensation's arithmetic on the host (csrc/motion.cu make_params + motion_point): packed
+ * {x, y, z, intensity, factor} float records in and out; SM_ERR_BAD_ARGUMENT if a factor is outside [0, 1]. */
+int sm_debug_motion_host(const float* points_5n, int64_t n, const double* delta_4x4, float* out_5n);
+
 /* One (point, voxel) term of computeDerivatives (ndt_omp_impl.hpp:397-438 + :483-535; f64_math = 1: the stock PCL
  * double form NdtWithGicp uses): csrc/ndt.cu's update_derivatives compiled for the host, evaluation tables built by
  * csrc/ndt_host.h for the pose vector p.  out43 = {score increment, gradient term[6], Hessian term[36] row-major}. */

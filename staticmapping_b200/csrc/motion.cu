@@ -29,15 +29,9 @@ struct MotionParams {
   int lerp;           // |d| >= 1 - eps: Eigen falls back to linear weights
 };
 
-__global__ void __launch_bounds__(256)
-motion_compensation_kernel(const char* __restrict__ in, char* __restrict__ out, int64_t stride, int n,
-                           MotionParams P, int* __restrict__ bad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* p = reinterpret_cast<const float*>(in + (int64_t)i * stride);
-  const float x = p[0], y = p[1], z = p[2], intensity = p[3], factor = p[4];
-  // CHECK(factor >= 0. && factor <= 1.), common/math.h:201
-  if (!(factor >= 0.f && factor <= 1.f)) atomicOr(bad, 1);
+// one point: InterpolateTransform(Identity, delta, factor) applied to (x, y, z), written as float
+__host__ __device__ __forceinline__ void motion_point(const MotionParams& P, float x, float y, float z, float factor,
+                                                      float* o) {
   const double t = (double)factor;
   double scale0, scale1;
   if (P.lerp) {
@@ -64,8 +58,21 @@ motion_compensation_kernel(const char* __restrict__ in, char* __restrict__ out, 
   const double ox = ((r00 * px + r01 * py) + r02 * pz) + P.t[0] * t;
   const double oy = ((r10 * px + r11 * py) + r12 * pz) + P.t[1] * t;
   const double oz = ((r20 * px + r21 * py) + r22 * pz) + P.t[2] * t;
+  o[0] = (float)ox; o[1] = (float)oy; o[2] = (float)oz;
+}
+
+__global__ void __launch_bounds__(256)
+motion_compensation_kernel(const char* __restrict__ in, char* __restrict__ out, int64_t stride, int n,
+                           MotionParams P, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(in + (int64_t)i * stride);
+  const float x = p[0], y = p[1], z = p[2], intensity = p[3], factor = p[4];
+  // CHECK(factor >= 0. && factor <= 1.), common/math.h:201
+  if (!(factor >= 0.f && factor <= 1.f)) atomicOr(bad, 1);
   float* o = reinterpret_cast<float*>(out + (int64_t)i * stride);
-  o[0] = (float)ox; o[1] = (float)oy; o[2] = (float)oz; o[3] = intensity; o[4] = factor;
+  motion_point(P, x, y, z, factor, o);
+  o[3] = intensity; o[4] = factor;
 }
 
 // Eigen::Quaternion(Matrix3) (quaternionbase_assign_impl); m column-major 4x4
@@ -141,6 +148,20 @@ int sm_motion_compensation_device(int device, const float* dev_points, int64_t n
   cudaFree(bad);
   if (rc) return rc;
   return host_bad ? SM_ERR_BAD_ARGUMENT : SM_OK;
+}
+
+// test hook (include/sm_b200_debug.h): make_params + motion_point on the host, packed 5-float records
+int sm_debug_motion_host(const float* points, int64_t n, const double* delta_4x4, float* out) {
+  if (!points || !out || !delta_4x4 || n < 0) return SM_ERR_BAD_ARGUMENT;
+  const MotionParams P = make_params(delta_4x4);
+  int bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = points + 5 * i;
+    if (!(p[4] >= 0.f && p[4] <= 1.f)) bad = 1;
+    motion_point(P, p[0], p[1], p[2], p[4], out + 5 * i);
+    out[5 * i + 3] = p[3]; out[5 * i + 4] = p[4];
+  }
+  return bad ? SM_ERR_BAD_ARGUMENT : SM_OK;
 }
 
 int sm_motion_compensation(int device, const float* points, int64_t n, int64_t stride_bytes,

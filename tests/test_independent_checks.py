@@ -360,3 +360,51 @@ def test_icp_pose_update_helpers_of_the_product_against_scipy():
         Rm = Rotation.from_rotvec(axis * 3.1).as_matrix()
         q = _icp_host(2, Rm.ravel(), 0, 4)
         assert np.allclose(Rotation.from_quat(q[[1, 2, 3, 0]]).as_matrix(), Rm, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------- motion compensation (no GPU)
+def _motion_host(pts5, delta):
+    lib = _lib.lib()
+    p = np.ascontiguousarray(pts5, dtype=np.float32)
+    out = np.zeros_like(p)
+    d = np.asfortranarray(np.asarray(delta, dtype=np.float64))
+    rc = lib.sm_debug_motion_host(p.ctypes.data, p.shape[0], d.ctypes.data_as(_lib._DP), out.ctypes.data)
+    return rc, out
+
+
+def _se3_deg(rpy_deg, t):
+    from scipy.spatial.transform import Rotation
+    T = np.eye(4)
+    T[:3, :3] = Rotation.from_euler("xyz", rpy_deg, degrees=True).as_matrix()
+    T[:3, 3] = t
+    return T
+
+
+@pytest.mark.parametrize("delta", [_se3_deg((0.4, -0.3, 2.0), (0.9, -0.1, 0.02)),       # a typical 0.1 s of motion
+                                   _se3_deg((20, -35, 170), (3.0, -2.0, 1.0)),         # large rotation
+                                   _se3_deg((0, 0, 0), (0.5, 0.0, 0.0)),               # pure translation: lerp branch
+                                   _se3_deg((180, 0, 0), (0, 0, 0)),                   # w = 0 quaternion
+                                   _se3_deg((0, 0, 179.0), (0, 0, 0)) @ _se3_deg((0, 170.0, 0), (0, 0, 0))])   # d < 0
+def test_motion_compensation_of_the_product_on_the_host(delta):
+    """csrc/motion.cu make_params + motion_point (the kernel's per-point body) on the host: bit-identical to the oracle
+    (same glibc sin), and the interpolated rotation is scipy's slerp between identity and delta."""
+    from scipy.spatial.transform import Rotation, Slerp
+    rng = np.random.default_rng(4)
+    n = 3000
+    pts = np.zeros((n, 5), np.float32)
+    pts[:, :3] = rng.normal(size=(n, 3)) * np.array([20.0, 20.0, 2.0])
+    pts[:, 3] = rng.random(n) * 100
+    pts[:, 4] = np.arange(n, dtype=np.float32) / n
+    rc, got = _motion_host(pts, delta)
+    rco, want = O.motion_compensation(pts, delta)
+    assert rc == 0 and rco == 0 and np.array_equal(got, want)
+    s = Slerp([0, 1], Rotation.from_matrix(np.stack([np.eye(3), delta[:3, :3]])))
+    f = pts[:, 4].astype(np.float64)
+    ref = np.einsum("nij,nj->ni", s(f).as_matrix(), pts[:, :3].astype(np.float64)) + f[:, None] * delta[:3, 3]
+    assert np.allclose(got[:, :3], ref.astype(np.float32), rtol=0, atol=2e-5)
+    assert np.array_equal(got[:, 3:], pts[:, 3:])
+
+
+def test_motion_compensation_host_rejects_a_factor_outside_the_unit_interval():
+    pts = np.zeros((10, 5), np.float32); pts[3, 4] = 1.5
+    assert _motion_host(pts, np.eye(4))[0] == -1          # CHECK(factor >= 0. && factor <= 1.), common/math.h:201
