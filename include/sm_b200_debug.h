@@ -63,6 +63,11 @@ int sm_debug_ndt_host(int32_t op, const double* in, double* out);
  *   op 4: in = two column-major 4x4    out = their product */
 int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out);
 
+/* Host pieces of the GICP stage besides the minimiser (csrc/gicp_host.h):
+ *   op 0: applyState, gicp_omp_impl.hpp:516-527   in = T[16] col-major, x[6]      out = T'[16] (float arithmetic)
+ *   op 1: computeRDerivative, :133-183            in = x[6], R[9] row-major       out = {g[3], g[4], g[5]} */
+int sm_debug_gicp_host(int32_t op, const double* in, double* out);
+
 /* sm_motion_compensation's arithmetic on the host (csrc/motion.cu make_params + motion_point): packed
  * {x, y, z, intensity, factor} float records in and out; SM_ERR_BAD_ARGUMENT if a factor is outside [0, 1]. */
 int sm_debug_motion_host(const float* points_5n, int64_t n, const double* delta_4x4, float* out_5n);

@@ -1324,6 +1324,24 @@ int sm_debug_solve6_host(const double* A, const double* b, double* x, int32_t* p
   return SM_OK;
 }
 
+// test hook: the host pieces of the GICP stage other than the minimiser (csrc/gicp_host.h), no GPU involved
+int sm_debug_gicp_host(int32_t op, const double* in, double* out) {
+  if (!in || !out) return SM_ERR_BAD_ARGUMENT;
+  switch (op) {
+    case 0: {   // applyState (gicp_omp_impl.hpp:516-527): in = T[16] col-major (cast to float), x[6]; out = T'[16]
+      float T[16];
+      for (int i = 0; i < 16; ++i) T[i] = (float)in[i];
+      gicp::apply_state(T, in + 16);
+      for (int i = 0; i < 16; ++i) out[i] = (double)T[i];
+      return SM_OK;
+    }
+    case 1:     // computeRDerivative (:133-183): in = x[6], R[9] row-major; out[0..2] = g[3..5]
+      { double g[6] = {0, 0, 0, 0, 0, 0}; gicp::r_derivative(in, in + 6, g); out[0] = g[3]; out[1] = g[4]; out[2] = g[5]; }
+      return SM_OK;
+    default: return SM_ERR_BAD_ARGUMENT;
+  }
+}
+
 // test hook: the per-match contribution to the point-to-plane normal equations (icp_dev.cuh match_terms /
 // add_terms, the functions icp_accum_kernel and icp_finish_kernel call) and the pose-update helpers of
 // linalg_dev.cuh, compiled for the HOST

