@@ -63,6 +63,17 @@ int sm_debug_ndt_host(int32_t op, const double* in, double* out);
  *   op 4: in = two column-major 4x4    out = their product */
 int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out);
 
+/* The Newton loop of registrator::Ndt (NormalDistributionsTransform::computeTransformation, ndt_omp_impl.hpp:81-171,
+ * with the step-length routine whose More-Thuente loop never runs, :757-916) as the product runs it: csrc/ndt_host.h
+ * newton_loop, the function that drives the device evaluations in sm_align.  Here the evaluation is the caller's:
+ * fn(T, p, sums, user) receives final_transformation_ (column-major 4x4, float-valued) and the pose vector p[6] it
+ * was built from (the angle-derivative tables belong to p) and fills sums[0] = score, [1..6] = gradient, [7..42] = Hessian row-major, [43] = neighbour count
+ * summed over the points; it returns < 0 to abort. */
+typedef int (*sm_debug_ndt_eval)(const double* T_4x4, const double* p_6, double* sums_44, void* user);
+int sm_debug_ndt_newton(sm_debug_ndt_eval fn, void* user, const double* guess_4x4, int32_t n_source, float resolution,
+                        double step_size, double outlier_ratio, double transformation_epsilon, int32_t max_iterations,
+                        double* final_4x4, int32_t* iterations, int32_t* evaluations, double* score);
+
 /* Host pieces of the GICP stage besides the minimiser (csrc/gicp_host.h):
  *   op 0: applyState, gicp_omp_impl.hpp:516-527   in = T[16] col-major, x[6]      out = T'[16] (float arithmetic)
  *   op 1: computeRDerivative, :133-183            in = x[6], R[9] row-major       out = {g[3], g[4], g[5]} */

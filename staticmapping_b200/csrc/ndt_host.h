@@ -153,6 +153,92 @@ inline void svd_solve6(const double* A, const double* b, double* x) {
   }
 }
 
+// NormalDistributionsTransform::computeTransformation (ndt_omp_impl.hpp:81-171) as the reference executes it, over
+// an evaluation callback: eval(P, p, sums) runs computeDerivatives for the pose vector p (P.T and the angle tables
+// of P are built from it) and fills
+// sums[0] = score, sums[1..6] = gradient, sums[7..42] = Hessian (row-major), sums[43] = neighbour count over all
+// points; it returns < 0 on error (propagated).  P comes in with the Gauss constants, radius and f64_math set.
+// The device path passes a lambda around ndt_eval_sync (sm_api.cu ndt_run); the test hook sm_debug_ndt_newton passes a
+// caller-supplied function, so this control flow is exercised on the host against an independent restatement.
+struct NewtonOut {
+  float final_T[16];           // final_transformation_, column-major
+  int iterations = 0;          // nr_iterations_
+  int evaluations = 0;         // computeDerivatives calls
+  double score = 0.0;          // of the last evaluation
+  double nb_sum = 0.0;         // sum over the evaluations of (neighbours per point)
+};
+
+template <class Eval>
+inline int newton_loop(const Options& o, const double* guess, int ns, NdtEvalParams& P, Eval eval, NewtonOut* out) {
+  float* final_T = out->final_T;
+  bool guess_is_identity = true;
+  for (int i = 0; i < 16; ++i) {
+    final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    if ((float)guess[i] != final_T[i]) guess_is_identity = false;
+  }
+  if (!guess_is_identity) for (int i = 0; i < 16; ++i) final_T[i] = (float)guess[i];   // :95-101
+  double p[6];
+  p_from_transform(final_T, p);                                       // :103-111
+  for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
+  angle_tables(p, &P);
+  double sums[44] = {0.0}, score = 0, grad[6], hess[36], nb_sum = 0.0;
+  int evals = 0;
+  auto read_sums = [&]() {
+    score = sums[0];
+    for (int i = 0; i < 6; ++i) grad[i] = sums[1 + i];
+    for (int i = 0; i < 36; ++i) hess[i] = sums[7 + i];
+    nb_sum += sums[43] / (double)ns;
+    ++evals;
+  };
+  int rc = eval(P, p, sums);                                          // :119
+  if (rc < 0) return rc;
+  read_sums();
+  int nr_iterations = 0;
+  bool converged = false;
+  while (!converged) {
+    double neg_grad[6], delta[6];
+    for (int i = 0; i < 6; ++i) neg_grad[i] = -grad[i];
+    svd_solve6(hess, neg_grad, delta);                                // :127-129
+    double norm = 0.0;
+    for (int i = 0; i < 6; ++i) norm += delta[i] * delta[i];
+    norm = sqrt(norm);
+    if (norm == 0.0 || norm != norm) break;                           // :134-139
+    for (int i = 0; i < 6; ++i) delta[i] /= norm;
+    // computeStepLengthMT (:757-916); its More-Thuente loop never runs because
+    // interval_converged starts as (step_max - step_min) > 0 == true (:802)
+    double d_phi_0 = 0.0;
+    for (int i = 0; i < 6; ++i) d_phi_0 += grad[i] * delta[i];
+    d_phi_0 = -d_phi_0;
+    double a_t = 0.0;
+    bool evaluate = true;
+    if (d_phi_0 >= 0.0) {
+      if (d_phi_0 == 0.0) evaluate = false;
+      else for (int i = 0; i < 6; ++i) delta[i] = -delta[i];
+    }
+    if (evaluate) {
+      a_t = std::max(std::min(norm, o.step_size), o.transformation_epsilon / 2.0);
+      double x_t[6];
+      for (int i = 0; i < 6; ++i) x_t[i] = p[i] + delta[i] * a_t;
+      transform_from_p(x_t, final_T);                                 // :809-812
+      for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
+      angle_tables(x_t, &P);
+      rc = eval(P, x_t, sums);                                        // :818
+      if (rc < 0) return rc;
+      read_sums();
+    }
+    for (int i = 0; i < 6; ++i) p[i] += delta[i] * a_t;               // :143,152
+    if (nr_iterations > o.max_iterations ||
+        (nr_iterations && fabs(a_t) < o.transformation_epsilon))
+      converged = true;                                                // :158-162
+    ++nr_iterations;
+  }
+  out->iterations = nr_iterations;
+  out->evaluations = evals;
+  out->score = score;
+  out->nb_sum = nb_sum;
+  return 0;
+}
+
 }  // namespace ndt
 }  // namespace smb
 

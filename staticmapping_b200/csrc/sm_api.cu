@@ -734,66 +734,22 @@ int ndt_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, co
   ndt::gauss_constants(o, &P.gauss_d1, &P.gauss_d2);
   P.radius = o.resolution;
   P.f64_math = f64_math ? 1 : 0;
+  // the Newton loop itself is host code shared with the test hook sm_debug_ndt_newton (ndt_host.h newton_loop);
+  // one evaluation = computeDerivatives on the device, 44 sums handed back through mapped pinned memory
+  ndt::NewtonOut nw;
+  int launches = 12 + 12;
+  const int nrc = ndt::newton_loop(o, guess, ns, P, [&](const NdtEvalParams& Pe, const double*, double* sums) -> int {
+    const int rc = ndt_eval_sync(h, src, ns, Pe, ws);
+    if (rc < 0) return rc;
+    for (int i = 0; i < 44; ++i) sums[i] = h->host_sums[i];
+    launches += 2;
+    return 0;
+  }, &nw);
+  H_RC(nrc);
   float* final_T = out->final_T;
-  bool guess_is_identity = true;
-  for (int i = 0; i < 16; ++i) {
-    final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-    if ((float)guess[i] != final_T[i]) guess_is_identity = false;
-  }
-  if (!guess_is_identity) for (int i = 0; i < 16; ++i) final_T[i] = (float)guess[i];   // :95-101
-  double p[6];
-  ndt::p_from_transform(final_T, p);                                  // :103-111
-  for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
-  ndt::angle_tables(p, &P);
-  double score = 0, grad[6], hess[36], nb_sum = 0.0;
-  int evals = 0, launches = 12 + 12;
-  auto read_sums = [&]() {
-    score = h->host_sums[0];
-    for (int i = 0; i < 6; ++i) grad[i] = h->host_sums[1 + i];
-    for (int i = 0; i < 36; ++i) hess[i] = h->host_sums[7 + i];
-    nb_sum += h->host_sums[43] / (double)ns;
-    ++evals; launches += 2;
-  };
-  H_RC(ndt_eval_sync(h, src, ns, P, ws));                             // :119
-  read_sums();
-  int nr_iterations = 0;
-  bool converged = false;
-  while (!converged) {
-    double neg_grad[6], delta[6];
-    for (int i = 0; i < 6; ++i) neg_grad[i] = -grad[i];
-    ndt::svd_solve6(hess, neg_grad, delta);                           // :127-129
-    double norm = 0.0;
-    for (int i = 0; i < 6; ++i) norm += delta[i] * delta[i];
-    norm = sqrt(norm);
-    if (norm == 0.0 || norm != norm) break;                           // :134-139
-    for (int i = 0; i < 6; ++i) delta[i] /= norm;
-    // computeStepLengthMT (:757-916); its More-Thuente loop never runs because
-    // interval_converged starts as (step_max - step_min) > 0 == true (:802)
-    double d_phi_0 = 0.0;
-    for (int i = 0; i < 6; ++i) d_phi_0 += grad[i] * delta[i];
-    d_phi_0 = -d_phi_0;
-    double a_t = 0.0;
-    bool evaluate = true;
-    if (d_phi_0 >= 0.0) {
-      if (d_phi_0 == 0.0) evaluate = false;
-      else for (int i = 0; i < 6; ++i) delta[i] = -delta[i];
-    }
-    if (evaluate) {
-      a_t = std::max(std::min(norm, o.step_size), o.transformation_epsilon / 2.0);
-      double x_t[6];
-      for (int i = 0; i < 6; ++i) x_t[i] = p[i] + delta[i] * a_t;
-      ndt::transform_from_p(x_t, final_T);                            // :809-812
-      for (int i = 0; i < 16; ++i) P.T[i] = final_T[i];
-      ndt::angle_tables(x_t, &P);
-      H_RC(ndt_eval_sync(h, src, ns, P, ws));                         // :818
-      read_sums();
-    }
-    for (int i = 0; i < 6; ++i) p[i] += delta[i] * a_t;               // :143,152
-    if (nr_iterations > o.max_iterations ||
-        (nr_iterations && fabs(a_t) < o.transformation_epsilon))
-      converged = true;                                                // :158-162
-    ++nr_iterations;
-  }
+  for (int i = 0; i < 16; ++i) final_T[i] = nw.final_T[i];
+  const int nr_iterations = nw.iterations, evals = nw.evaluations;
+  const double score = nw.score, nb_sum = nw.nb_sum;
   H_CUDA(cudaEventRecord(h->ev[2], h->stream));
   // getFitnessScore (ndt.cc:60): exact 1-NN over the full target (PCL builds this search
   // tree in setInputTarget; the reference calls that on every Align)
@@ -1321,6 +1277,32 @@ int sm_debug_solve6(int device, const double* A, const double* b, double* x, int
 int sm_debug_solve6_host(const double* A, const double* b, double* x, int32_t* path) {
   if (!A || !b || !x || !path) return SM_ERR_BAD_ARGUMENT;
   *path = la::solve_possibly_underdetermined(A, b, x);
+  return SM_OK;
+}
+
+// test hook: the NDT Newton loop of the product (ndt_host.h newton_loop, the function ndt_run drives the device
+// with) over a caller-supplied evaluation — no GPU involved
+int sm_debug_ndt_newton(sm_debug_ndt_eval fn, void* user, const double* guess_4x4, int32_t n_source, float resolution,
+                        double step_size, double outlier_ratio, double transformation_epsilon, int32_t max_iterations,
+                        double* final_4x4, int32_t* iterations, int32_t* evaluations, double* score) {
+  if (!fn || !guess_4x4 || !final_4x4 || !iterations || !evaluations || !score || n_source <= 0)
+    return SM_ERR_BAD_ARGUMENT;
+  ndt::Options o;
+  o.resolution = resolution; o.step_size = step_size; o.outlier_ratio = outlier_ratio;
+  o.transformation_epsilon = transformation_epsilon; o.max_iterations = max_iterations;
+  NdtEvalParams P;
+  memset(&P, 0, sizeof(P));
+  ndt::gauss_constants(o, &P.gauss_d1, &P.gauss_d2);
+  P.radius = o.resolution;
+  ndt::NewtonOut nw;
+  const int rc = ndt::newton_loop(o, guess_4x4, n_source, P, [&](const NdtEvalParams& Pe, const double* p6, double* sums) -> int {
+    double T[16];
+    for (int i = 0; i < 16; ++i) T[i] = (double)Pe.T[i];
+    return fn(T, p6, sums, user);
+  }, &nw);
+  if (rc < 0) return rc;
+  for (int i = 0; i < 16; ++i) final_4x4[i] = (double)nw.final_T[i];
+  *iterations = nw.iterations; *evaluations = nw.evaluations; *score = nw.score;
   return SM_OK;
 }
 

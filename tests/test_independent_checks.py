@@ -444,3 +444,47 @@ def test_gicp_apply_state_and_rotation_derivative_of_the_product():
             e = np.zeros(3); e[k] = h
             fd = (f(x[3:] + e) - f(x[3:] - e)) / (2 * h)
             assert abs(g[k] - fd) < 1e-7 * max(1.0, abs(fd)), (k, g[k], fd)
+
+
+# ---------------------------------------------------------------------------------- NDT Newton loop (no GPU)
+@pytest.mark.parametrize("f64,eps", [(False, 0.1), (True, 0.01)])
+def test_ndt_newton_loop_of_the_product_over_the_numpy_evaluation(f64, eps):
+    """csrc/ndt_host.h newton_loop — the function sm_align drives the device evaluations with — run on the host with
+    tests/pyref.py's computeDerivatives as the evaluation: iteration and evaluation counts, final pose and score
+    against the independent restatement of the whole loop (pyref.ndt_align) and against the oracle."""
+    import pyref
+    import scenes
+    src, sub, _ = scenes.lidar_pair(pair=2)
+    s32 = src[::2].astype(np.float32); t32 = sub.astype(np.float32)
+    grid = pyref.NdtGrid(t32)
+    calls = []
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+    def evaluate(T_ptr, p_ptr, sums_ptr, _user):
+        T = np.array([T_ptr[i] for i in range(16)]).reshape(4, 4).T.astype(np.float32)
+        p = np.array([p_ptr[i] for i in range(6)])
+        trans = pyref._transform_cloud_f32(T, s32)
+        score, g, H, nbar = pyref.ndt_derivatives(grid, s32, trans, p, f64=f64)
+        sums_ptr[0] = score
+        for i in range(6):
+            sums_ptr[1 + i] = g[i]
+        for i in range(36):
+            sums_ptr[7 + i] = H.ravel()[i]
+        sums_ptr[43] = nbar * s32.shape[0]
+        calls.append(p.copy())
+        return 0
+
+    lib = _lib.lib()
+    guess = np.asfortranarray(np.eye(4))
+    final = np.zeros(16); it = C.c_int32(); ev = C.c_int32(); sc = C.c_double()
+    rc = lib.sm_debug_ndt_newton(evaluate, None, guess.ctypes.data, s32.shape[0], 1.0, 0.1, 0.55, eps, 35,
+                                 final.ctypes.data, C.byref(it), C.byref(ev), C.byref(sc))
+    assert rc == 0 and ev.value == len(calls)
+    want = pyref.ndt_align(s32, t32, transformation_epsilon=eps, f64=f64)
+    assert it.value == want["iterations"] and ev.value == want["evaluations"]
+    T = final.reshape(4, 4).T
+    assert np.allclose(T, want["result"], rtol=0, atol=2e-6)
+    assert abs(sc.value / s32.shape[0] - want["trans_probability"]) <= 1e-6 * abs(want["trans_probability"])
+    if not f64:
+        o = O.ndt_align(s32, t32)
+        assert it.value == o["iterations"] and np.allclose(T, o["result"], rtol=0, atol=2e-5)
