@@ -74,6 +74,19 @@ int sm_debug_ndt_newton(sm_debug_ndt_eval fn, void* user, const double* guess_4x
                         double step_size, double outlier_ratio, double transformation_epsilon, int32_t max_iterations,
                         double* final_4x4, int32_t* iterations, int32_t* evaluations, double* score);
 
+/* The outer loop of the GICP stage as the product runs it (csrc/gicp_host.h outer_loop =
+ * GeneralizedIterativeClosestPoint::computeTransformation + estimateRigidTransformationBFGS, gicp_omp_impl.hpp:381-514,
+ * :187-246, with the options of ndt_gicp.cc:50-51), over the caller's per-point work:
+ *   correspond(transformation_4x4, R_9, &m, user): correspondences and Mahalanobis matrices for transformation_ (column-
+ *       major, float-valued) with R = rot(transformation_ * guess) row-major in double; m = number of correspondences
+ *   cost(T_4x4, S_13, user): S[0] = sum res^T M res, S[1..3] = sum M res, S[4..12] = sum (guess p)(M res)^T row-major
+ *       for T = guess with applyState(x) (column-major, float-valued)
+ * both return < 0 to abort. */
+typedef int (*sm_debug_gicp_correspond)(const double* transformation_4x4, const double* R_9, int32_t* m, void* user);
+typedef int (*sm_debug_gicp_cost)(const double* T_4x4, double* S_13, void* user);
+int sm_debug_gicp_outer(sm_debug_gicp_correspond correspond, sm_debug_gicp_cost cost, void* user,
+                        const double* guess_4x4, double* final_4x4, int32_t* iterations, int32_t* bfgs_evaluations);
+
 /* Host pieces of the GICP stage besides the minimiser (csrc/gicp_host.h):
  *   op 0: applyState, gicp_omp_impl.hpp:516-527   in = T[16] col-major, x[6]      out = T'[16] (float arithmetic)
  *   op 1: computeRDerivative, :133-183            in = x[6], R[9] row-major       out = {g[3], g[4], g[5]} */

@@ -270,6 +270,103 @@ struct Minimizer {
   int test_gradient(double epsabs) const { return norm(gradient) < epsabs ? kSuccess : kRunning; }
 };
 
+// GeneralizedIterativeClosestPoint::computeTransformation (gicp_omp_impl.hpp:381-514) with
+// estimateRigidTransformationBFGS (:187-246) as the reference executes them, over two callbacks:
+//   correspond(transformation, R, &m): the per-point part of one outer iteration (:419-463) for transformation_
+//       (column-major float 4x4) and R = rot(transformation_ * guess) in double, row-major; m = correspondences
+//   cost(T, S): the sums of one functor evaluation (:255-377) for T = base with applyState(x):
+//       S[0] = sum res^T M res, S[1..3] = sum M res, S[4..12] = sum (base p)(M res)^T row-major
+// both return < 0 on error (propagated as -1).  The device path passes lambdas around the kernels (sm_api.cu
+// gicp_run); the test hook sm_debug_gicp_outer passes a caller's functions, so this control flow — start vector,
+// f / g assembly, BFGS driver, convergence test, final composition — is exercised on the host.
+struct OuterOut {
+  float final_T[16];
+  int iterations = 0;
+  int bfgs_evals = 0;
+};
+
+template <class Correspond, class Cost>
+inline int outer_loop(const Options& o, const float* guess, Correspond correspond, Cost cost, OuterOut* out) {
+  float transformation[16], previous[16];
+  for (int i = 0; i < 16; ++i) transformation[i] = previous[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  int nr_iterations = 0, evals = 0;
+  bool converged = false, callback_error = false;
+  while (!converged) {
+    double R[9];
+    for (int i = 0; i < 3; ++i)          // transform_R = transformation_ * guess in double (:423-429)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < 4; ++k) s += (double)transformation[i + 4 * k] * (double)guess[k + 4 * j];
+        R[i * 3 + j] = s;
+      }
+    int m = 0;
+    if (correspond(transformation, R, &m) < 0) return -1;
+    for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
+    if (m < 4) break;                    // NotEnoughPointsException, caught at :489-492
+    double x[6] = {(double)transformation[12], (double)transformation[13], (double)transformation[14],
+                   atan2((double)transformation[2 + 4 * 1], (double)transformation[2 + 4 * 2]),
+                   asin(-(double)transformation[2 + 4 * 0]),
+                   atan2((double)transformation[1 + 4 * 0], (double)transformation[0 + 4 * 0])};
+    Minimizer mz;
+    mz.fdf = [&](const double* xx, double* f, double* g) -> int {
+      ++evals;
+      float T[16];
+      for (int i = 0; i < 16; ++i) T[i] = guess[i];
+      apply_state(T, xx);
+      double S[13];
+      if (cost(T, S) < 0) return -1;
+      if (f) *f = S[0] / (double)m;
+      if (g) {
+        double Rm[9];
+        for (int r = 0; r < 3; ++r) g[r] = S[1 + r] * (2.0 / m);
+        for (int q = 0; q < 9; ++q) Rm[q] = S[4 + q] * (2.0 / m);
+        r_derivative(xx, Rm, g);
+      }
+      return 0;
+    };
+    mz.init(x);
+    int result = kRunning, inner = 0;
+    do {
+      ++inner;
+      result = mz.one_step(x);
+      if (result) break;
+      result = mz.test_gradient(1e-2);
+    } while (result == kRunning && inner < o.max_inner_iterations);
+    if (mz.failed) { callback_error = true; break; }
+    if (result == kNoProgress || result == kSuccess || inner == o.max_inner_iterations) {
+      for (int i = 0; i < 16; ++i) transformation[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+      apply_state(transformation, x);
+    } else {
+      break;
+    }
+    double delta = 0.0;
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 4; ++l) {
+        const double ratio = (k < 3 && l < 3) ? 1.0 / o.rotation_epsilon : 1.0 / o.transformation_epsilon;
+        const double c_delta = ratio * fabs((double)previous[k + 4 * l] - (double)transformation[k + 4 * l]);
+        if (c_delta > delta) delta = c_delta;
+      }
+    ++nr_iterations;
+    if (nr_iterations >= o.max_iterations || delta < 1) {
+      converged = true;
+      for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
+    }
+  }
+  if (callback_error) return -1;
+  float Rp[9], Rg[9], Rf[9];            // :505-508
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Rp[r * 3 + c] = previous[r + 4 * c]; Rg[r * 3 + c] = guess[r + 4 * c]; }
+  ndt::mul3(Rp, Rg, Rf);
+  float* final_T = out->final_T;
+  for (int i = 0; i < 16; ++i) final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) final_T[r + 4 * c] = Rf[r * 3 + c];
+    final_T[12 + r] = previous[12 + r] + guess[12 + r];
+  }
+  out->iterations = nr_iterations;
+  out->bfgs_evals = evals;
+  return 0;
+}
+
 }  // namespace gicp
 }  // namespace smb
 

@@ -829,101 +829,50 @@ int gicp_run(sm_handle* h, const float* src, int ns, const float* tgt, int nt, c
     H_RC(gicp_covariances(src, ns, (const KdNode*)h->nodes2.p, (const BucketPoint*)h->bpts2.p, o.gicp_epsilon,
                           (double*)h->cov_s.p, h->stream));
   else H_CUDA(cudaMemsetAsync(h->cov_s.p, 0, (size_t)ns * 9 * sizeof(double), h->stream));
-  float transformation[16], previous[16];
-  for (int i = 0; i < 16; ++i) transformation[i] = previous[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-  int nr_iterations = 0, evals = 0;
-  bool converged = false, device_error = false;
-  while (!converged) {
-    GicpIterParams IP;
-    for (int i = 0; i < 16; ++i) { IP.guess[i] = guess[i]; IP.transformation[i] = transformation[i]; }
-    for (int i = 0; i < 3; ++i)          // transform_R = transformation_ * guess in double (:423-429)
-      for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
-        for (int k = 0; k < 4; ++k) s += (double)transformation[i + 4 * k] * (double)guess[k + 4 * j];
-        IP.R[i * 3 + j] = s;
-      }
-    IP.dist_threshold = o.corr_dist_threshold * o.corr_dist_threshold;
-    H_RC(gicp_correspond(src, ns, tgt, IP, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p,
-                         (const double*)h->cov_s.p, (const double*)h->cov_t.p, (int32_t*)h->match.p,
-                         (double*)h->maha.p, (uint32_t*)h->counter.p, h->stream));
-    uint32_t m_u = 0;
-    H_CUDA(cudaMemcpyAsync(&m_u, h->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    H_CUDA(cudaStreamSynchronize(h->stream));
-    const int m = (int)m_u;
-    for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
-    if (m < 4) break;                    // NotEnoughPointsException, caught at :489-492
-    double x[6] = {(double)transformation[12], (double)transformation[13], (double)transformation[14],
-                   atan2((double)transformation[2 + 4 * 1], (double)transformation[2 + 4 * 2]),
-                   asin(-(double)transformation[2 + 4 * 0]),
-                   atan2((double)transformation[1 + 4 * 0], (double)transformation[0 + 4 * 0])};
-    gicp::Minimizer mz;
-    mz.fdf = [&](const double* xx, double* f, double* g) -> int {
-      ++evals;
-      GicpCostParams CP;
-      for (int i = 0; i < 16; ++i) { CP.T[i] = guess[i]; CP.base[i] = guess[i]; }
-      gicp::apply_state(CP.T, xx);
-      // the kernel's last block writes the 13 sums and then the sequence word into mapped pinned memory
-      volatile long long* flag = reinterpret_cast<volatile long long*>(h->host_sums + 60);
-      const long long seq = ++h->gicp_seq;
-      if (gicp_cost(src, ns, tgt, CP, (const int32_t*)h->match.p, (const double*)h->maha.p,
-                    (double*)h->gicp_partials.p, sums_dev, ticket_dev, h->host_sums_dev,
-                    reinterpret_cast<long long*>(h->host_sums_dev + 60), seq, h->stream) != 0) return -1;
-      for (long spins = 0; *flag != seq; ++spins) {
-        if ((spins & 0xfff) == 0xfff && cudaStreamQuery(h->stream) != cudaErrorNotReady) {
-          if (*flag == seq) break;
-          if (cudaStreamSynchronize(h->stream) != cudaSuccess || *flag != seq) return -1;   // the kernel failed
+  // the outer loop, the BFGS driver and the assembly of f / g from the 13 sums are host code shared with the test
+  // hook sm_debug_gicp_outer (gicp_host.h outer_loop); the two callbacks are the device work
+  gicp::OuterOut go;
+  bool cuda_error = false;
+  const int grc = gicp::outer_loop(
+      o, guess,
+      [&](const float* transformation, const double* R, int* m_out) -> int {
+        GicpIterParams IP;
+        for (int i = 0; i < 16; ++i) { IP.guess[i] = guess[i]; IP.transformation[i] = transformation[i]; }
+        for (int q = 0; q < 9; ++q) IP.R[q] = R[q];
+        IP.dist_threshold = o.corr_dist_threshold * o.corr_dist_threshold;
+        if (gicp_correspond(src, ns, tgt, IP, (const KdNode*)h->nodes.p, (const BucketPoint*)h->bpts.p,
+                            (const double*)h->cov_s.p, (const double*)h->cov_t.p, (int32_t*)h->match.p,
+                            (double*)h->maha.p, (uint32_t*)h->counter.p, h->stream) != 0) { cuda_error = true; return -1; }
+        uint32_t m_u = 0;
+        if (cudaMemcpyAsync(&m_u, h->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { cuda_error = true; return -1; }
+        *m_out = (int)m_u;
+        return 0;
+      },
+      [&](const float* T, double* S) -> int {
+        GicpCostParams CP;
+        for (int i = 0; i < 16; ++i) { CP.T[i] = T[i]; CP.base[i] = guess[i]; }
+        // the kernel's last block writes the 13 sums and then the sequence word into mapped pinned memory
+        volatile long long* flag = reinterpret_cast<volatile long long*>(h->host_sums + 60);
+        const long long seq = ++h->gicp_seq;
+        if (gicp_cost(src, ns, tgt, CP, (const int32_t*)h->match.p, (const double*)h->maha.p,
+                      (double*)h->gicp_partials.p, sums_dev, ticket_dev, h->host_sums_dev,
+                      reinterpret_cast<long long*>(h->host_sums_dev + 60), seq, h->stream) != 0) { cuda_error = true; return -1; }
+        for (long spins = 0; *flag != seq; ++spins) {
+          if ((spins & 0xfff) == 0xfff && cudaStreamQuery(h->stream) != cudaErrorNotReady) {
+            if (*flag == seq) break;
+            if (cudaStreamSynchronize(h->stream) != cudaSuccess || *flag != seq) { cuda_error = true; return -1; }   // the kernel failed
+          }
         }
-      }
-      std::atomic_thread_fence(std::memory_order_acquire);
-      const double* S = h->host_sums;
-      if (f) *f = S[0] / (double)m;
-      if (g) {
-        double Rm[9];
-        for (int r = 0; r < 3; ++r) g[r] = S[1 + r] * (2.0 / m);
-        for (int q = 0; q < 9; ++q) Rm[q] = S[4 + q] * (2.0 / m);
-        gicp::r_derivative(xx, Rm, g);
-      }
-      return 0;
-    };
-    mz.init(x);
-    int result = gicp::kRunning, inner = 0;
-    do {
-      ++inner;
-      result = mz.one_step(x);
-      if (result) break;
-      result = mz.test_gradient(1e-2);
-    } while (result == gicp::kRunning && inner < o.max_inner_iterations);
-    if (mz.failed) { device_error = true; break; }
-    if (result == gicp::kNoProgress || result == gicp::kSuccess || inner == o.max_inner_iterations) {
-      for (int i = 0; i < 16; ++i) transformation[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-      gicp::apply_state(transformation, x);
-    } else {
-      break;
-    }
-    double delta = 0.0;
-    for (int k = 0; k < 4; ++k)
-      for (int l = 0; l < 4; ++l) {
-        const double ratio = (k < 3 && l < 3) ? 1.0 / o.rotation_epsilon : 1.0 / o.transformation_epsilon;
-        const double c_delta = ratio * fabs((double)previous[k + 4 * l] - (double)transformation[k + 4 * l]);
-        if (c_delta > delta) delta = c_delta;
-      }
-    ++nr_iterations;
-    if (nr_iterations >= o.max_iterations || delta < 1) {
-      converged = true;
-      for (int i = 0; i < 16; ++i) previous[i] = transformation[i];
-    }
-  }
-  if (device_error) return cuda_fail(h);
-  float Rp[9], Rg[9], Rf[9];            // :505-508
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Rp[r * 3 + c] = previous[r + 4 * c]; Rg[r * 3 + c] = guess[r + 4 * c]; }
-  ndt::mul3(Rp, Rg, Rf);
-  for (int i = 0; i < 16; ++i) final_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) final_T[r + 4 * c] = Rf[r * 3 + c];
-    final_T[12 + r] = previous[12 + r] + guess[12 + r];
-  }
-  *iterations = nr_iterations;
-  *bfgs_evals = evals;
+        std::atomic_thread_fence(std::memory_order_acquire);
+        for (int q = 0; q < 13; ++q) S[q] = h->host_sums[q];
+        return 0;
+      },
+      &go);
+  if (grc < 0 || cuda_error) return cuda_fail(h);
+  for (int i = 0; i < 16; ++i) final_T[i] = go.final_T[i];
+  *iterations = go.iterations;
+  *bfgs_evals = go.bfgs_evals;
   return 0;
 }
 
@@ -1303,6 +1252,38 @@ int sm_debug_ndt_newton(sm_debug_ndt_eval fn, void* user, const double* guess_4x
   if (rc < 0) return rc;
   for (int i = 0; i < 16; ++i) final_4x4[i] = (double)nw.final_T[i];
   *iterations = nw.iterations; *evaluations = nw.evaluations; *score = nw.score;
+  return SM_OK;
+}
+
+// test hook: the GICP outer loop of the product (gicp_host.h outer_loop: start vector, f / g from the 13 sums, BFGS
+// driver, convergence test, final composition — the function gicp_run drives the device with) over a caller's
+// correspondence and cost functions; no GPU involved
+int sm_debug_gicp_outer(sm_debug_gicp_correspond correspond, sm_debug_gicp_cost cost, void* user, const double* guess_4x4,
+                        double* final_4x4, int32_t* iterations, int32_t* bfgs_evaluations) {
+  if (!correspond || !cost || !guess_4x4 || !final_4x4 || !iterations || !bfgs_evaluations) return SM_ERR_BAD_ARGUMENT;
+  float guess[16];
+  for (int i = 0; i < 16; ++i) guess[i] = (float)guess_4x4[i];
+  gicp::OuterOut go;
+  const int rc = gicp::outer_loop(
+      gicp::Options(), guess,
+      [&](const float* transformation, const double* R, int* m) -> int {
+        double T[16];
+        for (int i = 0; i < 16; ++i) T[i] = (double)transformation[i];
+        int32_t mm = 0;
+        const int r = correspond(T, R, &mm, user);
+        *m = (int)mm;
+        return r;
+      },
+      [&](const float* Tf, double* S) -> int {
+        double T[16];
+        for (int i = 0; i < 16; ++i) T[i] = (double)Tf[i];
+        return cost(T, S, user);
+      },
+      &go);
+  if (rc < 0) return SM_ERR_CUDA;
+  for (int i = 0; i < 16; ++i) final_4x4[i] = (double)go.final_T[i];
+  *iterations = go.iterations;
+  *bfgs_evaluations = go.bfgs_evals;
   return SM_OK;
 }
 

@@ -488,3 +488,53 @@ def test_ndt_newton_loop_of_the_product_over_the_numpy_evaluation(f64, eps):
     if not f64:
         o = O.ndt_align(s32, t32)
         assert it.value == o["iterations"] and np.allclose(T, o["result"], rtol=0, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------- GICP outer loop (no GPU)
+def test_gicp_outer_loop_of_the_product_over_the_numpy_per_point_work():
+    """csrc/gicp_host.h outer_loop — the function sm_align drives the device kernels with — run on the host with
+    tests/pyref.py's correspondences / Mahalanobis matrices / cost sums as the per-point work: outer iterations, BFGS
+    evaluations and the final pose against the oracle's GICP stage (which has its own copies of all of it)."""
+    import pyref
+    import scenes
+    src, sub, _ = scenes.lidar_pair(pair=1)
+    s = O.approx_voxel_grid(src.astype(np.float32), 0.2)[::2].copy()
+    t = O.approx_voxel_grid(sub.astype(np.float32), 0.2)[::3].copy()
+    cs, ct = pyref.gicp_covariances(s), pyref.gicp_covariances(t)
+    guess = np.eye(4); guess[:3, 3] = (0.05, -0.04, 0.02)
+    g32 = guess.astype(np.float32)
+    state = {}
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p)
+    def correspond(T_ptr, R_ptr, m_ptr, _user):
+        tr = np.array([T_ptr[i] for i in range(16)]).reshape(4, 4).T.astype(np.float32)
+        R = np.array([R_ptr[i] for i in range(9)]).reshape(3, 3)
+        assert np.allclose(R, (tr.astype(np.float64) @ g32.astype(np.float64))[:3, :3], atol=1e-15)
+        state["si"], state["ti"], state["M"] = pyref.gicp_correspond(s, t, g32, tr, cs, ct)
+        m_ptr[0] = int(state["si"].size)
+        return 0
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+    def cost(T_ptr, S_ptr, _user):
+        T = np.array([T_ptr[i] for i in range(16)]).reshape(4, 4).T.astype(np.float32)
+        si, ti, M = state["si"], state["ti"], state["M"]
+        res = (pyref._transform_cloud_f32(T, s[si]) - t[ti]).astype(np.float64)
+        temp = np.einsum("mij,mj->mi", M[si], res)
+        pb = pyref._transform_cloud_f32(g32, s[si]).astype(np.float64)
+        S = np.concatenate([[np.einsum("mi,mi->", res, temp)], temp.sum(axis=0), (pb.T @ temp).ravel()])
+        for i in range(13):
+            S_ptr[i] = S[i]
+        return 0
+
+    lib = _lib.lib()
+    final = np.zeros(16); it = C.c_int32(); ev = C.c_int32()
+    gc = np.asfortranarray(guess)
+    rc = lib.sm_debug_gicp_outer(correspond, cost, None, gc.ctypes.data, final.ctypes.data, C.byref(it), C.byref(ev))
+    assert rc == 0
+    o = O.ndt_gicp_align(s, t, guess=guess, using_voxel_filter=False, use_ndt=False)
+    assert o["rc"] == 1
+    assert it.value == o["gicp_iterations"]
+    assert abs(ev.value - o["bfgs_evaluations"]) <= 1          # sums differ in the last bits: one evaluation at most
+    T = final.reshape(4, 4).T
+    dt, dr = scenes.se3_error(o["result"], T)
+    assert dt < 1e-5 and dr < 1e-5, (dt, dr)
