@@ -1,18 +1,24 @@
 /* sm_b200_debug.h — TEST HOOKS of libsm_b200.so.  Not part of the drop-in boundary (include/sm_b200.h):
- * nothing in the reference binds these.  They let tests/ drive three pieces of product code that have no
- * entry point of their own against INDEPENDENT implementations (numpy / scipy), so that a transcription
- * error shared by the product and the oracle cannot pass unnoticed:
- *   - the 6x6 solver of the ICP iteration (csrc/linalg_dev.cuh: pivoted-QR rank test, LLT, rank-reduced
- *     minimum-norm branch, SVD fallback = SolvePossiblyUnderdeterminedLinearSystem, icp_fast.cc:204-254),
- *     run on the device exactly as icp_finish_kernel calls it;
- *   - the BFGS minimiser of the GICP stage (csrc/gicp_host.h: PCL's port of GSL vector_bfgs2 with the
- *     Fletcher line search, parameters of gicp_omp_impl.hpp:218-224), run on a caller-supplied function.
- *   - the host-side scalar pieces of the NDT Newton loop (csrc/ndt_host.h: 6x6 Jacobi SVD solve, pose <-> 6-vector
- *     with Eigen's eulerAngles(0,1,2), Gauss constants), run on the host without a GPU.
- * And one launch shape that is otherwise only reachable through whole alignments:
- *   - sm_knn1 with the scheduling the ICP iteration uses when many alignments are in flight
- *     (queries_per_cta > 256: lockstep root visits, then the lanes of a warp pull parked searches), so the
- *     index sets and squared distances of that path are compared with the oracle's directly. */
+ * nothing in the reference binds these.  They let tests/ drive pieces of PRODUCT code that have no entry point of
+ * their own against INDEPENDENT implementations (numpy / scipy / tests/pyref.py), so that a transcription error
+ * shared by the product and the oracle cannot pass unnoticed — most of them without a GPU:
+ *   host code of the product, over caller-supplied evaluations
+ *     sm_debug_bfgs_minimize   the BFGS minimiser of the GICP stage (csrc/gicp_host.h: PCL's port of GSL
+ *                              vector_bfgs2 with the Fletcher line search, gicp_omp_impl.hpp:218-224)
+ *     sm_debug_ndt_newton      the NDT Newton loop (csrc/ndt_host.h newton_loop, ndt_omp_impl.hpp:81-171)
+ *     sm_debug_gicp_outer      the GICP outer loop (csrc/gicp_host.h outer_loop, gicp_omp_impl.hpp:381-514, :187-246)
+ *     sm_debug_ndt_host        6x6 Jacobi-SVD solve, pose <-> 6-vector with Eigen's eulerAngles(0,1,2), Gauss constants
+ *     sm_debug_gicp_host       applyState, computeRDerivative
+ *   device math of the product compiled for the host (the same __host__ __device__ source the kernels call)
+ *     sm_debug_solve6_host     SolvePossiblyUnderdeterminedLinearSystem (csrc/linalg_dev.cuh, icp_fast.cc:204-254)
+ *     sm_debug_icp_host        per-match normal-equation terms, AngleAxis / quaternion / angularDistance helpers
+ *     sm_debug_ndt_term        one (point, voxel) term of computeDerivatives, pclomp float and stock-PCL double forms
+ *     sm_debug_motion_host     InterpolateTransform(Identity, delta, factor) applied to a point
+ *   on the device
+ *     sm_debug_solve6          the 6x6 solver exactly as icp_finish_kernel calls it
+ *     sm_debug_knn1_batched    sm_knn1 with the scheduling the ICP iteration uses when many alignments are in flight
+ *                              (queries_per_cta > 256: lockstep root visits, then the lanes of a warp pull parked
+ *                              searches), so that path's index sets and squared distances meet the oracle's directly */
 #ifndef SM_B200_DEBUG_H_
 #define SM_B200_DEBUG_H_
 
