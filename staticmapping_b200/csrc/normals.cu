@@ -15,6 +15,38 @@
 namespace smb {
 namespace {
 
+// The leaf routine (cloud_types.cc:73-103): M = sum d d^T and b = sum d over the members in the given order, mean,
+// C = sum (d - mean)(d - mean)^T; dropped if rank(C) + 1 < 3 (:89-91); normal = normalize(M^-1 b) (:93-101).
+// Returns false for a dropped leaf.  __host__ too: the test hook sm_debug_normals_leaf runs this very function.
+__host__ __device__ __forceinline__ bool leaf_plane_fit(const double (*d)[3], int count, double* mean, double* unit) {
+  double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < count; ++i)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) M[r * 3 + c] += d[i][r] * d[i][c];
+  double b[3] = {0, 0, 0};
+  for (int r = 0; r < 3; ++r)
+    for (int i = 0; i < count; ++i) b[r] += d[i][r];
+  for (int r = 0; r < 3; ++r) mean[r] = b[r] / count;
+  double C[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double s = 0.0;
+      for (int i = 0; i < count; ++i) s += (d[i][r] - mean[r]) * (d[i][c] - mean[c]);
+      C[r * 3 + c] = s;
+    }
+  la::PivQR<3> qr;
+  qr.compute(C);
+  if (qr.rank() + 1 < 3) return false;              // :89-91
+  double Minv[9], nrm[3];
+  la::lu_inverse3(M, Minv);                         // :93
+  for (int r = 0; r < 3; ++r)
+    nrm[r] = Minv[r * 3 + 0] * b[0] + Minv[r * 3 + 1] * b[1] + Minv[r * 3 + 2] * b[2];
+  const double sq = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
+  const double len = sqrt(sq);
+  for (int r = 0; r < 3; ++r) unit[r] = (sq > 0.0) ? nrm[r] / len : nrm[r];
+  return true;
+}
+
 __global__ void normals_leaf_kernel(const double* __restrict__ coord, int64_t cstride,
                                     const KdNode* __restrict__ nodes,
                                     const uint32_t* __restrict__ leaf_order, int n, int levels,
@@ -35,40 +67,17 @@ __global__ void normals_leaf_kernel(const double* __restrict__ coord, int64_t cs
     }
   }
   if (count > 7) return;
-  // cloud_types.cc:73-103
-  double d[7][3];
-  double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double d[7][3], mean[3], unit[3];
   for (int i = 0; i < count; ++i) {
     const uint32_t id = leaf_order[first + i];
     for (int r = 0; r < 3; ++r) d[i][r] = coord[r * cstride + id];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) M[r * 3 + c] += d[i][r] * d[i][c];
   }
-  double b[3] = {0, 0, 0}, mean[3];
-  for (int r = 0; r < 3; ++r)
-    for (int i = 0; i < count; ++i) b[r] += d[i][r];
-  for (int r = 0; r < 3; ++r) mean[r] = b[r] / count;
-  double C[9];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
-      double s = 0.0;
-      for (int i = 0; i < count; ++i) s += (d[i][r] - mean[r]) * (d[i][c] - mean[c]);
-      C[r * 3 + c] = s;
-    }
-  la::PivQR<3> qr;
-  qr.compute(C);
-  if (qr.rank() + 1 < 3) return;                    // :89-91
-  double Minv[9], nrm[3];
-  la::lu_inverse3(M, Minv);                         // :93
-  for (int r = 0; r < 3; ++r)
-    nrm[r] = Minv[r * 3 + 0] * b[0] + Minv[r * 3 + 1] * b[1] + Minv[r * 3 + 2] * b[2];
-  const double sq = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
-  const double len = sqrt(sq);
+  if (!leaf_plane_fit(d, count, mean, unit)) return;
   const uint32_t k = leaf_order[first];             // smallest original index of the leaf
   keep[k] = 1u;
   for (int r = 0; r < 3; ++r) {
     out_pts[3 * (int64_t)k + r] = mean[r];
-    out_nrm[3 * (int64_t)k + r] = (sq > 0.0) ? nrm[r] / len : nrm[r];
+    out_nrm[3 * (int64_t)k + r] = unit[r];
   }
 }
 
@@ -124,6 +133,14 @@ compact_scatter_kernel(const uint32_t* __restrict__ keep, int n, const uint32_t*
 }
 
 }  // namespace
+
+// host build of the leaf routine (test hook sm_debug_normals_leaf): members[count][3] in member order
+int normals_debug_leaf_host(const double* members, int count, double* mean, double* unit) {
+  if (count < 1 || count > 7) return -1;
+  double d[7][3];
+  for (int i = 0; i < count; ++i) for (int r = 0; r < 3; ++r) d[i][r] = members[3 * i + r];
+  return leaf_plane_fit(d, count, mean, unit) ? 1 : 0;
+}
 
 // coord: SoA [3][cstride] (un-centred input).  Outputs are AoS 3xM (Eigen layout) in
 // device memory; *m_dev receives M.  tmp_pts/tmp_nrm: AoS 3xN scratch; keep: N u32.

@@ -1287,6 +1287,15 @@ int sm_debug_gicp_outer(sm_debug_gicp_correspond correspond, sm_debug_gicp_cost 
   return SM_OK;
 }
 
+// test hook: the leaf routine of CalculateNormals (normals.cu leaf_plane_fit) compiled for the host
+int sm_debug_normals_leaf(const double* members_3k, int32_t count, double* mean3, double* normal3, int32_t* kept) {
+  if (!members_3k || !mean3 || !normal3 || !kept) return SM_ERR_BAD_ARGUMENT;
+  const int r = normals_debug_leaf_host(members_3k, count, mean3, normal3);
+  if (r < 0) return SM_ERR_BAD_ARGUMENT;
+  *kept = r;
+  return SM_OK;
+}
+
 // test hook: the host pieces of the GICP stage other than the minimiser (csrc/gicp_host.h), no GPU involved
 int sm_debug_gicp_host(int32_t op, const double* in, double* out) {
   if (!in || !out) return SM_ERR_BAD_ARGUMENT;

@@ -538,3 +538,54 @@ def test_gicp_outer_loop_of_the_product_over_the_numpy_per_point_work():
     T = final.reshape(4, 4).T
     dt, dr = scenes.se3_error(o["result"], T)
     assert dt < 1e-5 and dr < 1e-5, (dt, dr)
+
+
+# ---------------------------------------------------------------------------------- CalculateNormals leaf (no GPU)
+def _leaf_host(members):
+    lib = _lib.lib()
+    m = np.ascontiguousarray(members, dtype=np.float64)
+    mean = np.zeros(3); nrm = np.zeros(3); kept = C.c_int32(-1)
+    rc = lib.sm_debug_normals_leaf(m.ctypes.data, m.shape[0], mean.ctypes.data, nrm.ctypes.data, C.byref(kept))
+    return rc, kept.value, mean, nrm
+
+
+def test_calculate_normals_leaf_of_the_product_against_numpy():
+    """csrc/normals.cu leaf_plane_fit (the body of normals_leaf_kernel) on the host: mean, rank test and the unconstrained
+    least-squares normal normalize(M^-1 b) of cloud_types.cc:73-103 against numpy, on plane patches, generic and
+    degenerate leaves; and leaf by leaf against the oracle's CalculateNormals on a whole cloud."""
+    rng = np.random.default_rng(8)
+    for count in range(1, 8):
+        for _ in range(40):
+            uv = rng.uniform(-0.5, 0.5, size=(count, 2))
+            n_true = rng.normal(size=3); n_true /= np.linalg.norm(n_true)
+            e1 = np.cross(n_true, [1.0, 0.3, 0.2]); e1 /= np.linalg.norm(e1); e2 = np.cross(n_true, e1)
+            pts = 12.0 * n_true + rng.normal(size=3) + uv[:, :1] * e1 + uv[:, 1:] * e2 + rng.normal(scale=1e-3, size=(count, 3))
+            rc, kept, mean, nrm = _leaf_host(pts)
+            assert rc == 0
+            c = (pts - pts.mean(0)).T @ (pts - pts.mean(0))
+            want_kept = int(np.linalg.matrix_rank(c) + 1 >= 3)
+            assert kept == want_kept
+            if kept:
+                assert np.allclose(mean, pts.sum(0) / count, rtol=0, atol=1e-13)
+                want = np.linalg.solve(pts.T @ pts, pts.sum(0)); want /= np.linalg.norm(want)
+                assert np.allclose(nrm, want, rtol=0, atol=1e-6) and abs(np.linalg.norm(nrm) - 1) < 1e-14
+                if count >= 4:
+                    assert abs(abs(nrm @ n_true) - 1) < 1e-3          # and it is the patch's plane
+    # collinear and coincident members are dropped (rank(C) + 1 < 3)
+    line = np.outer(np.arange(5.0), [1.0, 2.0, -1.0]) + 7.0
+    assert _leaf_host(line)[1] == 0 and _leaf_host(np.tile([[3.0, 4.0, 5.0]], (4, 1)))[1] == 0
+    assert _leaf_host(np.zeros((8, 3)))[0] == -1                      # more than 7 members is not a leaf
+    # a whole cloud: every leaf of the Python recursion, through the product's leaf routine, equals the oracle's output
+    import pyref
+    import scenes
+    _, tgt, _ = scenes.corner_pair()
+    p_o, n_o = O.calculate_normals(tgt)
+    _, _, leaves = pyref.calculate_normals(tgt)
+    rows = []
+    for leaf in leaves:
+        rc, kept, mean, nrm = _leaf_host(tgt[leaf])
+        if kept:
+            rows.append((leaf[0], mean, nrm))
+    rows.sort(key=lambda r: r[0])
+    assert np.array_equal(np.array([r[1] for r in rows]), p_o)        # bit-identical: same source, same operation order
+    assert np.array_equal(np.array([r[2] for r in rows]), n_o)
