@@ -12,6 +12,7 @@
  *   device math of the product compiled for the host (the same __host__ __device__ source the kernels call)
  *     sm_debug_solve6_host     SolvePossiblyUnderdeterminedLinearSystem (csrc/linalg_dev.cuh, icp_fast.cc:204-254)
  *     sm_debug_icp_host        per-match normal-equation terms, AngleAxis / quaternion / angularDistance helpers
+ *     sm_debug_ndt_leaf        one leaf of the NDT target grid: covariance, eigenvalue inflation, inverse
  *     sm_debug_ndt_term        one (point, voxel) term of computeDerivatives, pclomp float and stock-PCL double forms
  *     sm_debug_motion_host     InterpolateTransform(Identity, delta, factor) applied to a point
  *     sm_debug_normals_leaf    the leaf plane fit of CalculateNormals (cloud_types.cc:73-103)
@@ -107,6 +108,13 @@ int sm_debug_normals_leaf(const double* members_3k, int32_t count, double* mean_
 /* sm_motion_compensation's arithmetic on the host (csrc/motion.cu make_params + motion_point): packed
  * {x, y, z, intensity, factor} float records in and out; SM_ERR_BAD_ARGUMENT if a factor is outside [0, 1]. */
 int sm_debug_motion_host(const float* points_5n, int64_t n, const double* delta_4x4, float* out_5n);
+
+/* One leaf of VoxelGridCovariance::applyFilter (voxel_grid_covariance_omp_impl.hpp:209-366; csrc/ndt.cu finish_leaf
+ * compiled for the host): the n points of a voxel in input order -> mean, inverse covariance (zero when the leaf has
+ * fewer than min_points points or fails the eigenvalue test), float centroid, nr_points (-1 = invalid covariance),
+ * searchable. */
+int sm_debug_ndt_leaf(const float* points_3n, int32_t n, int32_t min_points, double eig_mult, double* mean_3,
+                      double* icov_9, float* centroid_3, int32_t* nr_points, int32_t* searchable);
 
 /* One (point, voxel) term of computeDerivatives (ndt_omp_impl.hpp:397-438 + :483-535; f64_math = 1: the stock PCL
  * double form NdtWithGicp uses): csrc/ndt.cu's update_derivatives compiled for the host, evaluation tables built by

@@ -80,6 +80,7 @@ SIGNATURES = {
     "sm_debug_gicp_host": (C.c_int, [C.c_int32, _VP, _VP]),
     "sm_debug_motion_host": (C.c_int, [_VP, C.c_int64, _DP, _VP]),
     "sm_debug_icp_host": (C.c_int, [C.c_int32, _VP, C.c_int64, _VP]),
+    "sm_debug_ndt_leaf": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sm_debug_ndt_term": (C.c_int, [_VP, C.c_double, C.c_float, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
     "sm_debug_ndt_host": (C.c_int, [C.c_int32, _VP, _VP]),
     "sm_debug_knn1_batched": (C.c_int, [C.c_int, _VP, C.c_int64, _VP, C.c_int64, C.c_double, C.c_int, C.c_int32, _VP, _VP]),

@@ -179,6 +179,9 @@ struct NdtEvalParams {      // everything one computeDerivatives call needs, by 
 uint32_t ndt_table_size(int nt);
 // host build of the leaf plane fit of normals.cu (test hook sm_debug_normals_leaf): 1 kept, 0 dropped, < 0 bad count
 int normals_debug_leaf_host(const double* members, int count, double* mean, double* unit);
+// host build of one target-grid leaf of ndt.cu (test hook sm_debug_ndt_leaf)
+void ndt_debug_leaf_host(const float* pts, int n, int min_points, double eig_mult, double* mean3, double* icov9,
+                         float* centroid3, int* nr_points, int* searchable);
 // host build of the per-(point, voxel) derivative term of ndt.cu (test hook sm_debug_ndt_term)
 void ndt_debug_term_host(const NdtEvalParams& P, const float* x_orig, const float* x_trans, const double* mean,
                          const double* icov, double* out43);

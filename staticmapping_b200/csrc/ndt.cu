@@ -143,7 +143,7 @@ ndt_heads_scatter_kernel(const uint64_t* __restrict__ keys, int n, const uint32_
 }
 
 // ---- per-voxel statistics (_impl.hpp:226-237, 283-366) --------------------------------------
-__device__ __forceinline__ void inverse3_cofactor(const double* m, double* inv) {
+__host__ __device__ __forceinline__ void inverse3_cofactor(const double* m, double* inv) {
   const double c00 = m[4] * m[8] - m[5] * m[7];
   const double c10 = m[5] * m[6] - m[3] * m[8];
   const double c20 = m[3] * m[7] - m[4] * m[6];
@@ -169,6 +169,59 @@ __global__ void ndt_gather_kernel(const float* __restrict__ pts, const uint32_t*
 }
 
 // pts: the target points ALREADY in voxel order (ndt_gather_kernel), so a voxel is a contiguous run
+// Second pass of applyFilter for one leaf (voxel_grid_covariance_omp_impl.hpp:283-366) from its running sums: sum x,
+// cov = I + sum x x^T (Leaf() starts cov_ as identity), float centroid sum, point count.  __host__ too: the test hook
+// sm_debug_ndt_leaf runs this very function.
+__host__ __device__ __forceinline__ void finish_leaf(int n, const double* sum, const double* cov, const float* cen,
+                                                     int min_points, double eig_mult, NdtLeaf* out_p) {
+  NdtLeaf& out = *out_p;
+  out.pad = 0;
+  out.nr_points = n; out.searchable = 0;
+  for (int k = 0; k < 9; ++k) out.icov[k] = 0.0;
+  for (int d = 0; d < 3; ++d) { out.centroid[d] = cen[d] / (float)n; out.mean[d] = sum[d] / (double)n; }
+  if (n >= min_points) {
+    out.searchable = 1;
+    double cv[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        cv[r * 3 + c] = (cov[r * 3 + c] - 2 * (sum[r] * out.mean[c])) / (double)n + out.mean[r] * out.mean[c];
+    const double scale = (n - 1.0) / n;
+    for (int k = 0; k < 9; ++k) cv[k] *= scale;
+    double w[3], V[9];
+    la::jacobi_eig_sym(cv, 3, w, V);
+    int ord[3] = {0, 1, 2};
+    for (int a = 0; a < 3; ++a)
+      for (int b = a + 1; b < 3; ++b)
+        if (w[ord[b]] < w[ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+    double ev[3], E[9];
+    for (int a = 0; a < 3; ++a) {
+      ev[a] = w[ord[a]];
+      for (int r = 0; r < 3; ++r) E[r * 3 + a] = V[r * 3 + ord[a]];
+    }
+    if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+      out.nr_points = -1;
+    } else {
+      const double min_ev = eig_mult * ev[2];
+      if (ev[0] < min_ev) {
+        ev[0] = min_ev;
+        if (ev[1] < min_ev) ev[1] = min_ev;
+        double Einv[9], ED[9];
+        inverse3_cofactor(E, Einv);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) ED[r * 3 + c] = E[r * 3 + c] * ev[c];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            cv[r * 3 + c] = (ED[r * 3 + 0] * Einv[0 * 3 + c] + ED[r * 3 + 1] * Einv[1 * 3 + c]) + ED[r * 3 + 2] * Einv[2 * 3 + c];
+      }
+      inverse3_cofactor(cv, out.icov);
+      const double inf = (double)INFINITY;
+      double mx = -inf, mn = inf;
+      for (int k = 0; k < 9; ++k) { mx = fmax(mx, out.icov[k]); mn = fmin(mn, out.icov[k]); }
+      if (mx == inf || mn == -inf) out.nr_points = -1;
+    }
+  }
+}
+
 __global__ void ndt_leaf_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ order,
                                 const uint32_t* __restrict__ voxel_start, const NdtGrid* __restrict__ grid,
                                 NdtLeaf* __restrict__ leaves, int min_points, double eig_mult) {
@@ -241,50 +294,7 @@ __global__ void ndt_leaf_kernel(const float* __restrict__ pts, const uint32_t* _
   }
   if (lane != 0) return;
   NdtLeaf out;
-  out.nr_points = n; out.searchable = 0;
-  for (int k = 0; k < 9; ++k) out.icov[k] = 0.0;
-  for (int d = 0; d < 3; ++d) { out.centroid[d] = cen[d] / (float)n; out.mean[d] = sum[d] / (double)n; }
-  if (n >= min_points) {
-    out.searchable = 1;
-    double cv[9];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c)
-        cv[r * 3 + c] = (cov[r * 3 + c] - 2 * (sum[r] * out.mean[c])) / (double)n + out.mean[r] * out.mean[c];
-    const double scale = (n - 1.0) / n;
-    for (int k = 0; k < 9; ++k) cv[k] *= scale;
-    double w[3], V[9];
-    la::jacobi_eig_sym(cv, 3, w, V);
-    int ord[3] = {0, 1, 2};
-    for (int a = 0; a < 3; ++a)
-      for (int b = a + 1; b < 3; ++b)
-        if (w[ord[b]] < w[ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
-    double ev[3], E[9];
-    for (int a = 0; a < 3; ++a) {
-      ev[a] = w[ord[a]];
-      for (int r = 0; r < 3; ++r) E[r * 3 + a] = V[r * 3 + ord[a]];
-    }
-    if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
-      out.nr_points = -1;
-    } else {
-      const double min_ev = eig_mult * ev[2];
-      if (ev[0] < min_ev) {
-        ev[0] = min_ev;
-        if (ev[1] < min_ev) ev[1] = min_ev;
-        double Einv[9], ED[9];
-        inverse3_cofactor(E, Einv);
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) ED[r * 3 + c] = E[r * 3 + c] * ev[c];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c)
-            cv[r * 3 + c] = (ED[r * 3 + 0] * Einv[0 * 3 + c] + ED[r * 3 + 1] * Einv[1 * 3 + c]) + ED[r * 3 + 2] * Einv[2 * 3 + c];
-      }
-      inverse3_cofactor(cv, out.icov);
-      const double inf = __longlong_as_double(0x7ff0000000000000ll);
-      double mx = -inf, mn = inf;
-      for (int k = 0; k < 9; ++k) { mx = fmax(mx, out.icov[k]); mn = fmin(mn, out.icov[k]); }
-      if (mx == inf || mn == -inf) out.nr_points = -1;
-    }
-  }
+  finish_leaf(n, sum, cov, cen, min_points, eig_mult, &out);
   leaves[v] = out;
 }
 
@@ -569,6 +579,28 @@ ndt_fitness_kernel(const float* __restrict__ src, int n, NdtEvalParams P, const 
 }
 
 }  // namespace
+
+// Host build of one leaf of the target grid (test hook sm_debug_ndt_leaf): the running sums are formed here in input
+// order (the kernel forms them with one warp per voxel, in the same order), the rest is finish_leaf.
+void ndt_debug_leaf_host(const float* pts, int n, int min_points, double eig_mult, double* mean3, double* icov9,
+                         float* centroid3, int* nr_points, int* searchable) {
+  double sum[3] = {0, 0, 0}, cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float cen[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    const double x[3] = {(double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2]};
+    for (int r = 0; r < 3; ++r) {
+      sum[r] += x[r];
+      cen[r] += pts[3 * i + r];
+      for (int c = 0; c < 3; ++c) cov[r * 3 + c] += x[r] * x[c];
+    }
+  }
+  NdtLeaf leaf;
+  finish_leaf(n, sum, cov, cen, min_points, eig_mult, &leaf);
+  for (int d = 0; d < 3; ++d) { mean3[d] = leaf.mean[d]; centroid3[d] = leaf.centroid[d]; }
+  for (int q = 0; q < 9; ++q) icov9[q] = leaf.icov[q];
+  *nr_points = leaf.nr_points;
+  *searchable = leaf.searchable;
+}
 
 // Host build of the per-(point, voxel) term (test hook sm_debug_ndt_term): out[0] = score increment,
 // out[1..6] = gradient term, out[7..42] = Hessian term (row-major) of ONE neighbour voxel.

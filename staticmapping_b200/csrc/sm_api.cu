@@ -1340,6 +1340,16 @@ int sm_debug_icp_host(int32_t op, const double* in, int64_t n, double* out) {
   }
 }
 
+// test hook: one leaf of the NDT target grid (ndt.cu finish_leaf: covariance, eigen-inflation, inverse) on the host
+int sm_debug_ndt_leaf(const float* points_3n, int32_t n, int32_t min_points, double eig_mult, double* mean3,
+                      double* icov9, float* centroid3, int32_t* nr_points, int32_t* searchable) {
+  if (!points_3n || n <= 0 || !mean3 || !icov9 || !centroid3 || !nr_points || !searchable) return SM_ERR_BAD_ARGUMENT;
+  int np = 0, se = 0;
+  ndt_debug_leaf_host(points_3n, n, min_points, eig_mult, mean3, icov9, centroid3, &np, &se);
+  *nr_points = np; *searchable = se;
+  return SM_OK;
+}
+
 // test hook: the per-(point, voxel) derivative term of ndt.cu (update_derivatives / update_derivatives_f64, the
 // functions ndt_derivatives_kernel calls) compiled for the HOST, with the evaluation parameters built by the
 // product's own host code (ndt_host.h) for pose vector p — no GPU involved

@@ -589,3 +589,53 @@ def test_calculate_normals_leaf_of_the_product_against_numpy():
     rows.sort(key=lambda r: r[0])
     assert np.array_equal(np.array([r[1] for r in rows]), p_o)        # bit-identical: same source, same operation order
     assert np.array_equal(np.array([r[2] for r in rows]), n_o)
+
+
+# ---------------------------------------------------------------------------------- NDT target-grid leaf (no GPU)
+def test_ndt_leaf_of_the_product_against_numpy_and_the_oracle():
+    """csrc/ndt.cu finish_leaf (lane 0 of ndt_leaf_kernel: covariance with the identity-initialised cov_, eigenvalue
+    test and inflation, inverse) on the host, for every voxel of a lidar target: against tests/pyref.py's numpy grid
+    (eigh / inv) and against the oracle's leaves."""
+    import pyref
+    import scenes
+    _, sub, _ = scenes.lidar_pair(pair=2)
+    t32 = np.ascontiguousarray(sub.astype(np.float32))
+    grid = pyref.NdtGrid(t32)
+    v = O.ndt_voxels(t32)
+    # the points of every voxel in input order (the same grouping pyref.NdtGrid does)
+    inv = np.float32(1.0)
+    min_b = np.floor(t32.min(axis=0) * inv).astype(np.int64)
+    div_b = np.floor(t32.max(axis=0) * inv).astype(np.int64) - min_b + 1
+    idx = (np.floor(t32 * inv) - min_b.astype(np.float32)).astype(np.int64) @ np.array([1, div_b[0], div_b[0] * div_b[1]])
+    order = np.argsort(idx, kind="stable")
+    sidx = idx[order]
+    starts = np.flatnonzero(np.r_[True, sidx[1:] != sidx[:-1]]); ends = np.r_[starts[1:], sidx.size]
+    assert len(starts) == len(grid.leaf_idx) == len(v["idx"])
+    lib = _lib.lib()
+    mean = np.zeros(3); icov = np.zeros(9); cen = np.zeros(3, np.float32); npts = C.c_int32(); srch = C.c_int32()
+    for k, (s0, s1) in enumerate(zip(starts, ends)):
+        pts = np.ascontiguousarray(t32[order[s0:s1]])
+        assert lib.sm_debug_ndt_leaf(pts.ctypes.data, pts.shape[0], 6, 0.01, mean.ctypes.data, icov.ctypes.data,
+                                     cen.ctypes.data, C.byref(npts), C.byref(srch)) == 0
+        assert npts.value == grid.n[k] == v["n"][k] and srch.value == grid.searchable[k] == v["searchable"][k]
+        assert np.array_equal(cen, grid.centroid[k]) and np.array_equal(cen, v["centroid"][k])
+        assert np.allclose(mean, grid.mean[k], rtol=0, atol=1e-12) and np.array_equal(mean, v["mean"][k])
+        if npts.value >= 6:
+            ic = icov.reshape(3, 3)
+            assert np.all(np.abs(ic - grid.icov[k]) <= 1e-8 * np.abs(grid.icov[k]).max())
+            assert np.array_equal(ic, v["icov"][k])        # same source order as the oracle: the same bits
+    # the eigenvalue-inflation branch needs a dense flat voxel: the identity that Leaf() leaves in cov_ adds 1/n to
+    # every eigenvalue (n = 5 000 -> 2e-4 < 0.01 * lambda_2)
+    rng = np.random.default_rng(2)
+    flat = np.stack([rng.random(5000), rng.random(5000), 0.5 + 1e-4 * rng.normal(size=5000)], axis=1).astype(np.float32)
+    assert lib.sm_debug_ndt_leaf(flat.ctypes.data, 5000, 6, 0.01, mean.ctypes.data, icov.ctypes.data, cen.ctypes.data,
+                                 C.byref(npts), C.byref(srch)) == 0
+    x = flat.astype(np.float64); n = 5000
+    sx = x.sum(0); m = sx / n
+    cov = ((np.eye(3) + x.T @ x) - 2.0 * np.outer(sx, m)) / n + np.outer(m, m)
+    cov *= (n - 1.0) / n
+    w, V = np.linalg.eigh(cov)
+    assert w[0] < 0.01 * w[2] and w[1] > 0.01 * w[2]       # only the smallest one is raised
+    w[0] = 0.01 * w[2]
+    want = np.linalg.inv(V @ np.diag(w) @ np.linalg.inv(V))
+    assert npts.value == n and np.all(np.abs(icov.reshape(3, 3) - want) <= 1e-9 * np.abs(want).max())
