@@ -70,3 +70,29 @@ def test_lidar_geometry_and_the_float_lower_bound_mask_is_a_superset():
             off = q[m.dim[n]] - m.cut[n]
             if (off * off) * me2 < st["head"]:
                 assert mask & (1 << a)
+
+
+def _adversarial_clouds():
+    rng = np.random.default_rng(0)
+    yield "grid", np.stack(np.meshgrid(np.arange(12.0), np.arange(9.0), np.arange(5.0)), -1).reshape(-1, 3)
+    yield "line", np.stack([np.linspace(-3, 3, 700), np.zeros(700), np.zeros(700)], 1)
+    yield "identical", np.tile([[1.5, -2.0, 0.25]], (100, 1))
+    yield "signed-zeros", np.stack([rng.integers(-20, 20, 900).astype(float), rng.integers(-20, 20, 900).astype(float),
+                                    np.where(rng.random(900) < 0.5, -0.0, 0.0)], 1)
+    yield "huge-range", rng.normal(size=(1500, 3)) * np.array([1e6, 1e-6, 1.0])
+    yield "quantised", np.round(rng.normal(size=(3000, 3)) * 4) / 4
+    yield "two-clusters", np.concatenate([rng.normal(size=(800, 3)) * 0.01, rng.normal(size=(800, 3)) * 0.01 + 100])
+
+
+@pytest.mark.parametrize("name,T", list(_adversarial_clouds()), ids=[n for n, _ in _adversarial_clouds()])
+def test_adversarial_clouds_all_four_statements_agree(name, T):
+    # grids and quantised coordinates (ties in every split), degenerate extents (argmax of all-zero extents is axis 0),
+    # both zeros, twelve orders of magnitude between the axes: oracle, Python recursion, kernel formulation, warp-pulled
+    rng = np.random.default_rng(len(name))
+    step = max(1, len(T) // 150)
+    Q = np.concatenate([T[::step] + rng.normal(size=(len(T[::step]), 3)) * 0.3, rng.normal(size=(100, 3)) * np.abs(T).max()])
+    m = GpuKnnModel(T)
+    for eps in (0.0, 3.16):
+        ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
+        for ids, d2 in (pyref.PyNabo(T).knn1(Q, eps), m.knn1(Q, eps), m.knn1_batched(Q, eps)):
+            assert np.array_equal(ids, ids_o) and np.array_equal(d2, d2_o)
