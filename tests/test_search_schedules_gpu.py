@@ -99,3 +99,29 @@ def test_signed_zero_coordinates_split_like_the_oracle():
         for qpc in (0, 1024):
             ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, queries_per_cta=qpc)
             assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
+
+
+def _adversarial_clouds():
+    rng = np.random.default_rng(0)
+    yield "grid", np.stack(np.meshgrid(np.arange(12.0), np.arange(9.0), np.arange(5.0)), -1).reshape(-1, 3)
+    yield "line", np.stack([np.linspace(-3, 3, 700), np.zeros(700), np.zeros(700)], 1)
+    yield "identical", np.tile([[1.5, -2.0, 0.25]], (100, 1))
+    yield "signed-zeros", np.stack([rng.integers(-20, 20, 900).astype(float), rng.integers(-20, 20, 900).astype(float),
+                                    np.where(rng.random(900) < 0.5, -0.0, 0.0)], 1)
+    yield "huge-range", rng.normal(size=(1500, 3)) * np.array([1e6, 1e-6, 1.0])
+    yield "quantised", np.round(rng.normal(size=(3000, 3)) * 4) / 4
+    yield "two-clusters", np.concatenate([rng.normal(size=(800, 3)) * 0.01, rng.normal(size=(800, 3)) * 0.01 + 100])
+
+
+@pytest.mark.parametrize("name,T", list(_adversarial_clouds()), ids=[n for n, _ in _adversarial_clouds()])
+def test_adversarial_clouds(name, T):
+    # the clouds of tests/test_search_formulation_model.py (ties in every split, degenerate extents, both zeros, twelve
+    # orders of magnitude between the axes) through the kernels, both launch shapes
+    rng = np.random.default_rng(len(name))
+    step = max(1, len(T) // 150)
+    Q = np.concatenate([T[::step] + rng.normal(size=(len(T[::step]), 3)) * 0.3, rng.normal(size=(100, 3)) * np.abs(T).max()])
+    for eps in (0.0, 3.16):
+        ids_o, d2_o = O.knn1(T, Q, epsilon=eps)
+        for qpc in (0, 512):
+            ids_g, d2_g = smb.knn1(T, Q, epsilon=eps, queries_per_cta=qpc)
+            assert np.array_equal(ids_g, ids_o) and np.array_equal(d2_g, d2_o)
