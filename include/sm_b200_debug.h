@@ -14,6 +14,7 @@
  *     sm_debug_icp_host        per-match normal-equation terms, AngleAxis / quaternion / angularDistance helpers
  *     sm_debug_ndt_leaf        one leaf of the NDT target grid: covariance, eigenvalue inflation, inverse
  *     sm_debug_ndt_term        one (point, voxel) term of computeDerivatives, pclomp float and stock-PCL double forms
+ *     sm_debug_gicp_point      Mahalanobis matrix of a correspondence, one correspondence's cost / gradient terms
  *     sm_debug_motion_host     InterpolateTransform(Identity, delta, factor) applied to a point
  *     sm_debug_normals_leaf    the leaf plane fit of CalculateNormals (cloud_types.cc:73-103)
  *   on the device
@@ -94,6 +95,12 @@ typedef int (*sm_debug_gicp_correspond)(const double* transformation_4x4, const 
 typedef int (*sm_debug_gicp_cost)(const double* T_4x4, double* S_13, void* user);
 int sm_debug_gicp_outer(sm_debug_gicp_correspond correspond, sm_debug_gicp_cost cost, void* user,
                         const double* guess_4x4, double* final_4x4, int32_t* iterations, int32_t* bfgs_evaluations);
+
+/* The per-point arithmetic of the GICP kernels compiled for the host (csrc/gicp.cu mahalanobis / cost_terms):
+ *   op 0: M = (R C1 R^T + C2)^-1, gicp_omp_impl.hpp:450-457    in = R[9], C1[9], C2[9] row-major     out = M[9]
+ *   op 1: one correspondence of the functor, :341-377          in = T[16], base[16] col-major, p_src[3], p_tgt[3], M[9]
+ *         out = {res^T M res, (M res)[3], ((base p_src)(M res)^T)[9] row-major} */
+int sm_debug_gicp_point(int32_t op, const double* in, double* out);
 
 /* Host pieces of the GICP stage besides the minimiser (csrc/gicp_host.h):
  *   op 0: applyState, gicp_omp_impl.hpp:516-527   in = T[16] col-major, x[6]      out = T'[16] (float arithmetic)

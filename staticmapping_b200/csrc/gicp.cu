@@ -238,12 +238,12 @@ gicp_knn20_cov_kernel(const float* __restrict__ cloud, int n, const KdNode* __re
 }
 
 // ---- correspondences + Mahalanobis ---------------------------------------------------------------
-__device__ __forceinline__ void mulpt_f(const float* T, const float* p, float* out) {
+__host__ __device__ __forceinline__ void mulpt_f(const float* T, const float* p, float* out) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) out[r] = ((T[r] * p[0] + T[r + 4] * p[1]) + T[r + 8] * p[2]) + T[r + 12] * 1.0f;
 }
 
-__device__ __forceinline__ void inverse3(const double* m, double* inv) {
+__host__ __device__ __forceinline__ void inverse3(const double* m, double* inv) {
   const double c00 = m[4] * m[8] - m[5] * m[7];
   const double c10 = m[5] * m[6] - m[3] * m[8];
   const double c20 = m[3] * m[7] - m[4] * m[6];
@@ -256,6 +256,18 @@ __device__ __forceinline__ void inverse3(const double* m, double* inv) {
   inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet;
   inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet;
   inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
+}
+
+// M_i = (R C1 R^T + C2)^-1 (gicp_omp_impl.hpp:450-457); R row-major.  __host__ too (test hook sm_debug_gicp_point).
+__host__ __device__ __forceinline__ void mahalanobis(const double* R, const double* C1, const double* C2, double* out) {
+  double M[9], tmp[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      M[r * 3 + c] = (R[r * 3] * C1[c] + R[r * 3 + 1] * C1[3 + c]) + R[r * 3 + 2] * C1[6 + c];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      tmp[r * 3 + c] = ((M[r * 3] * R[c * 3] + M[r * 3 + 1] * R[c * 3 + 1]) + M[r * 3 + 2] * R[c * 3 + 2]) + C2[r * 3 + c];
+  inverse3(tmp, out);
 }
 
 __global__ void __launch_bounds__(128)
@@ -278,16 +290,7 @@ gicp_correspond_kernel(const float* __restrict__ src, int ns, const float* __res
       const float dx = q[0] - t[0], dy = q[1] - t[1], dz = q[2] - t[2];
       const float d = (dx * dx + dy * dy) + dz * dz;
       if ((double)d < P.dist_threshold) {                // :448
-        const double* C1 = cov_s + 9 * (int64_t)i;
-        const double* C2 = cov_t + 9 * (int64_t)j;
-        double M[9], tmp[9];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c)
-            M[r * 3 + c] = (P.R[r * 3] * C1[c] + P.R[r * 3 + 1] * C1[3 + c]) + P.R[r * 3 + 2] * C1[6 + c];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c)
-            tmp[r * 3 + c] = ((M[r * 3] * P.R[c * 3] + M[r * 3 + 1] * P.R[c * 3 + 1]) + M[r * 3 + 2] * P.R[c * 3 + 2]) + C2[r * 3 + c];
-        inverse3(tmp, maha + 9 * (int64_t)i);
+        mahalanobis(P.R, cov_s + 9 * (int64_t)i, cov_t + 9 * (int64_t)j, maha + 9 * (int64_t)i);
         valid = true;
       }
     }
@@ -299,6 +302,22 @@ gicp_correspond_kernel(const float* __restrict__ src, int ns, const float* __res
 
 // ---- cost / gradient ------------------------------------------------------------------------------
 constexpr int kCostSums = 13;
+
+// one correspondence of OptimizationFunctorWithIndices (gicp_omp_impl.hpp:341-377): acc[0] = res^T M res,
+// acc[1..3] = M res, acc[4..12] = (base p)(M res)^T row-major.  __host__ too (test hook sm_debug_gicp_point).
+__host__ __device__ __forceinline__ void cost_terms(const float* T, const float* base, const float* ps, const float* pt,
+                                                    const double* M, double* acc) {
+  float pp[3], pb[3];
+  mulpt_f(T, ps, pp);
+  const double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
+  double temp[3];
+  for (int r = 0; r < 3; ++r) temp[r] = (M[r * 3] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
+  acc[0] = (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
+  for (int r = 0; r < 3; ++r) acc[1 + r] = temp[r];
+  mulpt_f(base, ps, pb);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) acc[4 + r * 3 + c] = (double)pb[r] * temp[c];
+}
 
 __global__ void __launch_bounds__(256)
 gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict__ tgt, GicpCostParams P,
@@ -314,19 +333,7 @@ gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict_
   if (i < ns) {
     const int j = match[i];
     if (j >= 0) {
-      const float* ps = src + 3 * (int64_t)i;
-      const float* pt = tgt + 3 * (int64_t)j;
-      float pp[3], pb[3];
-      mulpt_f(P.T, ps, pp);
-      const double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
-      const double* M = maha + 9 * (int64_t)i;
-      double temp[3];
-      for (int r = 0; r < 3; ++r) temp[r] = (M[r * 3] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
-      acc[0] = (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
-      for (int r = 0; r < 3; ++r) acc[1 + r] = temp[r];
-      mulpt_f(P.base, ps, pb);
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) acc[4 + r * 3 + c] = (double)pb[r] * temp[c];
+      cost_terms(P.T, P.base, src + 3 * (int64_t)i, tgt + 3 * (int64_t)j, maha + 9 * (int64_t)i, acc);
     }
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -368,6 +375,15 @@ gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict_
 }
 
 }  // namespace
+
+// host builds of the per-point GICP arithmetic (test hook sm_debug_gicp_point)
+void gicp_debug_mahalanobis_host(const double* R, const double* C1, const double* C2, double* out9) {
+  mahalanobis(R, C1, C2, out9);
+}
+void gicp_debug_cost_terms_host(const float* T, const float* base, const float* ps, const float* pt, const double* M,
+                                double* acc13) {
+  cost_terms(T, base, ps, pt, M, acc13);
+}
 
 size_t approx_ws_bytes(int n) {
   const int64_t st = (n + 63) & ~63;

@@ -222,6 +222,10 @@ struct GicpCostParams {     // one BFGS function evaluation (:255-377)
   float T[16];              // base with applyState(x)
   float base[16];
 };
+// host builds of gicp.cu's per-point arithmetic (test hook sm_debug_gicp_point)
+void gicp_debug_mahalanobis_host(const double* R, const double* C1, const double* C2, double* out9);
+void gicp_debug_cost_terms_host(const float* T, const float* base, const float* ps, const float* pt, const double* M,
+                                double* acc13);
 size_t approx_ws_bytes(int n);
 int approx_voxel_grid(const float* pts, int n, float leaf, void* ws_base, float* out, uint32_t* n_out_dev,
                       cudaStream_t stream);

@@ -1296,6 +1296,22 @@ int sm_debug_normals_leaf(const double* members_3k, int32_t count, double* mean3
   return SM_OK;
 }
 
+// test hook: the per-point arithmetic of the GICP kernels (gicp.cu mahalanobis / cost_terms) compiled for the host
+int sm_debug_gicp_point(int32_t op, const double* in, double* out) {
+  if (!in || !out) return SM_ERR_BAD_ARGUMENT;
+  switch (op) {
+    case 0: gicp_debug_mahalanobis_host(in, in + 9, in + 18, out); return SM_OK;   // in = R[9], C1[9], C2[9] row-major
+    case 1: {   // in = T[16], base[16] (col-major, cast to float), p_src[3], p_tgt[3] (cast to float), M[9]
+      float T[16], base[16], ps[3], pt[3];
+      for (int i = 0; i < 16; ++i) { T[i] = (float)in[i]; base[i] = (float)in[16 + i]; }
+      for (int i = 0; i < 3; ++i) { ps[i] = (float)in[32 + i]; pt[i] = (float)in[35 + i]; }
+      gicp_debug_cost_terms_host(T, base, ps, pt, in + 38, out);
+      return SM_OK;
+    }
+    default: return SM_ERR_BAD_ARGUMENT;
+  }
+}
+
 // test hook: the host pieces of the GICP stage other than the minimiser (csrc/gicp_host.h), no GPU involved
 int sm_debug_gicp_host(int32_t op, const double* in, double* out) {
   if (!in || !out) return SM_ERR_BAD_ARGUMENT;

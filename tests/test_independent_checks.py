@@ -639,3 +639,40 @@ def test_ndt_leaf_of_the_product_against_numpy_and_the_oracle():
     w[0] = 0.01 * w[2]
     want = np.linalg.inv(V @ np.diag(w) @ np.linalg.inv(V))
     assert npts.value == n and np.all(np.abs(icov.reshape(3, 3) - want) <= 1e-9 * np.abs(want).max())
+
+
+# ---------------------------------------------------------------------------------- GICP per-point math (no GPU)
+def test_gicp_per_point_arithmetic_of_the_product_against_numpy():
+    """csrc/gicp.cu mahalanobis / cost_terms (the bodies of gicp_correspond_kernel and gicp_cost_kernel) on the host:
+    summed over the correspondences of a scene they give tests/pyref.py's Mahalanobis matrices and the oracle's cost and
+    gradient (through the product's own r_derivative)."""
+    import pyref
+    import scenes
+    src, sub, _ = scenes.lidar_pair(pair=1)
+    s = O.approx_voxel_grid(src.astype(np.float32), 0.2)[::3].copy()
+    t = O.approx_voxel_grid(sub.astype(np.float32), 0.2)[::3].copy()
+    cs, ct = pyref.gicp_covariances(s), pyref.gicp_covariances(t)
+    from staticmapping_b200 import synth
+    guess = synth.se3_from_rpy_t(0.01, -0.005, 0.02, (0.2, -0.1, 0.03)).astype(np.float32)
+    tr = synth.se3_from_rpy_t(-0.002, 0.003, -0.004, (0.02, 0.01, -0.01)).astype(np.float32)
+    x = np.array([0.03, -0.02, 0.01, 0.004, -0.006, 0.008])
+    si, ti, M = pyref.gicp_correspond(s, t, guess, tr, cs, ct)
+    R = (tr.astype(np.float64) @ guess.astype(np.float64))[:3, :3]
+    lib = _lib.lib()
+    out9 = np.zeros(9); acc = np.zeros(13); S = np.zeros(13)
+    T = _gicp_host(0, np.concatenate([guess.astype(np.float64).T.ravel(), x]), 16)          # applyState(base, x), col-major
+    for a, b in zip(si, ti):
+        vin = np.ascontiguousarray(np.concatenate([R.ravel(), cs[a].ravel(), ct[b].ravel()]))
+        assert lib.sm_debug_gicp_point(0, vin.ctypes.data, out9.ctypes.data) == 0
+        assert np.all(np.abs(out9.reshape(3, 3) - M[a]) <= 1e-9 * np.abs(M[a]).max())
+        vin = np.ascontiguousarray(np.concatenate([T, guess.astype(np.float64).T.ravel(), s[a].astype(np.float64),
+                                                   t[b].astype(np.float64), out9]))
+        assert lib.sm_debug_gicp_point(1, vin.ctypes.data, acc.ctypes.data) == 0
+        S += acc
+    m = si.size
+    f = S[0] / m
+    g = np.zeros(6); g[:3] = S[1:4] * (2.0 / m)
+    g[3:] = _gicp_host(1, np.concatenate([x, S[4:] * (2.0 / m)]), 3)
+    o = O.gicp_cost(s, t, guess, tr, x)
+    assert np.array_equal(o["si"], si)
+    assert abs(f - o["f"]) <= 1e-9 * abs(o["f"]) and np.all(np.abs(g - o["g"]) <= 1e-8 * np.abs(o["g"]).max())
