@@ -76,6 +76,7 @@ SIGNATURES = {
     "sm_debug_ndt_newton": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_float, C.c_double, C.c_double, C.c_double, C.c_int32,
                                       _VP, _VP, _VP, _VP]),
     "sm_debug_normals_leaf": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "sm_debug_voxel_index": (C.c_int, [C.c_int32, _VP, C.c_float, C.c_int32, _VP]),
     "sm_debug_gicp_point": (C.c_int, [C.c_int32, _VP, _VP]),
     "sm_debug_gicp_outer": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "sm_debug_gicp_host": (C.c_int, [C.c_int32, _VP, _VP]),

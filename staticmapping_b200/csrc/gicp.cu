@@ -27,7 +27,7 @@ namespace {
 // ---- ApproximateVoxelGrid -------------------------------------------------------------------
 constexpr int kHist = 512;
 
-__device__ __forceinline__ void approx_cell(const float* p, float inv, int* ix, int* iy, int* iz, uint32_t* slot) {
+__host__ __device__ __forceinline__ void approx_cell(const float* p, float inv, int* ix, int* iy, int* iz, uint32_t* slot) {
   *ix = (int)floorf(p[0] * inv); *iy = (int)floorf(p[1] * inv); *iz = (int)floorf(p[2] * inv);
   *slot = (uint32_t)((*ix * 7171 + *iy * 3079 + *iz * 4231) & (kHist - 1));
 }
@@ -375,6 +375,11 @@ gicp_cost_kernel(const float* __restrict__ src, int ns, const float* __restrict_
 }
 
 }  // namespace
+
+// host build of ApproximateVoxelGrid's cell and hash slot of one point (test hook sm_debug_voxel_index op 2)
+void gicp_debug_approx_cell_host(const float* p, float inv, int* ixyz, uint32_t* slot) {
+  approx_cell(p, inv, &ixyz[0], &ixyz[1], &ixyz[2], slot);
+}
 
 // host builds of the per-point GICP arithmetic (test hook sm_debug_gicp_point)
 void gicp_debug_mahalanobis_host(const double* R, const double* C1, const double* C2, double* out9) {

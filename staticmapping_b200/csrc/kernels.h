@@ -222,6 +222,10 @@ struct GicpCostParams {     // one BFGS function evaluation (:255-377)
   float T[16];              // base with applyState(x)
   float base[16];
 };
+// host builds of the three voxel-index functions (test hook sm_debug_voxel_index)
+bool vf_debug_index_host(const float* p, float voxel, long long* ixyz);
+int ndt_debug_voxel_coord_host(float v, float inv_leaf, int min_b);
+void gicp_debug_approx_cell_host(const float* p, float inv, int* ixyz, uint32_t* slot);
 // host builds of gicp.cu's per-point arithmetic (test hook sm_debug_gicp_point)
 void gicp_debug_mahalanobis_host(const double* R, const double* C1, const double* C2, double* out9);
 void gicp_debug_cost_terms_host(const float* T, const float* base, const float* ps, const float* pt, const double* M,

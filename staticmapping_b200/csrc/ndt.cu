@@ -30,7 +30,7 @@ namespace {
 constexpr int kNdtThreads = 128;
 constexpr int kNdtSums = 44;   // score, 6 gradient, 36 hessian, neighbour count
 
-__device__ __forceinline__ int voxel_coord(float v, float inv_leaf, int min_b) {
+__host__ __device__ __forceinline__ int voxel_coord(float v, float inv_leaf, int min_b) {
   return (int)(floorf(v * inv_leaf) - (float)min_b);
 }
 
@@ -579,6 +579,9 @@ ndt_fitness_kernel(const float* __restrict__ src, int n, NdtEvalParams P, const 
 }
 
 }  // namespace
+
+// host build of the per-axis voxel coordinate of the NDT grid (test hook sm_debug_voxel_index op 1)
+int ndt_debug_voxel_coord_host(float v, float inv_leaf, int min_b) { return voxel_coord(v, inv_leaf, min_b); }
 
 // Host build of one leaf of the target grid (test hook sm_debug_ndt_leaf): the running sums are formed here in input
 // order (the kernel forms them with one warp per voxel, in the same order), the rest is finish_leaf.

@@ -1296,6 +1296,30 @@ int sm_debug_normals_leaf(const double* members_3k, int32_t count, double* mean3
   return SM_OK;
 }
 
+// test hook: the voxel index of a point as the three voxelisations compute it, compiled for the host
+int sm_debug_voxel_index(int32_t op, const float* p3, float param, int32_t min_b, int64_t* out4) {
+  if (!p3 || !out4) return SM_ERR_BAD_ARGUMENT;
+  switch (op) {
+    case 0: {   // submap filter (filter_voxel_grid.cc:50-52): lround(x / voxel); out[3] = 0 when the point is dropped
+      long long ix[3] = {0, 0, 0};
+      const bool ok = vf_debug_index_host(p3, param, ix);
+      out4[0] = ix[0]; out4[1] = ix[1]; out4[2] = ix[2]; out4[3] = ok ? 1 : 0;
+      return SM_OK;
+    }
+    case 1:     // NDT grid (voxel_grid_covariance_omp_impl.hpp:218-220): int(floor(x * inv) - float(min_b)), per axis
+      for (int d = 0; d < 3; ++d) out4[d] = ndt_debug_voxel_coord_host(p3[d], param, min_b);
+      out4[3] = 1;
+      return SM_OK;
+    case 2: {   // ApproximateVoxelGrid: floor(x * inv) per axis and the 512-slot hash
+      int ix[3]; uint32_t slot = 0;
+      gicp_debug_approx_cell_host(p3, param, ix, &slot);
+      out4[0] = ix[0]; out4[1] = ix[1]; out4[2] = ix[2]; out4[3] = (int64_t)slot;
+      return SM_OK;
+    }
+    default: return SM_ERR_BAD_ARGUMENT;
+  }
+}
+
 // test hook: the per-point arithmetic of the GICP kernels (gicp.cu mahalanobis / cost_terms) compiled for the host
 int sm_debug_gicp_point(int32_t op, const double* in, double* out) {
   if (!in || !out) return SM_ERR_BAD_ARGUMENT;

@@ -27,7 +27,7 @@ constexpr int kT = 256, kItems = 8, kTile = kT * kItems;
 
 // meta[0..2]: per-axis minimum voxel index over the finite points; meta[3]: dropped (non-finite) points;
 // meta[4]: 1 if an axis spans 2^21 voxels or more
-__device__ __forceinline__ bool vf_index(const float* p, float voxel, long long* ix, long long* iy, long long* iz) {
+__host__ __device__ __forceinline__ bool vf_index(const float* p, float voxel, long long* ix, long long* iy, long long* iz) {
   const float qx = p[0] / voxel, qy = p[1] / voxel, qz = p[2] / voxel;
   // std::lround of a NaN / inf quotient is unspecified in the reference: such points are dropped here
   if (!(fabsf(qx) < 9.0e18f && fabsf(qy) < 9.0e18f && fabsf(qz) < 9.0e18f)) return false;
@@ -154,6 +154,9 @@ vf_mean_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ v
 }
 
 }  // namespace
+
+// host build of the voxel index of one point (test hook sm_debug_voxel_index op 0)
+bool vf_debug_index_host(const float* p, float voxel, long long* ixyz) { return vf_index(p, voxel, &ixyz[0], &ixyz[1], &ixyz[2]); }
 }  // namespace smb
 
 using namespace smb;

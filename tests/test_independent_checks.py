@@ -676,3 +676,42 @@ def test_gicp_per_point_arithmetic_of_the_product_against_numpy():
     o = O.gicp_cost(s, t, guess, tr, x)
     assert np.array_equal(o["si"], si)
     assert abs(f - o["f"]) <= 1e-9 * abs(o["f"]) and np.all(np.abs(g - o["g"]) <= 1e-8 * np.abs(o["g"]).max())
+
+
+# ---------------------------------------------------------------------------------- voxel indices (no GPU)
+def _voxel_index(op, p, param, min_b=0):
+    lib = _lib.lib()
+    pp = np.ascontiguousarray(p, dtype=np.float32)
+    out = np.zeros(4, dtype=np.int64)
+    assert lib.sm_debug_voxel_index(op, pp.ctypes.data, float(param), int(min_b), out.ctypes.data) == 0
+    return out
+
+
+def test_voxel_indices_of_the_three_voxelisations_of_the_product():
+    rng = np.random.default_rng(6)
+    pts = np.concatenate([rng.normal(size=(400, 3)) * 30.0,
+                          np.array([[0.05, -0.05, 0.15], [0.25, -0.25, 0.35], [-0.0, 0.0, 1e-30], [1e5, -1e5, 0.1]])]).astype(np.float32)
+    for p in pts:
+        # submap filter: std::lround(p / voxel) in float, halves away from zero (filter_voxel_grid.cc:50-52)
+        for voxel in (0.1, 0.2, 0.4):
+            q = p / np.float32(voxel)
+            want = np.where(q >= 0, np.floor(q.astype(np.float64) + 0.5), np.ceil(q.astype(np.float64) - 0.5)).astype(np.int64)
+            got = _voxel_index(0, p, voxel)
+            assert got[3] == 1 and np.array_equal(got[:3], want)
+        # NDT grid: int(floor(x * inv) - float(min_b))
+        for min_b in (-40, 0, 7):
+            want = (np.floor(p * np.float32(1.0)) - np.float32(min_b)).astype(np.int64)
+            assert np.array_equal(_voxel_index(1, p, 1.0, min_b)[:3], want)
+        # ApproximateVoxelGrid: floor(x * inv) and the 512-slot hash
+        inv = np.float32(1.0) / np.float32(0.2)
+        cell = np.floor(p * inv).astype(np.int64)
+        got = _voxel_index(2, p, inv)
+        assert np.array_equal(got[:3], cell) and got[3] == ((cell[0] * 7171 + cell[1] * 3079 + cell[2] * 4231) & 511)
+    # the reference's unit-test lattice (test_filter_voxel_grid.cc:52-100): 10 x 10 points 0.1 apart -> 100 / 36 / 9 voxels
+    import scenes
+    cloud = scenes.reference_voxel_test_cloud()
+    for voxel, count in ((0.1, 100), (0.2, 36), (0.4, 9)):
+        keys = {tuple(_voxel_index(0, p[:3], voxel)[:3]) for p in cloud}
+        assert len(keys) == count
+    # non-finite coordinates are dropped
+    assert _voxel_index(0, [np.nan, 0.0, 0.0], 0.1)[3] == 0 and _voxel_index(0, [0.0, np.inf, 0.0], 0.1)[3] == 0
